@@ -1,0 +1,115 @@
+"""ctypes binding of libdsnt_b200.so (C ABI declared in include/dsnt_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing the import fails loudly, and
+every operator refuses non-CUDA tensors (north_star: "no CPU fallback, no multi-backend dispatch").
+"""
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdsnt_b200.so')
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+REG_IDS = {'none': 0, 'var': 1, 'kl': 2, 'js': 3, 'mse': 4}
+STATS_K = 8
+FLAG_STRICT_NAN = 1
+FLAG_NO_EUCLID = 2
+
+_c_long, _c_int, _c_float, _c_ptr = ctypes.c_long, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/dsnt_b200.h one to one
+SIGNATURES = {
+    'dsnt_b200_version': (_c_int, []),
+    'dsnt_b200_last_error': (ctypes.c_char_p, []),
+    'dsnt_head_fwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_int, _c_float,
+                               _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]),
+    'dsnt_head_bwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
+                               _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int,
+                               _c_ptr, _c_int, _c_ptr]),
+    'dsnt_finish_workspace_bytes': (_c_int, []),
+    'dsnt_finish_loss': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_float, _c_ptr, _c_ptr, _c_ptr]),
+    'dsnt_combine_loss': (_c_int, [_c_ptr, _c_float, _c_ptr]),
+    'dsnt_euclid_fwd': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_ptr, _c_ptr]),
+    'dsnt_euclid_bwd': (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_long, _c_int, _c_int, _c_ptr,
+                                 _c_ptr]),
+    'dsnt_tsoftmax_fwd': (_c_int, [_c_ptr, _c_int, _c_long, _c_long, _c_float, _c_float, _c_ptr, _c_ptr]),
+    'dsnt_tsoftmax_bwd': (_c_int, [_c_ptr, _c_ptr, _c_int, _c_long, _c_long, _c_ptr, _c_ptr]),
+    'dsnt_make_gauss_fwd': (_c_int, [_c_ptr, _c_long, _c_int, _c_int, _c_float, _c_ptr, _c_ptr]),
+    'dsnt_make_gauss_bwd': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_int, _c_float, _c_ptr, _c_ptr]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'dsnt_pose2d_b200: %s is missing. Build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            'or `make -C dsnt_pose2d_b200/csrc`. There is no CPU / PyTorch fallback for this path.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+LIB = _load()
+launch_count = 0          # kernels enqueued through this binding (bench.py reports it as gpu_launches)
+
+
+def version():
+    return LIB.dsnt_b200_version()
+
+
+def last_error():
+    return LIB.dsnt_b200_last_error().decode('utf-8', 'replace')
+
+
+def call(name, *args, launches=1):
+    """Invoke an entry point; a non-zero return raises RuntimeError with the library's message."""
+    global launch_count
+    rc = getattr(LIB, name)(*args)
+    if rc != 0:
+        raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))
+    launch_count += launches
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def dtype_id(t):
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise NotImplementedError(
+        'dsnt_pose2d_b200 supports float32 and bfloat16 heatmaps only (got %s); float16 already yields NaN in '
+        'the reference because 1e-24 underflows, float64 has no kernel' % (t.dtype,))
+
+
+def require_cuda(t, what):
+    if not torch.is_tensor(t):
+        raise TypeError('%s must be a tensor' % what)
+    if not t.is_cuda:
+        raise NotImplementedError('%s must be a CUDA tensor: dsnt_pose2d_b200 has no CPU fallback' % what)
+
+
+_workspaces = {}
+
+
+def finish_workspace(device):
+    """Per-(device, stream) zero-initialised scratch for dsnt_finish_loss (the kernel re-zeroes its ticket)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(LIB.dsnt_finish_workspace_bytes() // 4, dtype=torch.float32, device=device)
+        _workspaces[key] = ws
+    return ws

@@ -1,0 +1,191 @@
+// capi.cu -- the extern "C" surface of libdsnt_b200.so (see include/dsnt_b200.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "aux_kernels.cuh"
+#include "launch.cuh"
+
+namespace dsnt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return DSNT_ERR_LAUNCH;
+  }
+  return DSNT_OK;
+}
+
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// Widest vector the layout allows: a vector must not straddle a row (W % VEC == 0) and every heatmap
+// base must be VEC*sizeof aligned (then H*W*sizeof is a multiple of it as well).
+static int pick_vec(int dtype, int W, const void* a, const void* b) {
+  if (dtype == DSNT_DTYPE_F32) {
+    if (W % 4 == 0 && aligned(a, 16) && (!b || aligned(b, 16))) return 4;
+    return 1;
+  }
+  if (W % 8 == 0 && aligned(a, 16) && (!b || aligned(b, 16))) return 8;
+  if (W % 4 == 0 && aligned(a, 8) && (!b || aligned(b, 8))) return 4;
+  return 1;
+}
+
+static int check_common(const void* z, int dtype, long n, int H, int W, int reg) {
+  if (!z) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
+  if (dtype != DSNT_DTYPE_F32 && dtype != DSNT_DTYPE_BF16) { set_error("unsupported dtype %d (fp32 and bf16 only)", dtype); return DSNT_ERR_UNSUPPORTED; }
+  if (n < 0 || H <= 0 || W <= 0) { set_error("bad shape n=%ld H=%d W=%d", n, H, W); return DSNT_ERR_BAD_ARG; }
+  if (static_cast<long>(H) * W > (1L << 28)) { set_error("heatmap %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
+  if (n > 0x7fffffffL) { set_error("too many heatmaps: %ld", n); return DSNT_ERR_UNSUPPORTED; }
+  if (reg < DSNT_REG_NONE || reg > DSNT_REG_MSE) { set_error("bad reg %d", reg); return DSNT_ERR_BAD_ARG; }
+  return DSNT_OK;
+}
+
+}  // namespace dsnt
+
+using namespace dsnt;
+
+extern "C" {
+
+DSNT_API int dsnt_b200_version(void) { return DSNT_B200_VERSION; }
+
+DSNT_API const char* dsnt_b200_last_error(void) { return g_err; }
+
+DSNT_API int dsnt_head_fwd(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* target, int reg,
+                  float sigma, float* coords, float* stats, float* terms, int variant, void* stream) {
+  int rc = check_common(z, dtype, n, H, W, reg);
+  if (rc) return rc;
+  if (!coords) { set_error("coords output is required"); return DSNT_ERR_BAD_ARG; }
+  if (reg_needs_gauss(reg) && !target) { set_error("reg %d needs a target", reg); return DSNT_ERR_BAD_ARG; }
+  if (reg != DSNT_REG_NONE && !(sigma > 0.f)) { set_error("sigma must be > 0"); return DSNT_ERR_BAD_ARG; }
+  if (!aligned(coords, 8) || (stats && !aligned(stats, 16)) || (terms && !aligned(terms, 8)) || (target && !aligned(target, 8))) {
+    set_error("per-heatmap buffers must be naturally aligned (coords/terms/target 8 B, stats 16 B)");
+    return DSNT_ERR_BAD_ARG;
+  }
+  if (n == 0) return DSNT_OK;
+  HeadFwdParams p;
+  p.z = z; p.target = target; p.coords = coords; p.stats = stats; p.terms = terms;
+  p.n = n; p.H = H; p.W = W; p.reg = reg; p.sigma = sigma;
+  const int vec = pick_vec(dtype, W, z, nullptr);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dtype == DSNT_DTYPE_F32 ? launch_head_fwd_f32(p, vec, input_is_logits != 0, variant, s)
+                                 : launch_head_fwd_bf16(p, vec, input_is_logits != 0, variant, s);
+}
+
+DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* target,
+                  const float* mask, const float* stats, const float* g_coords, const float* g_reg,
+                  const float* g_loss, const float* denom, float reg_coeff, int reg, float sigma, int flags, void* dz,
+                  int variant, void* stream) {
+  int rc = check_common(dz, dtype, n, H, W, reg);
+  if (rc) return rc;
+  const bool need_z = input_is_logits || reg_needs_gauss(reg);
+  if (need_z && !z) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
+  if (!stats) { set_error("stats from the forward are required"); return DSNT_ERR_BAD_ARG; }
+  if (reg_needs_gauss(reg) && !target) { set_error("reg %d needs a target", reg); return DSNT_ERR_BAD_ARG; }
+  if ((g_loss == nullptr) != (denom == nullptr)) { set_error("g_loss and denom go together"); return DSNT_ERR_BAD_ARG; }
+  if (reg != DSNT_REG_NONE && !(sigma > 0.f)) { set_error("sigma must be > 0"); return DSNT_ERR_BAD_ARG; }
+  if (!aligned(stats, 16) || (target && !aligned(target, 8)) || (g_coords && !aligned(g_coords, 8))) {
+    set_error("per-heatmap buffers must be naturally aligned (target/g_coords 8 B, stats 16 B)");
+    return DSNT_ERR_BAD_ARG;
+  }
+  if (n == 0) return DSNT_OK;
+  HeadBwdParams p;
+  p.z = z; p.target = target; p.mask = mask; p.stats = stats; p.g_coords = g_coords; p.g_reg = g_reg;
+  p.g_loss = g_loss; p.denom = denom; p.dz = dz; p.n = n; p.H = H; p.W = W; p.reg = reg; p.flags = flags;
+  p.sigma = sigma; p.reg_coeff = reg_coeff;
+  const int vec = pick_vec(dtype, W, dz, need_z ? z : nullptr);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dtype == DSNT_DTYPE_F32 ? launch_head_bwd_f32(p, vec, input_is_logits != 0, variant, s)
+                                 : launch_head_bwd_bf16(p, vec, input_is_logits != 0, variant, s);
+}
+
+DSNT_API int dsnt_finish_workspace_bytes(void) { return static_cast<int>(sizeof(float) * kFinishWorkspaceFloats); }
+
+DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, float reg_coeff, float* out, float* workspace,
+                     void* stream) {
+  if (!terms || !out || !workspace || n < 0) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (!aligned(terms, 8) || !aligned(workspace, 16)) { set_error("dsnt_finish_loss: misaligned buffers"); return DSNT_ERR_BAD_ARG; }
+  long ctas = (n + 1023) / 1024;  // >= 4 heatmaps per thread before adding CTAs
+  if (ctas < 1) ctas = 1;
+  if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
+  finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      terms, mask, n, reg_coeff, out, workspace);
+  return check_launch("finish_loss_kernel");
+}
+
+DSNT_API int dsnt_combine_loss(float* out, float reg_coeff, void* stream) {
+  if (!out) { set_error("dsnt_combine_loss: null"); return DSNT_ERR_BAD_ARG; }
+  combine_loss_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out, reg_coeff);
+  return check_launch("combine_loss_kernel");
+}
+
+DSNT_API int dsnt_euclid_fwd(const float* actual, const float* target, long n, int d, float* terms, void* stream) {
+  if (!actual || !target || !terms || n < 0 || d <= 0 || !aligned(terms, 8)) { set_error("dsnt_euclid_fwd: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (n == 0) return DSNT_OK;
+  euclid_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(actual, target, n, d, terms);
+  return check_launch("euclid_fwd_kernel");
+}
+
+DSNT_API int dsnt_euclid_bwd(const float* actual, const float* target, const float* terms, const float* mask,
+                             const float* g_loss, const float* denom, long n, int d, int flags, float* g_actual,
+                             void* stream) {
+  if (!actual || !target || !terms || !g_loss || !denom || !g_actual || n < 0 || d <= 0) { set_error("dsnt_euclid_bwd: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (n == 0) return DSNT_OK;
+  euclid_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      actual, target, terms, mask, g_loss, denom, n, d, flags, g_actual);
+  return check_launch("euclid_bwd_kernel");
+}
+
+DSNT_API int dsnt_tsoftmax_fwd(const void* x, int dtype, long rows, long len, float threshold, float eps, void* out,
+                      void* stream) {
+  if (!x || !out || rows < 0 || len <= 0 || rows > 0x7fffffffL) { set_error("dsnt_tsoftmax_fwd: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (rows == 0) return DSNT_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == DSNT_DTYPE_F32)
+    tsoftmax_fwd_kernel<float><<<static_cast<unsigned>(rows), kRowBlock, 0, s>>>(static_cast<const float*>(x), len, threshold, eps, static_cast<float*>(out));
+  else if (dtype == DSNT_DTYPE_BF16)
+    tsoftmax_fwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), kRowBlock, 0, s>>>(static_cast<const __nv_bfloat16*>(x), len, threshold, eps, static_cast<__nv_bfloat16*>(out));
+  else { set_error("unsupported dtype %d", dtype); return DSNT_ERR_UNSUPPORTED; }
+  return check_launch("tsoftmax_fwd_kernel");
+}
+
+DSNT_API int dsnt_tsoftmax_bwd(const void* out, const void* g, int dtype, long rows, long len, void* dx, void* stream) {
+  if (!out || !g || !dx || rows < 0 || len <= 0 || rows > 0x7fffffffL) { set_error("dsnt_tsoftmax_bwd: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (rows == 0) return DSNT_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == DSNT_DTYPE_F32)
+    tsoftmax_bwd_kernel<float><<<static_cast<unsigned>(rows), kRowBlock, 0, s>>>(static_cast<const float*>(out), static_cast<const float*>(g), len, static_cast<float*>(dx));
+  else if (dtype == DSNT_DTYPE_BF16)
+    tsoftmax_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), kRowBlock, 0, s>>>(static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(g), len, static_cast<__nv_bfloat16*>(dx));
+  else { set_error("unsupported dtype %d", dtype); return DSNT_ERR_UNSUPPORTED; }
+  return check_launch("tsoftmax_bwd_kernel");
+}
+
+DSNT_API int dsnt_make_gauss_fwd(const float* mu, long n, int W, int H, float sigma, float* out, void* stream) {
+  if (!mu || !out || n < 0 || W <= 0 || H <= 0 || !(sigma > 0.f) || n > 0x7fffffffL) { set_error("dsnt_make_gauss_fwd: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (n == 0) return DSNT_OK;
+  const size_t smem = sizeof(float) * table_floats(H, W);
+  if (smem > kMaxDynSmem) { set_error("gaussian %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
+  make_gauss_fwd_kernel<<<static_cast<unsigned>(n), kGaussBlock, smem, static_cast<cudaStream_t>(stream)>>>(mu, W, H, sigma, out);
+  return check_launch("make_gauss_fwd_kernel");
+}
+
+DSNT_API int dsnt_make_gauss_bwd(const float* mu, const float* g, long n, int W, int H, float sigma, float* dmu, void* stream) {
+  if (!mu || !g || !dmu || n < 0 || W <= 0 || H <= 0 || !(sigma > 0.f) || n > 0x7fffffffL) { set_error("dsnt_make_gauss_bwd: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (n == 0) return DSNT_OK;
+  const size_t smem = sizeof(float) * table_floats(H, W);
+  if (smem > kMaxDynSmem) { set_error("gaussian %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
+  make_gauss_bwd_kernel<<<static_cast<unsigned>(n), kGaussBlock, smem, static_cast<cudaStream_t>(stream)>>>(mu, g, W, H, sigma, dmu);
+  return check_launch("make_gauss_bwd_kernel");
+}
+
+}  // extern "C"

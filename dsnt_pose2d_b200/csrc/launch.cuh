@@ -1,0 +1,116 @@
+// launch.cuh -- host-side kernel selection for the fused head (shared by the per-dtype translation units).
+#pragma once
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "head_bwd.cuh"
+#include "head_fwd.cuh"
+
+namespace dsnt {
+
+void set_error(const char* fmt, ...);  // capi.cu
+int check_launch(const char* what);    // capi.cu: cudaGetLastError -> DSNT_ERR_LAUNCH
+
+// per-dtype entry points (one translation unit each so they compile in parallel)
+int launch_head_fwd_f32(const HeadFwdParams& p, int vec, bool logits, int variant, cudaStream_t stream);
+int launch_head_fwd_bf16(const HeadFwdParams& p, int vec, bool logits, int variant, cudaStream_t stream);
+int launch_head_bwd_f32(const HeadBwdParams& p, int vec, bool logits, int variant, cudaStream_t stream);
+int launch_head_bwd_bf16(const HeadBwdParams& p, int vec, bool logits, int variant, cudaStream_t stream);
+
+constexpr size_t kMaxDynSmem = 48 * 1024;  // stay under the no-opt-in limit: tables are (W+H+8) floats
+
+// ------------------------------------------------------------------------------------------------ forward
+template <typename T, int VEC, int GROUP, int NV, int REG, bool LOGITS>
+int launch_fwd_resident(const HeadFwdParams& p, cudaStream_t stream) {
+  constexpr int BLOCK = fwd_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  const bool gauss = REG >= 0 ? reg_needs_gauss(REG) : reg_needs_gauss(p.reg);
+  const size_t smem = gauss ? sizeof(float) * GPB * table_floats(p.H, p.W) : 0;
+  if (smem > kMaxDynSmem) { set_error("heatmap %dx%d: Gaussian tables exceed shared memory", p.H, p.W); return DSNT_ERR_UNSUPPORTED; }
+  const long grid = (p.n + GPB - 1) / GPB;
+  head_fwd_kernel<T, VEC, GROUP, NV, REG, LOGITS><<<static_cast<unsigned>(grid), BLOCK, smem, stream>>>(p);
+  return check_launch("head_fwd_kernel");
+}
+
+template <typename T, int VEC, int REG, bool LOGITS>
+int launch_fwd_large(const HeadFwdParams& p, cudaStream_t stream) {
+  const bool gauss = REG >= 0 ? reg_needs_gauss(REG) : reg_needs_gauss(p.reg);
+  const size_t smem = gauss ? sizeof(float) * table_floats(p.H, p.W) : 0;
+  if (smem > kMaxDynSmem) { set_error("heatmap %dx%d: Gaussian tables exceed shared memory", p.H, p.W); return DSNT_ERR_UNSUPPORTED; }
+  head_fwd_large_kernel<T, VEC, REG, LOGITS><<<static_cast<unsigned>(p.n), kLargeBlock, smem, stream>>>(p);
+  return check_launch("head_fwd_large_kernel");
+}
+
+// variant: 0 auto; 1 force the streaming two-pass kernel (for tests / comparison)
+template <typename T, int VEC, int REG, bool LOGITS>
+int launch_fwd_shape(const HeadFwdParams& p, int variant, cudaStream_t stream) {
+  const long nvec = static_cast<long>(p.H) * p.W / VEC;
+  if (variant == 1) return launch_fwd_large<T, VEC, REG, LOGITS>(p, stream);
+  if (nvec <= 32 * 2) return launch_fwd_resident<T, VEC, 32, 2, REG, LOGITS>(p, stream);
+  if (nvec <= 32 * 8) return launch_fwd_resident<T, VEC, 32, 8, REG, LOGITS>(p, stream);
+  if (nvec <= 256 * 4) return launch_fwd_resident<T, VEC, 256, 4, REG, LOGITS>(p, stream);
+  if (nvec <= 512 * 8) return launch_fwd_resident<T, VEC, 512, 8, REG, LOGITS>(p, stream);
+  return launch_fwd_large<T, VEC, REG, LOGITS>(p, stream);
+}
+
+template <typename T, int VEC, bool LOGITS>
+int launch_fwd_reg(const HeadFwdParams& p, int variant, cudaStream_t stream) {
+  if constexpr (VEC == 1) {
+    return launch_fwd_shape<T, VEC, -1, LOGITS>(p, variant, stream);  // odd sizes: regulariser chosen at run time
+  } else {
+    switch (p.reg) {
+      case DSNT_REG_NONE: return launch_fwd_shape<T, VEC, DSNT_REG_NONE, LOGITS>(p, variant, stream);
+      case DSNT_REG_VAR: return launch_fwd_shape<T, VEC, DSNT_REG_VAR, LOGITS>(p, variant, stream);
+      case DSNT_REG_KL: return launch_fwd_shape<T, VEC, DSNT_REG_KL, LOGITS>(p, variant, stream);
+      case DSNT_REG_JS: return launch_fwd_shape<T, VEC, DSNT_REG_JS, LOGITS>(p, variant, stream);
+      case DSNT_REG_MSE: return launch_fwd_shape<T, VEC, DSNT_REG_MSE, LOGITS>(p, variant, stream);
+    }
+    set_error("bad reg %d", p.reg);
+    return DSNT_ERR_BAD_ARG;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+template <typename T, int VEC, int GROUP, int NV, int REG, bool LOGITS>
+int launch_bwd_one(const HeadBwdParams& p, cudaStream_t stream) {
+  constexpr int BLOCK = fwd_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  const bool gauss = REG >= 0 ? reg_needs_gauss(REG) : reg_needs_gauss(p.reg);
+  const size_t smem = gauss ? sizeof(float) * GPB * table_floats(p.H, p.W) : 0;
+  if (smem > kMaxDynSmem) { set_error("heatmap %dx%d: Gaussian tables exceed shared memory", p.H, p.W); return DSNT_ERR_UNSUPPORTED; }
+  const long nvec = static_cast<long>(p.H) * p.W / VEC;
+  const long chunks = (nvec + GROUP * NV - 1) / (GROUP * NV);
+  if (chunks > 65535) { set_error("heatmap %dx%d too large", p.H, p.W); return DSNT_ERR_UNSUPPORTED; }
+  dim3 grid(static_cast<unsigned>((p.n + GPB - 1) / GPB), static_cast<unsigned>(chunks));
+  head_bwd_kernel<T, VEC, GROUP, NV, REG, LOGITS><<<grid, BLOCK, smem, stream>>>(p);
+  return check_launch("head_bwd_kernel");
+}
+
+template <typename T, int VEC, int REG, bool LOGITS>
+int launch_bwd_shape(const HeadBwdParams& p, int variant, cudaStream_t stream) {
+  (void)variant;
+  const long nvec = static_cast<long>(p.H) * p.W / VEC;
+  if (nvec <= 32 * 2) return launch_bwd_one<T, VEC, 32, 2, REG, LOGITS>(p, stream);
+  if (nvec <= 32 * 8) return launch_bwd_one<T, VEC, 32, 8, REG, LOGITS>(p, stream);
+  return launch_bwd_one<T, VEC, 256, 4, REG, LOGITS>(p, stream);  // chunked over blockIdx.y beyond 1024 vectors
+}
+
+template <typename T, int VEC, bool LOGITS>
+int launch_bwd_reg(const HeadBwdParams& p, int variant, cudaStream_t stream) {
+  if constexpr (VEC == 1) {
+    return launch_bwd_shape<T, VEC, -1, LOGITS>(p, variant, stream);
+  } else {
+    switch (p.reg) {
+      case DSNT_REG_NONE: return launch_bwd_shape<T, VEC, DSNT_REG_NONE, LOGITS>(p, variant, stream);
+      case DSNT_REG_VAR: return launch_bwd_shape<T, VEC, DSNT_REG_VAR, LOGITS>(p, variant, stream);
+      case DSNT_REG_KL: return launch_bwd_shape<T, VEC, DSNT_REG_KL, LOGITS>(p, variant, stream);
+      case DSNT_REG_JS: return launch_bwd_shape<T, VEC, DSNT_REG_JS, LOGITS>(p, variant, stream);
+      case DSNT_REG_MSE: return launch_bwd_shape<T, VEC, DSNT_REG_MSE, LOGITS>(p, variant, stream);
+    }
+    set_error("bad reg %d", p.reg);
+    return DSNT_ERR_BAD_ARG;
+  }
+}
+
+}  // namespace dsnt

@@ -1,0 +1,156 @@
+"""The fused DSNT head: logits Z -> (coords, loss) with ONE forward kernel, one tiny finishing
+reduction and ONE streaming backward kernel (12 bytes/pixel for fp32 instead of the reference's ~400).
+
+This op is not in the reference; it is what `forward_part2` + `forward_loss` of
+`HumanPoseModel` compute together (src/dsnt/model.py:24-63,138-145,176-183):
+
+    P      = softmax over H*W of Z                      (model.py:28-30)
+    coords = dsnt(P)                                    (nn.py:66-78)
+    loss   = euclidean_loss(coords, target, mask)       (nn.py:97-116)
+             + reg_coeff * {var,kl,js,mse}_reg_loss(P, target, 2*hm_sigma/W, mask)   (model.py:47-63,145)
+
+P is never materialised; the autograd node saves Z and 8 floats per heatmap.
+
+Batch sharding: pass `group=` and every rank calls the op on its slice of the batch.
+The only coupling between heatmaps is the scalar normalisation of `masked_average`, so the op all-reduces
+three floats (sum mask*dist, sum mask*D, sum mask) and the result -- value and gradients -- equals the
+single-process op on the concatenated batch.
+"""
+
+import collections
+
+import torch
+
+from . import _lib
+
+HeadOutput = collections.namedtuple('HeadOutput', ['coords', 'loss', 'euclid', 'reg'])
+
+# Reproduce the reference's NaN gradient at coords == target (sqrt'(0)) instead of
+# the default zero gradient.  Test-only switch; real training never wants the NaN.
+STRICT_NAN = False
+
+
+def _flat_heatmaps(z):
+    if z.dim() < 2:
+        raise ValueError('heatmaps need at least 2 dimensions, got shape %s' % (tuple(z.shape),))
+    h, w = z.shape[-2], z.shape[-1]
+    n = z.numel() // (h * w) if h * w > 0 else 0
+    return z.contiguous(), n, h, w
+
+
+def _as_f32(t, n, last, what):
+    if t is None:
+        return None
+    _lib.require_cuda(t, what)
+    t = t.detach().to(torch.float32).contiguous()
+    expect = n * last
+    if t.numel() != expect:
+        raise ValueError('%s has %d elements, expected %d' % (what, t.numel(), expect))
+    return t
+
+
+def all_reduce_sums(out8, group):
+    """Sum the three partial sums out8[0:3] over the ranks of `group` (no-op for a single rank)."""
+    import torch.distributed as dist
+    if group is None or not dist.is_available() or not dist.is_initialized():
+        return
+    if dist.get_world_size(group) > 1:
+        dist.all_reduce(out8[0:3], op=dist.ReduceOp.SUM, group=group)
+
+
+class _FusedHead(torch.autograd.Function):
+    """forward: dsnt_head_fwd + dsnt_finish_loss;  backward: dsnt_head_bwd (include/dsnt_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, variant, input_is_logits, aux):
+        zc, n, h, w = _flat_heatmaps(z)
+        dev = zc.device
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zc)
+            coords = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            stats = torch.empty(n, _lib.STATS_K, dtype=torch.float32, device=dev)
+            terms = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            _lib.call('dsnt_head_fwd', zc.data_ptr(), _lib.dtype_id(zc), int(input_is_logits), n, h, w,
+                      _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(),
+                      variant, stream)
+            ws = _lib.finish_workspace(dev)
+            _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, reg_coeff, out8.data_ptr(),
+                      ws.data_ptr(), stream)
+            if group is not None:
+                all_reduce_sums(out8, group)
+                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+        ctx.save_for_backward(zc, target, mask, stats, out8)
+        ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, variant, input_is_logits, z.shape)
+        ctx.set_materialize_grads(False)
+        aux['out8'] = out8          # side channel: [sum m*d, sum m*D, count, denom, euclid, reg, loss, 0]
+        return coords.view(*z.shape[:-2], 2), out8[6]
+
+    @staticmethod
+    def backward(ctx, g_coords, g_loss):
+        zc, target, mask, stats, out8 = ctx.saved_tensors
+        n, h, w, reg_id, sigma, reg_coeff, flags, variant, input_is_logits, shape = ctx.meta
+        dev = zc.device
+        if g_coords is None and g_loss is None:
+            return (None,) * 11
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zc)
+            if g_coords is not None:
+                g_coords = g_coords.to(torch.float32).contiguous()
+            if g_loss is not None:
+                g_loss = g_loss.to(torch.float32).contiguous()
+            dz = torch.empty_like(zc)
+            _lib.call('dsnt_head_bwd', zc.data_ptr(), _lib.dtype_id(zc), int(input_is_logits), n, h, w,
+                      _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(), _lib.ptr(g_coords), None,
+                      _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
+                      reg_coeff, reg_id, sigma, flags, dz.data_ptr(), variant, stream)
+        return (dz.view(shape),) + (None,) * 10
+
+
+def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_sigma=None, group=None,
+              variant=0, input_is_logits=True):
+    """Fused head.
+
+    Args:
+        z: logits [..., H, W] (CUDA, float32 or bfloat16); any leading dims, usually [B, C, H, W].
+        target: [..., 2] target coordinates (x, y) in normalised [-1, 1] units.
+        mask: [...] joint visibility weights or None (src/dsnt/nn.py:81-94 semantics).
+        reg: 'none' | 'var' | 'kl' | 'js' | 'mse'  (src/dsnt/model.py:52-61).
+        sigma: target std-dev in normalised units; or give `hm_sigma` in pixels and the reference's
+            conversion sigma = 2*hm_sigma/W is applied (src/dsnt/model.py:49).
+        reg_coeff: weight of the regulariser (src/dsnt/model.py:145).
+        group: torch.distributed process group when the batch is sharded across ranks.
+    Returns:
+        HeadOutput(coords [..., 2] float32, loss 0-dim float32, euclid 0-dim, reg 0-dim);
+        `loss` and `coords` are differentiable w.r.t. `z`.
+    """
+    _lib.require_cuda(z, 'z')
+    if reg not in _lib.REG_IDS:
+        raise ValueError('unrecognised regulariser: %r' % (reg,))
+    h, w = z.shape[-2], z.shape[-1]
+    n = z.numel() // max(h * w, 1)
+    if sigma is None:
+        sigma = 2.0 * (1.0 if hm_sigma is None else hm_sigma) / w
+    if target is not None and target.requires_grad:
+        raise NotImplementedError('dsnt_head: gradients w.r.t. the target are not implemented')
+    target = _as_f32(target, n, 2, 'target')
+    mask = _as_f32(mask, n, 1, 'mask')
+    flags = _lib.FLAG_STRICT_NAN if STRICT_NAN else 0
+    aux = {}
+    coords, loss = _FusedHead.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
+                                    flags, group, int(variant), bool(input_is_logits), aux)
+    out8 = aux['out8']
+    return HeadOutput(coords, loss, out8[4], out8[5])
+
+
+def dsnt_head_stacked(zs, target, mask=None, **kwargs):
+    """Hourglass form (src/dsnt/model.py:233-246,286-292): one head per stack, losses summed.
+
+    Returns (list of coords per stack, total loss)."""
+    total = None
+    coords = []
+    for z in zs:
+        out = dsnt_head(z, target, mask, **kwargs)
+        coords.append(out.coords)
+        total = out.loss if total is None else total + out.loss
+    return coords, total

@@ -1,0 +1,151 @@
+/*
+ * dsnt_b200.h -- C ABI of libdsnt_b200.so, the sm_100a implementation of the DSNT head hot path.
+ *
+ * This is the drop-in boundary.  The reference (anibali/dsnt-pose2d) is pure
+ * Python: its "FFI" for this path is the set of tensor functions in src/dsnt/nn.py plus the two
+ * model shims in src/dsnt/model.py.  Each entry point below names the reference lines it replaces.
+ * The Python host side (dsnt_pose2d_b200/nn.py, head.py) binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer on the current device
+ *   - the library allocates nothing and keeps no state besides a thread-local error string
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no host sync,
+ *     so a sequence of calls is CUDA-graph capturable
+ *   - return value 0 = enqueued; negative = rejected (see dsnt_b200_last_error())
+ *   - heatmaps are N contiguous images of H rows x W columns (NCHW conv output viewed as [N=B*C,H,W]);
+ *     element (n,i,j) lives at base + (n*H*W + i*W + j)
+ *   - pixel-centre coordinates x_j = (2j+1)/W - 1, y_i = (2i+1)/H - 1   (src/dsnt/nn.py:30-37)
+ *   - all per-heatmap scalars (coords, stats, terms, targets, masks, gradients) are float32
+ */
+#ifndef DSNT_B200_H_
+#define DSNT_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSNT_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define DSNT_API __attribute__((visibility("default")))
+#else
+#define DSNT_API
+#endif
+
+/* element type of the heatmap tensors (math is always fp32) */
+#define DSNT_DTYPE_F32 0
+#define DSNT_DTYPE_BF16 1
+
+/* regulariser selector: src/dsnt/model.py:52-61 ('none'|'var'|'kl'|'js'|'mse') */
+#define DSNT_REG_NONE 0
+#define DSNT_REG_VAR 1
+#define DSNT_REG_KL 2
+#define DSNT_REG_JS 3
+#define DSNT_REG_MSE 4
+
+/* per-heatmap statistics saved by the forward for the reduction-free backward */
+#define DSNT_STATS_K 8
+/*   logits input : [0] m*log2(e)  [1] 1/S   [2] mu_x [3] mu_y [4] v_x [5] v_y [6] c_reg = sum P r [7] Gaussian normaliser 1/(sum G^ + 1e-24)
+ *   heatmap input: [0] sum P      [1] unused [2..7] as above                                                        */
+
+/* flags */
+#define DSNT_FLAG_STRICT_NAN 1 /* reproduce the reference's NaN gradient when coords == target (sqrt'(0)); default: 0-gradient */
+#define DSNT_FLAG_NO_EUCLID 2  /* dsnt_head_bwd: g_loss feeds the regulariser only (standalone *_reg_loss) */
+
+/* error codes */
+#define DSNT_OK 0
+#define DSNT_ERR_BAD_ARG (-1)
+#define DSNT_ERR_UNSUPPORTED (-2)
+#define DSNT_ERR_LAUNCH (-3)
+
+DSNT_API int dsnt_b200_version(void);
+DSNT_API const char* dsnt_b200_last_error(void);
+
+/*
+ * Fused forward of the head for N heatmaps.
+ *   replaces: F.softmax over H*W (src/dsnt/model.py:24-30,44-45) when input_is_logits != 0,
+ *             dsnt / generate_xy / expectation_2d (src/dsnt/nn.py:25-78),
+ *             the per-heatmap part of euclidean_loss (src/dsnt/nn.py:112-114),
+ *             make_gauss + _kl_2d/_js_2d/MSE/variance terms (src/dsnt/nn.py:168-216,232-233,250-251,268-270,288-296).
+ *   z         [N,H,W] logits, or normalised/un-normalised heatmaps P when input_is_logits == 0
+ *   target    [N,2] (x,y) in normalised units, or NULL (then dist = 0 and reg must be NONE or VAR)
+ *   sigma     target std-dev in NORMALISED units (= 2*hm_sigma/W, src/dsnt/model.py:49)
+ *   coords    [N,2] out: (E[x], E[y])
+ *   stats     [N,DSNT_STATS_K] out, or NULL when no backward will follow
+ *   terms     [N,2] out: (Euclidean distance to target, regulariser value D), or NULL
+ *   variant   0 = automatic kernel choice; >0 forces an implementation variant (benchmarks/tests)
+ */
+DSNT_API int dsnt_head_fwd(const void* z, int dtype, int input_is_logits, long n, int H, int W,
+                  const float* target, int reg, float sigma,
+                  float* coords, float* stats, float* terms, int variant, void* stream);
+
+/*
+ * Fused, reduction-free backward: recomputes softmax from the saved statistics and writes
+ * dL/dz directly.   replaces: the autograd replay of everything above (src/dsnt/nn.py:25-298 backward).
+ *
+ * Per heatmap n the upstream gradients are assembled on the device from up to three sources
+ *   a_n   = g_coords[n,0] + g_loss * w_n * (mu_x - t_x)/d_n       (second term iff g_loss != NULL)
+ *   b_n   = g_coords[n,1] + g_loss * w_n * (mu_y - t_y)/d_n
+ *   rho_n = g_reg[n]      + g_loss * w_n * reg_coeff
+ *   w_n   = (mask ? mask[n] : 1) / denom[0]                       (masked_average, src/dsnt/nn.py:81-94)
+ * and dz = P (a x + b y + rho r - c) for logits, dz = a x + b y + rho r for heatmap input.
+ *   g_coords [N,2] or NULL; g_reg [N] or NULL; g_loss, denom: device scalars or NULL (both or neither)
+ *   dz        [N,H,W] out, same dtype as z
+ */
+DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n, int H, int W,
+                  const float* target, const float* mask, const float* stats,
+                  const float* g_coords, const float* g_reg, const float* g_loss, const float* denom,
+                  float reg_coeff, int reg, float sigma, int flags,
+                  void* dz, int variant, void* stream);
+
+/*
+ * Deterministic finishing reduction over the per-heatmap terms (no float atomics, one launch).
+ *   replaces: masked_average (src/dsnt/nn.py:81-94) and loss = euclid + reg_coeff*reg (src/dsnt/model.py:145).
+ *   terms [N,2] from dsnt_head_fwd; mask [N] or NULL (then every weight is 1 and count = N)
+ *   out[0] = sum mask*dist   out[1] = sum mask*D   out[2] = sum mask (count)
+ *   out[3] = max(count,1)    out[4] = out[0]/out[3]   out[5] = out[1]/out[3]
+ *   out[6] = out[4] + reg_coeff*out[5] (the loss)     out[7] = 0
+ *   workspace: dsnt_finish_workspace_bytes() bytes of device scratch, 16-byte aligned, ZEROED ONCE by the
+ *   caller before first use; the kernel leaves it ready for the next call (stream-ordered reuse only).
+ */
+DSNT_API int dsnt_finish_workspace_bytes(void);
+DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, float reg_coeff, float* out,
+                     float* workspace, void* stream);
+
+/* Recompute out[3..6] from (possibly all-reduced) out[0..2]; used after the NCCL all-reduce of the sums. */
+DSNT_API int dsnt_combine_loss(float* out, float reg_coeff, void* stream);
+
+/*
+ * Per-point Euclidean distance for the standalone euclidean_loss (src/dsnt/nn.py:97-116):
+ *   terms[n] = (sqrt(sum_k (actual[n,k]-target[n,k])^2), 0), k < d  -- the [N,2] layout dsnt_finish_loss averages.
+ * Backward:  g_actual[n,k] = g_loss * w_n * (actual-target)/dist,  w_n = (mask ? mask[n] : 1)/denom
+ *   (0 instead of NaN at dist == 0 unless DSNT_FLAG_STRICT_NAN)
+ */
+DSNT_API int dsnt_euclid_fwd(const float* actual, const float* target, long n, int d, float* terms, void* stream);
+DSNT_API int dsnt_euclid_bwd(const float* actual, const float* target, const float* terms, const float* mask,
+                             const float* g_loss, const float* denom, long n, int d, int flags, float* g_actual,
+                             void* stream);
+
+/*
+ * (Thresholded) softmax over the last dimension of a [rows, len] matrix.
+ *   replaces: ThresholdedSoftmax.forward/backward (src/dsnt/nn.py:119-139) and, with threshold = -inf and
+ *   eps = 0, softmax_2d / flat_softmax (src/dsnt/nn.py:160-165).  The max is taken over ALL entries.
+ *   out = exp(x - max) * (x >= threshold) / (sum + eps);   dx = out * (g - sum(g*out))
+ */
+DSNT_API int dsnt_tsoftmax_fwd(const void* x, int dtype, long rows, long len, float threshold, float eps,
+                      void* out, void* stream);
+DSNT_API int dsnt_tsoftmax_bwd(const void* out, const void* g, int dtype, long rows, long len, void* dx, void* stream);
+
+/*
+ * Normalised separable Gaussians (make_gauss, src/dsnt/nn.py:168-205; note width before height).
+ *   mu [N,2]; out [N,H,W] float32.   Backward wrt mu: dmu [N,2] from g [N,H,W].
+ */
+DSNT_API int dsnt_make_gauss_fwd(const float* mu, long n, int W, int H, float sigma, float* out, void* stream);
+DSNT_API int dsnt_make_gauss_bwd(const float* mu, const float* g, long n, int W, int H, float sigma, float* dmu,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSNT_B200_H_ */

@@ -15,6 +15,20 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def ensure_built():
+    """The .so is a build artefact (git-ignored): compile it (nvcc cross-compiles without a GPU) if absent."""
+    lib = os.path.join(ROOT, 'dsnt_pose2d_b200', 'libdsnt_b200.so')
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(['make', '-C', os.path.join(ROOT, 'dsnt_pose2d_b200', 'csrc'), '-j', '8'], check=True)
+    return lib
+
+
+@pytest.fixture(scope='session')
+def libpath():
+    return ensure_built()
+
+
 class Golden:
     """Lazy view over an .npz fixture: g['case/key']."""
 

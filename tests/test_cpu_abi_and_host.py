@@ -1,0 +1,118 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/dsnt_b200.h declares (no compute
+calls without a GPU), the host logic (argument validation, sigma conversion, sharding) behaves, and the
+product never falls back to a CPU path."""
+
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'dsnt_b200.h')).read()
+    return re.findall(r'DSNT_API\s+[\w\s\*]+?\b(dsnt_\w+)\s*\(', text)
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    for must in ('dsnt_head_fwd', 'dsnt_head_bwd', 'dsnt_finish_loss', 'dsnt_combine_loss', 'dsnt_euclid_fwd',
+                 'dsnt_euclid_bwd', 'dsnt_tsoftmax_fwd', 'dsnt_tsoftmax_bwd', 'dsnt_make_gauss_fwd',
+                 'dsnt_make_gauss_bwd', 'dsnt_b200_version', 'dsnt_b200_last_error'):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(libpath)
+    for name in declared_symbols():
+        assert hasattr(lib, name), 'libdsnt_b200.so does not export %s' % name
+    lib.dsnt_b200_version.restype = ctypes.c_int
+    assert lib.dsnt_b200_version() >= 100
+
+
+def test_binding_table_matches_header(libpath):
+    from dsnt_pose2d_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == sorted(declared_symbols())
+    text = open(os.path.join(ROOT, 'include', 'dsnt_b200.h')).read()
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        proto = re.search(r'DSNT_API[^;(]*\b%s\s*\(([^;]*)\)\s*;' % name, text).group(1)
+        n_args = 0 if proto.strip() == 'void' else proto.count(',') + 1
+        assert n_args == len(argtypes), (name, n_args, len(argtypes))
+
+
+def test_argument_validation_without_gpu(libpath):
+    """Rejected calls return before any CUDA work, so they are safe on a GPU-less host."""
+    from dsnt_pose2d_b200 import _lib
+    lib = _lib.LIB
+    assert lib.dsnt_head_fwd(None, 0, 1, 4, 8, 8, None, 0, 1.0, None, None, None, 0, None) == -1
+    assert 'null heatmap' in _lib.last_error()
+    buf = (ctypes.c_float * 64)()
+    addr = ctypes.addressof(buf)
+    assert lib.dsnt_head_fwd(addr, 7, 1, 1, 4, 4, None, 0, 1.0, addr, None, None, 0, None) == -2   # dtype
+    assert lib.dsnt_head_fwd(addr, 0, 1, 1, 4, 4, None, 3, 1.0, addr, None, None, 0, None) == -1   # JS w/o target
+    assert 'needs a target' in _lib.last_error()
+    assert lib.dsnt_head_fwd(addr, 0, 1, 1, 4, 4, addr, 3, 0.0, addr, None, None, 0, None) == -1   # sigma
+    assert lib.dsnt_head_fwd(addr, 0, 1, 1, 4, 4, None, 9, 1.0, addr, None, None, 0, None) == -1   # reg id
+    assert lib.dsnt_head_fwd(addr, 0, 1, 0, 4, 4, None, 0, 1.0, addr, None, None, 0, None) == 0    # n = 0: no-op
+    assert lib.dsnt_head_bwd(addr, 0, 1, 1, 4, 4, None, None, None, None, None, None, None, 1.0, 0, 1.0, 0,
+                             addr, 0, None) == -1                                                   # no stats
+    assert lib.dsnt_head_bwd(addr, 0, 1, 1, 4, 4, None, None, addr, None, None, addr, None, 1.0, 0, 1.0, 0,
+                             addr, 0, None) == -1                                                   # g_loss w/o denom
+    assert lib.dsnt_finish_workspace_bytes() >= 4 * 128 * 4 + 4
+
+
+def test_no_cpu_fallback_anywhere():
+    import dsnt_pose2d_b200 as dp
+    z = torch.randn(1, 2, 8, 8)
+    t = torch.zeros(1, 2, 2)
+    for call in (lambda: dp.dsnt_head(z, t), lambda: dp.nn.dsnt(z), lambda: dp.nn.flat_softmax(z),
+                 lambda: dp.nn.softmax_2d(z), lambda: dp.nn.thresholded_softmax(z, 0.0),
+                 lambda: dp.nn.js_reg_loss(z, t, 0.1), lambda: dp.nn.kl_reg_loss(z, t, 0.1),
+                 lambda: dp.nn.mse_reg_loss(z, t, 0.1), lambda: dp.nn.variance_reg_loss(z, t, 0.1),
+                 lambda: dp.nn.euclidean_loss(t, t), lambda: dp.nn.make_gauss(t, 8, 8, 0.1),
+                 lambda: dp.nn.masked_average(t)):
+        with pytest.raises(NotImplementedError):
+            call()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, 'dsnt_pose2d_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'oracle' not in src, fn
+
+
+def test_api_names_match_reference_nn():
+    """Every public name of src/dsnt/nn.py (plus north_star's flat_softmax) exists with the same signature."""
+    import inspect
+    from dsnt_pose2d_b200 import nn
+    expect = {
+        'generate_xy': ['inp'], 'expectation_2d': ['values', 'probabilities'], 'dsnt': ['heatmaps'],
+        'masked_average': ['losses', 'mask'], 'euclidean_loss': ['actual', 'target', 'mask'],
+        'thresholded_softmax': ['inp', 'threshold', 'eps'], 'softmax_2d': ['inp'], 'flat_softmax': ['inp'],
+        'make_gauss': ['coords', 'width', 'height', 'sigma'],
+        'kl_reg_loss': ['heatmaps', 'mu_t', 'sigma_t', 'mask'], 'js_reg_loss': ['heatmaps', 'mu_t', 'sigma_t', 'mask'],
+        'mse_reg_loss': ['heatmaps', 'mu_t', 'sigma_t', 'mask'],
+        'variance_reg_loss': ['heatmaps', 'mu_t', 'sigma_t', 'mask'],
+    }
+    for name, params in expect.items():
+        assert list(inspect.signature(getattr(nn, name)).parameters) == params, name
+    assert hasattr(nn, 'ThresholdedSoftmax')
+
+
+def test_shard_range_partitions_the_batch():
+    from dsnt_pose2d_b200.parallel import shard_range
+    for batch in (0, 1, 7, 32, 4096, 4099):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(batch, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a1 >= a0
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
