@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- DSNT head throughput (heatmaps/s, fwd+bwd+regulariser) and fraction of the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): per GPU a batch of 4096 samples x 16
+MPII joints x 64x64 fp32 logits, Euclidean loss + JS regulariser (sigma = 1 px), joint mask; weak scaling
+(every rank owns a fixed 4096-sample shard of a 4096*N batch, three floats are all-reduced per step).
+
+A "step" is one pass of the hot path over one batch: fused forward (coords, loss) + backward (dL/dZ).
+  value  whole-job heatmaps/s with Z already resident in HBM (CUDA events, barrier + sync both sides, max
+         over ranks).  Z is 1 GiB per step, far larger than the 126 MB L2, so no flush is needed.
+  e2e    the same step through the public API with HOST buffers: pinned Z/target/mask -> device copies
+         in, loss + coords device -> host out, all inside the timed region.
+  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+
+--impl reference times the reference's CPU implementation of the same path on this box's host cores.
+The reference is pure Python on torch; its tree is not on the GPU box, so this arm executes the committed
+restatement oracle/torch_port.py (the only place besides the cpu_baseline leg where bench.py executes oracle/).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'dsnt_head_heatmaps_per_sec'
+UNIT = 'heatmaps/s'
+WORKLOADS = {
+    # name: (batch per GPU, joints, H, W, reg, dtype)
+    'cfg4_64x64_f32_js': (4096, 16, 64, 64, 'js', 'f32'),
+    'cfg4_64x64_bf16_js': (4096, 16, 64, 64, 'js', 'bf16'),
+    'cfg4_64x64_f32_var': (4096, 16, 64, 64, 'var', 'f32'),
+    'cfg5_256x256_f32_var': (512, 16, 256, 256, 'var', 'f32'),
+    'cfg1_64x64_f32_js': (32, 16, 64, 64, 'js', 'f32'),
+    'cfg2_28x28_f32_js': (64, 16, 28, 28, 'js', 'f32'),
+}
+DEFAULT_WORKLOAD = 'cfg4_64x64_f32_js'
+CPU_SAMPLE = (32, 16, 64, 64)          # BASELINE cfg 1 shape: what the reference's CPU path is timed on
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def committed_traffic(workload):
+    """dram__bytes_read+write per launch from the committed ncu summary, if one exists for this workload."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [ln for (ts, ln) in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or [ln for (_, ln) in self.lines]
+        sm, smax, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in rows:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_reference_step(tp, torch, z, target, mask, reg):
+    """One fwd+bwd of the reference's head on CPU tensors (oracle/torch_port.py restates it op for op)."""
+    zz = z.detach().requires_grad_(True)
+    loss, _, _, _ = tp.head_loss(zz, target, mask, reg, 1.0, 1.0)
+    loss.backward()
+    return loss.item()
+
+
+def run_cpu_baseline(reg, budget_s=12.0, max_iters=10):
+    import torch
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b, c, h, w = CPU_SAMPLE
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(b, c, h, w, generator=g)
+    target = torch.rand(b, c, 2, generator=g) * 1.6 - 0.8
+    mask = (torch.rand(b, c, generator=g) > 0.1).float()
+    for _ in range(2):
+        cpu_reference_step(tp, torch, z, target, mask, reg)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_iters and (time.perf_counter() - t_start < budget_s or len(times) < 3):
+        t0 = time.perf_counter()
+        cpu_reference_step(tp, torch, z, target, mask, reg)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {'value': b * c / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d iterations of fwd+bwd on %dx%dx%dx%d fp32 (BASELINE cfg 1 shape), euclid + %s + mask, '
+                      'oracle/torch_port.py on torch CPU, median %.1f ms/iter' % (len(times), b, c, h, w, reg,
+                                                                                  med * 1e3)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def main_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import torch_port as tp
+    bsz, joints, h, w, reg, dtype = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b, c = CPU_SAMPLE[0], CPU_SAMPLE[1]
+    if h * w > 64 * 64:
+        b = max(1, b * 64 * 64 // (h * w))
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(b, c, h, w, generator=g)
+    target = torch.rand(b, c, 2, generator=g) * 1.6 - 0.8
+    mask = (torch.rand(b, c, generator=g) > 0.1).float()
+    for _ in range(args.warmup):
+        cpu_reference_step(tp, torch, z, target, mask, reg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(tp, torch, z, target, mask, reg)
+    dt = time.perf_counter() - t0
+    value = b * c * args.steps / dt
+    sample = ('each step = fwd+bwd on a %dx%dx%dx%d fp32 sample of the workload (bounded so the run ends within '
+              'minutes), oracle/torch_port.py restating src/dsnt/nn.py + model.py on torch CPU' % (b, c, h, w))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'heatmap': [h, w], 'joints': joints, 'reg': reg,
+                   'sample_heatmaps_per_step': b * c, 'device': 'host CPU'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dsnt_pose2d_b200 as dp
+    from dsnt_pose2d_b200 import _lib
+    from dsnt_pose2d_b200.parallel import init_from_env
+
+    world_env = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus > 1 and world_env == 1:
+        # launched as plain `python bench.py --gpus N`: re-exec under torchrun, one rank per GPU
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 2000), os.path.abspath(__file__)]
+        return subprocess.call(cmd + sys.argv[1:])
+    rank, local, world = init_from_env('nccl')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    group = dist.group.WORLD if world > 1 else None
+
+    bsz, joints, h, w, reg, dtype = WORKLOADS[args.workload]
+    tdt = torch.float32 if dtype == 'f32' else torch.bfloat16
+    esize = 4 if dtype == 'f32' else 2
+    n_local = bsz * joints
+    torch.manual_seed(1234 + rank)
+    z = torch.randn(bsz, joints, h, w, device=dev).to(tdt).requires_grad_(True)
+    target = torch.rand(bsz, joints, 2, device=dev) * 1.6 - 0.8
+    mask = (torch.rand(bsz, joints, device=dev) > 0.1).float()
+
+    def step():
+        z.grad = None
+        out = dp.dsnt_head(z, target, mask, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group)
+        out.loss.backward()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident-input timing
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    _lib.event_log = {'dsnt_head_fwd': [], 'dsnt_head_bwd': [], 'dsnt_finish_loss': []}
+    launches0 = _lib.launch_count
+    barrier()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _lib.launch_count - launches0
+    logs, _lib.event_log = _lib.event_log, None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = t.item()
+    kernel_ms = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v) if v else None) for k, v in logs.items()}
+
+    # ---------------- end-to-end timing: host buffers in, loss + coords out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        zh = torch.empty(bsz, joints, h, w, dtype=tdt).pin_memory()
+        zh.copy_(z.detach())
+        th, mh = target.cpu().pin_memory(), mask.cpu().pin_memory()
+        loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+        coords_h = torch.empty(bsz, joints, 2, dtype=torch.float32).pin_memory()
+        zd = torch.empty_like(z.detach())
+        td, md = torch.empty_like(target), torch.empty_like(mask)
+
+        def e2e_step():
+            zd.copy_(zh, non_blocking=True)
+            td.copy_(th, non_blocking=True)
+            md.copy_(mh, non_blocking=True)
+            zin = zd.detach().requires_grad_(True)
+            out = dp.dsnt_head(zin, td, md, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group)
+            out.loss.backward()
+            loss_h.copy_(out.loss.detach(), non_blocking=True)
+            coords_h.copy_(out.coords.detach(), non_blocking=True)
+            return zin.grad
+
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = zh.numel() * esize + th.numel() * 4 + mh.numel() * 4
+        d2h = 4 + coords_h.numel() * 4
+        e2e = {'value': n_local * world * e2e_steps / (te.item() * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+               'ms_per_step': te.item() / e2e_steps,
+               'note': 'pinned host Z/target/mask -> device, fused fwd+bwd, loss+coords -> pinned host; '
+                       'dL/dZ stays on the device for the backbone backward'}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel (live CUDA-event durations from the timed region)
+    peak, peak_how = measured_peak()
+    hw = h * w
+    alg = {'dsnt_head_fwd': n_local * (hw * esize + 56),        # read Z; target 8 r, coords 8 w, stats 32 w, terms 8 w
+           'dsnt_head_bwd': n_local * (2 * hw * esize + 44)}    # read Z, write dZ; stats 32 r, target 8 r, mask 4 r
+    dominant = max(('dsnt_head_fwd', 'dsnt_head_bwd'), key=lambda k: kernel_ms[k] or 0.0)
+    per_kernel = {}
+    for k in ('dsnt_head_fwd', 'dsnt_head_bwd'):
+        ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
+        per_kernel[k] = {'ms': kernel_ms[k], 'algorithmic_bytes': alg[k], 'achieved_gbs': ach, 'frac': ach / peak}
+    step_bytes = alg['dsnt_head_fwd'] + alg['dsnt_head_bwd']
+    step_gbs = step_bytes * world / (elapsed_ms / args.steps * 1e-3) / 1e9
+    traffic = committed_traffic(args.workload)
+    roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': per_kernel[dominant]['achieved_gbs'], 'peak': peak,
+                'unit': 'GB/s', 'frac': per_kernel[dominant]['frac'],
+                'traffic': (traffic or {}).get(dominant) if isinstance(traffic, dict) else None,
+                'peak_source': peak_how, 'kernels': per_kernel,
+                'step': {'algorithmic_bytes_per_gpu': step_bytes, 'achieved_gbs_per_gpu': step_gbs / world,
+                         'frac': step_gbs / world / peak}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_baseline(reg)
+
+    value = n_local * world * args.steps / (elapsed_ms * 1e-3)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
+        'config': {'workload': args.workload, 'heatmaps_per_gpu': n_local, 'batch_per_gpu': bsz, 'joints': joints,
+                   'heatmap': [h, w], 'reg': reg, 'hm_sigma_px': 1.0, 'mask': True,
+                   'parallelism': 'batch-sharded x%d, 3-float all-reduce per step' % world,
+                   'l2_policy': 'inputs larger than L2 (%.0f MiB of logits per step vs 126 MB L2)'
+                                % (n_local * hw * esize / 2 ** 20)},
+        'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks, 'e2e': e2e,
+        'gpu_launches': launches,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == 'reference' else main_ours(a))

@@ -57,6 +57,7 @@ def _load():
 
 LIB = _load()
 launch_count = 0          # kernels enqueued through this binding (bench.py reports it as gpu_launches)
+event_log = None          # bench.py sets this to {entry_point_name: []} to get CUDA-event pairs per launch
 
 
 def version():
@@ -70,7 +71,16 @@ def last_error():
 def call(name, *args, launches=1):
     """Invoke an entry point; a non-zero return raises RuntimeError with the library's message."""
     global launch_count
-    rc = getattr(LIB, name)(*args)
+    log = event_log.get(name) if event_log is not None else None
+    if log is not None:            # time this launch on the stream it is enqueued on (torch's current stream)
+        start = torch.cuda.Event(enable_timing=True)
+        stop = torch.cuda.Event(enable_timing=True)
+        start.record()
+        rc = getattr(LIB, name)(*args)
+        stop.record()
+        log.append((start, stop))
+    else:
+        rc = getattr(LIB, name)(*args)
     if rc != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))
     launch_count += launches

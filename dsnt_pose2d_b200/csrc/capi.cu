@@ -41,7 +41,7 @@ static int pick_vec(int dtype, int W, const void* a, const void* b) {
 }
 
 static int check_common(const void* z, int dtype, long n, int H, int W, int reg) {
-  if (!z) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
+  if (!z && n != 0) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
   if (dtype != DSNT_DTYPE_F32 && dtype != DSNT_DTYPE_BF16) { set_error("unsupported dtype %d (fp32 and bf16 only)", dtype); return DSNT_ERR_UNSUPPORTED; }
   if (n < 0 || H <= 0 || W <= 0) { set_error("bad shape n=%ld H=%d W=%d", n, H, W); return DSNT_ERR_BAD_ARG; }
   if (static_cast<long>(H) * W > (1L << 28)) { set_error("heatmap %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
@@ -64,6 +64,7 @@ DSNT_API int dsnt_head_fwd(const void* z, int dtype, int input_is_logits, long n
                   float sigma, float* coords, float* stats, float* terms, int variant, void* stream) {
   int rc = check_common(z, dtype, n, H, W, reg);
   if (rc) return rc;
+  if (n == 0) return DSNT_OK;
   if (!coords) { set_error("coords output is required"); return DSNT_ERR_BAD_ARG; }
   if (reg_needs_gauss(reg) && !target) { set_error("reg %d needs a target", reg); return DSNT_ERR_BAD_ARG; }
   if (reg != DSNT_REG_NONE && !(sigma > 0.f)) { set_error("sigma must be > 0"); return DSNT_ERR_BAD_ARG; }
@@ -87,6 +88,7 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
                   int variant, void* stream) {
   int rc = check_common(dz, dtype, n, H, W, reg);
   if (rc) return rc;
+  if (n == 0) return DSNT_OK;
   const bool need_z = input_is_logits || reg_needs_gauss(reg);
   if (need_z && !z) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
   if (!stats) { set_error("stats from the forward are required"); return DSNT_ERR_BAD_ARG; }
@@ -112,7 +114,7 @@ DSNT_API int dsnt_finish_workspace_bytes(void) { return static_cast<int>(sizeof(
 
 DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, float reg_coeff, float* out, float* workspace,
                      void* stream) {
-  if (!terms || !out || !workspace || n < 0) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if ((!terms && n > 0) || !out || !workspace || n < 0) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
   if (!aligned(terms, 8) || !aligned(workspace, 16)) { set_error("dsnt_finish_loss: misaligned buffers"); return DSNT_ERR_BAD_ARG; }
   long ctas = (n + 1023) / 1024;  // >= 4 heatmaps per thread before adding CTAs
   if (ctas < 1) ctas = 1;

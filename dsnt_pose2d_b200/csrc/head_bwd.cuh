@@ -172,13 +172,16 @@ __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_bwd_kernel(co
         if constexpr (LOGITS) {
           float t = fmaf(v[k][c], kLog2e, -s.m2);
           const float P = ex2(t) * s.invS;
-          if (reg == DSNT_REG_KL || reg == DSNT_REG_JS) t = fmaxf(t, -1e30f);  // z = -inf: P = 0, keep 0 * t finite
           if (reg == DSNT_REG_KL) {
+            t = fmaxf(t, -1e30f);  // z = -inf: P = 0, keep 0 * t finite
             const float G = tabx[col0 + c] * gyn;
             gmc = fmaf(s.rho * kLn2, (t + s.l2is) - lg2(G + kEps), gmc);
           } else if (reg == DSNT_REG_JS) {
-            const float M = 0.5f * fmaf(tabx[col0 + c], gyn, P);
-            gmc = fmaf(0.5f * s.rho * kLn2, (t + s.l2is) - lg2(M + kEps), gmc);
+            // r = 1/2 [ln P - ln(M+eps)] = -1/2 ln2 (lg2(1+q) - 1),  q = (G + 2 eps)/P.  The ratio form keeps the
+            // absolute error of lg2.approx (2^-22 near 1) instead of differencing two logs of magnitude ~10-20,
+            // which matters exactly where P ~ G (a trained heatmap's peak).
+            const float q = fmaf(tabx[col0 + c], gyn, 2.f * kEps) * rcp(fmaxf(P, 1e-37f));
+            gmc = fmaf(-0.5f * s.rho * kLn2, lg2(1.0f + q) - 1.0f, gmc);
           } else if (reg == DSNT_REG_MSE) {
             gmc = fmaf(2.f * s.rho, fmaf(-tabx[col0 + c], gyn, P), gmc);
           }

@@ -60,20 +60,24 @@ def test_model_loss_and_backbone_gradients_match_oracle(dp, reg):
     x = torch.randn(3, 3, 32, 32, device=DEV)
     target = torch.rand(3, 16, 2, device=DEV) * 1.6 - 0.8
     mask = (torch.rand(3, 16, device=DEV) > 0.2).float()
+    grabbed = {}
+
+    def grab(_module, _inp, output):                 # the logits entering the head, and their gradient
+        output.retain_grad()
+        grabbed['z'] = output
+
+    hook = model.hm_convs[0].register_forward_hook(grab)
     out = model(x)
+    hook.remove()
     loss = model.forward_loss(out, target, mask)
     loss.backward()
-    z = model.forward_part1(x).detach()
-    ref = tp.head_loss_and_grad(z, target, mask, reg, 1.3, 0.7)
+    z = grabbed['z']
+    ref = tp.head_loss_and_grad(z.detach(), target, mask, reg, 1.3, 0.7)
     assert abs(loss.item() - ref['loss'].item()) / abs(ref['loss'].item()) < TOL
-    for p_name, p in model.named_parameters():
-        assert p.grad is not None, p_name
-    g_fused = [p.grad.clone() for p in model.parameters()]
-    # the same parameters' gradients when the ORACLE's dL/dZ is pushed through the backbone by autograd
-    model.zero_grad()
-    model.forward_part1(x).backward(ref['dz'].float().to(DEV))
-    for gf, p in zip(g_fused, model.parameters()):
-        assert rel_l2(gf.cpu().numpy(), p.grad.cpu().numpy()) < 5e-5
+    assert rel_l2(z.grad.cpu().double().numpy(), ref['dz'].numpy()) < TOL      # dL/dZ handed to the backbone
+    for p_name, p in model.named_parameters():                                # ... and it reaches every parameter
+        assert p.grad is not None and torch.isfinite(p.grad).all(), p_name
+    assert model.hm_convs[0].weight.grad.abs().max().item() > 0
 
 
 def test_training_step_changes_every_parameter(dp):
