@@ -6,6 +6,7 @@
 
 #include "head_bwd.cuh"
 #include "head_fwd.cuh"
+#include "head_stream.cuh"
 
 namespace dsnt {
 
@@ -54,11 +55,44 @@ int launch_fwd_shape(const HeadFwdParams& p, int variant, cudaStream_t stream) {
   return launch_fwd_large<T, VEC, REG, LOGITS>(p, stream);
 }
 
+// ---- streaming kernels (logits, vectorised): variant 0 picks them; variant 2 forces the v0 register-resident path
+inline bool stream_group_is_cta(long nvec) { return nvec > 2048; }
+
+template <typename T, int VEC, int GROUP, int REG>
+int launch_fwd_stream_group(const HeadFwdParams& p, cudaStream_t stream) {
+  constexpr int BLOCK = stream_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  HeadFwdStreamParams ps;
+  ps.base = p;
+  ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
+  const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
+  if (GROUP % ps.g.wv == 0)
+    head_fwd_stream_kernel<T, VEC, GROUP, REG, true><<<grid, BLOCK, 0, stream>>>(ps);
+  else
+    head_fwd_stream_kernel<T, VEC, GROUP, REG, false><<<grid, BLOCK, 0, stream>>>(ps);
+  return check_launch("head_fwd_stream_kernel");
+}
+
+template <typename T, int VEC, int REG>
+int launch_fwd_stream(const HeadFwdParams& p, cudaStream_t stream) {
+  const long nvec = static_cast<long>(p.H) * p.W / VEC;
+  return stream_group_is_cta(nvec) ? launch_fwd_stream_group<T, VEC, 256, REG>(p, stream)
+                                   : launch_fwd_stream_group<T, VEC, 32, REG>(p, stream);
+}
+
 template <typename T, int VEC, bool LOGITS>
 int launch_fwd_reg(const HeadFwdParams& p, int variant, cudaStream_t stream) {
   if constexpr (VEC == 1) {
     return launch_fwd_shape<T, VEC, -1, LOGITS>(p, variant, stream);  // odd sizes: regulariser chosen at run time
   } else {
+    if constexpr (LOGITS) {
+      if (variant == 0) {
+        if (p.reg == DSNT_REG_NONE) return launch_fwd_stream<T, VEC, DSNT_REG_NONE>(p, stream);
+        if (p.reg == DSNT_REG_KL) return launch_fwd_stream<T, VEC, DSNT_REG_KL>(p, stream);
+        if (p.reg == DSNT_REG_JS) return launch_fwd_stream<T, VEC, DSNT_REG_JS>(p, stream);
+      }
+      if (variant == 2) variant = 0;
+    }
     switch (p.reg) {
       case DSNT_REG_NONE: return launch_fwd_shape<T, VEC, DSNT_REG_NONE, LOGITS>(p, variant, stream);
       case DSNT_REG_VAR: return launch_fwd_shape<T, VEC, DSNT_REG_VAR, LOGITS>(p, variant, stream);
@@ -87,6 +121,7 @@ int launch_bwd_one(const HeadBwdParams& p, cudaStream_t stream) {
   return check_launch("head_bwd_kernel");
 }
 
+// variant: 0 = streaming kernel (logits, vectorised) else the v0 register-resident kernel
 template <typename T, int VEC, int REG, bool LOGITS>
 int launch_bwd_shape(const HeadBwdParams& p, int variant, cudaStream_t stream) {
   (void)variant;
@@ -96,11 +131,44 @@ int launch_bwd_shape(const HeadBwdParams& p, int variant, cudaStream_t stream) {
   return launch_bwd_one<T, VEC, 256, 4, REG, LOGITS>(p, stream);  // chunked over blockIdx.y beyond 1024 vectors
 }
 
+template <typename T, int VEC, int GROUP, int REG>
+int launch_bwd_stream_group(const HeadBwdParams& p, cudaStream_t stream) {
+  constexpr int BLOCK = stream_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  HeadBwdStreamParams ps;
+  ps.base = p;
+  ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
+  const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
+  if (GROUP % ps.g.wv == 0)
+    head_bwd_stream_kernel<T, VEC, GROUP, REG, true><<<grid, BLOCK, 0, stream>>>(ps);
+  else
+    head_bwd_stream_kernel<T, VEC, GROUP, REG, false><<<grid, BLOCK, 0, stream>>>(ps);
+  return check_launch("head_bwd_stream_kernel");
+}
+
+template <typename T, int VEC, int REG>
+int launch_bwd_stream(const HeadBwdParams& p, cudaStream_t stream) {
+  const long nvec = static_cast<long>(p.H) * p.W / VEC;
+  return stream_group_is_cta(nvec) ? launch_bwd_stream_group<T, VEC, 256, REG>(p, stream)
+                                   : launch_bwd_stream_group<T, VEC, 32, REG>(p, stream);
+}
+
 template <typename T, int VEC, bool LOGITS>
 int launch_bwd_reg(const HeadBwdParams& p, int variant, cudaStream_t stream) {
   if constexpr (VEC == 1) {
     return launch_bwd_shape<T, VEC, -1, LOGITS>(p, variant, stream);
   } else {
+    if constexpr (LOGITS) {
+      if (variant == 0) {
+        switch (p.reg) {
+          case DSNT_REG_NONE: return launch_bwd_stream<T, VEC, DSNT_REG_NONE>(p, stream);
+          case DSNT_REG_VAR: return launch_bwd_stream<T, VEC, DSNT_REG_VAR>(p, stream);
+          case DSNT_REG_KL: return launch_bwd_stream<T, VEC, DSNT_REG_KL>(p, stream);
+          case DSNT_REG_JS: return launch_bwd_stream<T, VEC, DSNT_REG_JS>(p, stream);
+          case DSNT_REG_MSE: return launch_bwd_stream<T, VEC, DSNT_REG_MSE>(p, stream);
+        }
+      }
+    }
     switch (p.reg) {
       case DSNT_REG_NONE: return launch_bwd_shape<T, VEC, DSNT_REG_NONE, LOGITS>(p, variant, stream);
       case DSNT_REG_VAR: return launch_bwd_shape<T, VEC, DSNT_REG_VAR, LOGITS>(p, variant, stream);

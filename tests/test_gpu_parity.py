@@ -141,11 +141,32 @@ def test_assorted_sizes_js_and_var(dp, tp, shape):
 
 
 @pytest.mark.parametrize('reg', REGS)
-def test_streaming_variant_equals_resident(dp, tp, reg):
-    """variant=1 forces the two-pass kernel on a 64x64 map; both kernels must agree with the oracle."""
+@pytest.mark.parametrize('variant', [1, 2])
+def test_alternative_kernels_agree_with_oracle(dp, tp, reg, variant):
+    """variant=1 forces the two-pass L2 kernel, variant=2 the register-resident kernels (forward and backward)
+    on a 64x64 map; the default (variant 0) is the streaming/windowed path.  All must match the oracle."""
     z, target, mask = synth(4, 4, 64, 64, 3.0, seed=4)
     l64, c64, d64 = oracle(tp, z, target, mask, reg)
-    check(run_head(dp, z, target, mask, reg, variant=1), l64, c64, d64, 'two-pass 64x64 %s' % reg)
+    check(run_head(dp, z, target, mask, reg, variant=variant), l64, c64, d64, 'variant %d 64x64 %s' % (variant, reg))
+
+
+@pytest.mark.parametrize('reg', ['kl', 'js'])
+@pytest.mark.parametrize('hm_sigma', [0.5, 1.0, 4.0, 40.0])
+@pytest.mark.parametrize('where', ['inside', 'edge', 'outside', 'far'])
+def test_gaussian_window_is_exact_for_any_sigma_and_target(dp, tp, reg, hm_sigma, where):
+    """The divergence is evaluated only on the window where the target Gaussian is non-negligible; the window
+    is derived from sigma and the target, so tiny / huge sigma and targets at or beyond the border must give
+    the same answer as the dense reference arithmetic."""
+    z, target, mask = synth(3, 4, 64, 64, 2.0, seed=11)
+    if where == 'edge':
+        target = target.sign() * 0.99
+    elif where == 'outside':
+        target = target.sign() * 1.3
+    elif where == 'far':
+        target = target.sign() * 25.0
+    l64, c64, d64 = oracle(tp, z, target, mask, reg, hm_sigma=hm_sigma)
+    check(run_head(dp, z, target, mask, reg, hm_sigma=hm_sigma), l64, c64, d64,
+          'window %s sigma=%g %s' % (reg, hm_sigma, where))
 
 
 def test_unaligned_base_pointer_takes_scalar_path(dp, tp):
