@@ -30,7 +30,7 @@
 
 namespace dsnt {
 
-constexpr float kThetaJS = 1e-14f;   // G below this is dropped from P-weighted terms (abs. error <= W*H*theta*140)
+constexpr float kThetaJS = 1e-14f;   // G below this is dropped from P-weighted terms (abs. error <= W*H*theta*140); also MSE
 constexpr float kThetaKL = 3e-32f;   // G + 1e-24 == 1e-24 exactly in fp32 below this
 constexpr float kLog2Eps = -79.726274277296700f;   // log2(1e-24)
 constexpr float kLnEps = -55.262042231857095f;     // ln(1e-24)
@@ -123,9 +123,12 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
   constexpr int U = VEC == 8 ? 4 : 8;  // vectors in flight per thread: 128 B (fp32) / 64 B (bf16) x U
   constexpr bool kKL = REG == DSNT_REG_KL;
   constexpr bool kJS = REG == DSNT_REG_JS;
+  constexpr bool kVar = REG == DSNT_REG_VAR;
+  constexpr bool kMSE = REG == DSNT_REG_MSE;
+  static_assert(!kVar || FIXC, "the single-pass variance needs thread-fixed columns");
   __shared__ float red_m[GPB * NW];
   __shared__ float red_a[GPB * NW * 4];
-  __shared__ float red_b[GPB * NW * 2];
+  __shared__ float red_b[GPB * NW * 4];
 
   const HeadFwdParams& p = ps.base;
   const Geom& g = ps.g;
@@ -148,8 +151,15 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
     ybase = axis_coord(wk.row, g.two_over_h, g.bias_h);
   }
 
-  // ---- streaming pass: online softmax statistics
-  float mt2 = -INFINITY, S = 0.f, Sx = 0.f, Sy = 0.f, Tt = 0.f;
+  // ---- streaming pass: online softmax statistics.
+  // FIXC: a thread always sees the same VEC columns, so it keeps one accumulator per column (E[c] = sum over its
+  // rows of e) and S, S_x follow exactly at the end.  The variance regulariser additionally runs a weighted
+  // Welford recurrence over the thread's rows (my, M2y), which is cancellation-free for any sigma.
+  float mt2 = -INFINITY, S = 0.f, Sx = 0.f, Sy = 0.f, Tt = 0.f, Q = 0.f;
+  float E[VEC];
+  float my = 0.f, M2y = 0.f;
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) E[c] = 0.f;
   for (int f0 = lane_g; f0 < nvec; f0 += GROUP * U) {
     float v[U][VEC];
     const bool full = f0 + (U - 1) * GROUP < nvec;
@@ -169,7 +179,15 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
     if (bm2 > mt2) {  // rare after the first batches: rescale the running sums to the new maximum
       const float sc = ex2(mt2 - bm2);
       if (kKL) Tt = S > 0.f ? sc * fmaf(mt2 - bm2, S, Tt) : 0.f;  // sum e'(t - d) = sc (T - d S)
-      S *= sc; Sx *= sc; Sy *= sc;
+      S *= sc; Sy *= sc;
+      if constexpr (FIXC) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) E[c] *= sc;
+      } else {
+        Sx *= sc;
+      }
+      if (kVar) M2y *= sc;
+      if (kMSE) Q *= sc * sc;
       mt2 = bm2;
     }
 #pragma unroll
@@ -183,21 +201,50 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
           for (int c = 0; c < VEC; ++c) xs[c] = axis_coord(wk.cv * VEC + c, g.two_over_w, g.bias_w);
           y = axis_coord(wk.row, g.two_over_h, g.bias_h);
         }
-        float rs = 0.f;
+        float ev[VEC];
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
           const float t = fmaf(v[u][c], kLog2e, -mt2);
-          const float e = ex2(t);
-          rs += e;
-          Sx = fmaf(e, xs[c], Sx);
-          if (kKL) Tt = fmaf(e, t, Tt);
+          ev[c] = ex2(t);
+          if (kKL) Tt = fmaf(ev[c], t, Tt);
+          if (kMSE) Q = fmaf(ev[c], ev[c], Q);
+          if constexpr (FIXC) E[c] += ev[c]; else Sx = fmaf(ev[c], xs[c], Sx);
         }
-        S += rs;
-        Sy = fmaf(rs, y, Sy);
+        float rs;
+        if constexpr (VEC == 8) rs = ((ev[0] + ev[1]) + (ev[2] + ev[3])) + ((ev[4] + ev[5]) + (ev[6] + ev[7]));
+        else if constexpr (VEC == 4) rs = (ev[0] + ev[1]) + (ev[2] + ev[3]);
+        else rs = ev[0];
+        if constexpr (kVar) {
+          // weighted Welford: S += rs; my += (y - my) rs / S; M2y += rs (y - my_old)(y - my_new)
+          S += rs;
+          const float dl = y - my;
+          const float wgt = rs * rcp(fmaxf(S, 1e-30f));
+          my = fmaf(dl, wgt, my);
+          M2y = fmaf(rs * dl, y - my, M2y);
+        } else {
+          if (!FIXC || kKL) S += rs;   // FIXC: S is the sum of the column accumulators (KL needs it on the fly)
+          Sy = fmaf(rs, y, Sy);
+        }
       }
       if constexpr (!FIXC) wk.next();
     }
     if constexpr (FIXC) ybase = fmaf(static_cast<float>(U), g.dy_step, ybase);
+  }
+
+  // ---- thread-local wrap-up
+  float mx = 0.f, M2x = 0.f;
+  if constexpr (FIXC) {
+    float s = 0.f, sx = 0.f;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) { s += E[c]; sx = fmaf(E[c], xs[c], sx); }
+    if (!kVar && !kKL) S = s;   // (Welford / KL already own S; it is the same sum)
+    Sx = sx;
+    if constexpr (kVar) {
+      mx = s > 0.f ? sx / s : 0.f;
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) { const float d = xs[c] - mx; M2x = fmaf(E[c] * d, d, M2x); }
+      Sy = S * my;
+    }
   }
 
   // ---- merge the per-thread statistics
@@ -206,7 +253,10 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
     const float sc = mt2 > -INFINITY ? ex2(mt2 - m2) : 0.f;
     if (kKL) Tt = S > 0.f ? sc * fmaf(mt2 - m2, S, Tt) : 0.f;
     S *= sc; Sx *= sc; Sy *= sc;
+    if (kVar) { M2x *= sc; M2y *= sc; }
+    if (kMSE) Tt = Q * sc * sc;     // MSE rides in the 4th slot of the reduction
   }
+  const float S_loc = S;
   group_sum4<GROUP>(S, Sx, Sy, Tt, red_a + gid * NW * 4, warp_g, lane);
   const float invS = 1.0f / S;
   const float mux = Sx * invS, muy = Sy * invS;
@@ -217,11 +267,23 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
     tx = t.x; ty = t.y;
   }
 
+  float D = 0.f, creg = 0.f, ginv = 0.f, vx = 0.f, vy = 0.f;
+
+  // ---- variance regulariser: second moments about the GLOBAL mean (Chan's update, all terms positive)
+  if constexpr (kVar) {
+    const float ddx = mx - mux, ddy = my - muy;
+    float ax = fmaf(S_loc * ddx, ddx, M2x), ay = fmaf(S_loc * ddy, ddy, M2y);
+    group_sum2<GROUP>(ax, ay, red_b + gid * NW * 4, warp_g, lane);
+    vx = ax * invS; vy = ay * invS;
+    const float s2 = p.sigma * p.sigma, ex = vx - s2, ey = vy - s2;
+    D = ex * ex + ey * ey;
+    creg = 2.f * (ex * vx + ey * vy);
+  }
+
   // ---- divergence on the window of the Gaussian only
-  float D = 0.f, creg = 0.f, ginv = 0.f;
-  if constexpr (kKL || kJS) {
+  if constexpr (kKL || kJS || kMSE) {
     const Window win = make_window(g, H, W, tx, ty);
-    float qa = 0.f, qb = 0.f;
+    float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
     if (!win.empty()) {
       float sx = axis_window_sum(win.j_lo, win.j_hi, tx, g.two_over_w, g.bias_w, g.k2, lane);
       float sy = axis_window_sum(win.i_lo, win.i_hi, ty, g.two_over_h, g.bias_h, g.k2, lane);
@@ -266,26 +328,38 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
                 const float L = lg2(Mp);
                 qa = fmaf(e * invS, (t + tlm1) - L, qa);                // P (log2 P - log2 M' - 1)
                 qb = fmaf(G, lgG - L, qb);                             // G (log2 G - log2 M')
-              } else {
+              } else if (kKL) {
                 qa = fmaf(e * invS, lg2(G + kEps) - kLog2Eps, qa);     // P (log2(G+eps) - log2 eps)
+              } else {
+                const float P = e * invS, df = P - G;
+                qa = fmaf(df, df, qa);                                 // (P - G)^2
+                qb = fmaf(P, P, qb);                                   // P^2 (to take the window out of sum P^2)
+                qc = fmaf(P, df, qc);                                  // P (P - G)
               }
             }
           }
         }
       }
     }
-    group_sum2<GROUP>(qa, qb, red_b + gid * NW * 2, warp_g, lane);
-    if (kJS) {
-      creg = 0.5f * kLn2 * (1.0f + qa);        // 1/2 sum P (ln P - ln M')
-      D = fmaf(0.5f * kLn2, qb, creg);         // + 1/2 sum G (ln G - ln M')
+    if constexpr (kMSE) {
+      group_sum4<GROUP>(qa, qb, qc, qd, red_b + gid * NW * 4, warp_g, lane);
+      const float outside = fmaxf(fmaf(Tt * invS, invS, -qb), 0.f);   // sum of P^2 where G is negligible
+      D = outside + qa;
+      creg = 2.f * (outside + qc);
     } else {
-      const float plnp = fmaf(kLn2 * invS, Tt, -logf(S));  // sum P ln P
-      D = plnp - kLnEps - kLn2 * qa;
-      creg = D + 1.0f;
+      group_sum2<GROUP>(qa, qb, red_b + gid * NW * 4, warp_g, lane);
+      if (kJS) {
+        creg = 0.5f * kLn2 * (1.0f + qa);        // 1/2 sum P (ln P - ln M')
+        D = fmaf(0.5f * kLn2, qb, creg);         // + 1/2 sum G (ln G - ln M')
+      } else {
+        const float plnp = fmaf(kLn2 * invS, Tt, -logf(S));  // sum P ln P
+        D = plnp - kLnEps - kLn2 * qa;
+        creg = D + 1.0f;
+      }
     }
   }
 
-  if (lane_g == 0) write_outputs(p, hm, m2, invS, mux, muy, 0.f, 0.f, creg, ginv, tx, ty, D);
+  if (lane_g == 0) write_outputs(p, hm, m2, invS, mux, muy, vx, vy, creg, ginv, tx, ty, D);
 }
 
 // ================================================================================================ backward

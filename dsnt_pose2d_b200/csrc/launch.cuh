@@ -66,10 +66,14 @@ int launch_fwd_stream_group(const HeadFwdParams& p, cudaStream_t stream) {
   ps.base = p;
   ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
   const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
-  if (GROUP % ps.g.wv == 0)
+  if (GROUP % ps.g.wv == 0) {
     head_fwd_stream_kernel<T, VEC, GROUP, REG, true><<<grid, BLOCK, 0, stream>>>(ps);
-  else
+  } else if constexpr (REG != DSNT_REG_VAR) {
     head_fwd_stream_kernel<T, VEC, GROUP, REG, false><<<grid, BLOCK, 0, stream>>>(ps);
+  } else {
+    // the single-pass variance needs thread-fixed columns; odd widths keep the two-pass kernels
+    return launch_fwd_shape<T, VEC, REG, true>(p, 0, stream);
+  }
   return check_launch("head_fwd_stream_kernel");
 }
 
@@ -88,8 +92,10 @@ int launch_fwd_reg(const HeadFwdParams& p, int variant, cudaStream_t stream) {
     if constexpr (LOGITS) {
       if (variant == 0) {
         if (p.reg == DSNT_REG_NONE) return launch_fwd_stream<T, VEC, DSNT_REG_NONE>(p, stream);
+        if (p.reg == DSNT_REG_VAR) return launch_fwd_stream<T, VEC, DSNT_REG_VAR>(p, stream);
         if (p.reg == DSNT_REG_KL) return launch_fwd_stream<T, VEC, DSNT_REG_KL>(p, stream);
         if (p.reg == DSNT_REG_JS) return launch_fwd_stream<T, VEC, DSNT_REG_JS>(p, stream);
+        if (p.reg == DSNT_REG_MSE) return launch_fwd_stream<T, VEC, DSNT_REG_MSE>(p, stream);
       }
       if (variant == 2) variant = 0;
     }
