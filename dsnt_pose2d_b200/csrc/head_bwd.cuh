@@ -60,12 +60,12 @@ __device__ __forceinline__ BwdScalars load_bwd_scalars(const HeadBwdParams& p, l
   float a = 0.f, b = 0.f, rho = 0.f;
   if (p.g_loss) {
     const float gl = __ldg(p.g_loss);
-    const float w = (p.mask ? __ldg(p.mask + hm) : 1.0f) / __ldg(p.denom);
+    const float w = __fdividef(p.mask ? __ldg(p.mask + hm) : 1.0f, __ldg(p.denom));
     if (p.target && !(p.flags & DSNT_FLAG_NO_EUCLID)) {
       const float dx = s.mux - s.tx, dy = s.muy - s.ty;
-      const float d = sqrtf(dx * dx + dy * dy);
+      const float d2 = dx * dx + dy * dy;
       // sqrt'(0) = inf: the reference back-propagates NaN there; default is 0.
-      const float invd = d > 0.f ? 1.0f / d : ((p.flags & DSNT_FLAG_STRICT_NAN) ? INFINITY : 0.f);
+      const float invd = d2 > 0.f ? rsqrtf(d2) : ((p.flags & DSNT_FLAG_STRICT_NAN) ? INFINITY : 0.f);
       a = gl * w * (dx * invd);
       b = gl * w * (dy * invd);
     }

@@ -3,9 +3,12 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 
 #include "head_bwd.cuh"
 #include "head_fwd.cuh"
+#include "head_fast.cuh"
 #include "head_stream.cuh"
 
 namespace dsnt {
@@ -58,6 +61,103 @@ int launch_fwd_shape(const HeadFwdParams& p, int variant, cudaStream_t stream) {
 // ---- streaming kernels (logits, vectorised): variant 0 picks them; variant 2 forces the v0 register-resident path
 inline bool stream_group_is_cta(long nvec) { return nvec > 2048; }
 
+// ---- tuned kernels (head_fast.cuh): variant 0 picks them whenever the layout qualifies; variant 3 forces v1
+inline bool make_fast_geom(int H, int W, int vec, int group, FastGeom& f) {
+  const int wv = W / vec;
+  if (wv <= 0 || (wv & (wv - 1)) != 0 || group % wv != 0) return false;
+  const long nvec = static_cast<long>(H) * wv;
+  if (nvec % (static_cast<long>(group) * kFastU) != 0) return false;
+  f.wv_shift = 0;
+  while ((1 << f.wv_shift) < wv) ++f.wv_shift;
+  f.nbatch = static_cast<int>(nvec / (static_cast<long>(group) * kFastU));
+  f.rstep = group / wv;
+  f.dy_step = static_cast<float>(f.rstep) * (2.0f / static_cast<float>(H));
+  f.dy_batch = static_cast<float>(kFastU) * f.dy_step;
+  return true;
+}
+
+// Upper bound of the Gaussian window (make_window) for any target: floor(n sqrt(r2 + 1/n^2)) + 3 pixels per axis,
+// widened to whole vectors along x.  When that cannot fit the shared-memory stash the generic kernels run instead.
+inline bool stash_fits(int H, int W, int vec, int reg, float r2_win) {
+  if (!reg_needs_gauss(reg)) return true;
+  const double r2 = r2_win;
+  const int mc = static_cast<int>(std::floor(W * std::sqrt(r2 + 1.0 / (static_cast<double>(W) * W)))) + 4;
+  const int mr = static_cast<int>(std::floor(H * std::sqrt(r2 + 1.0 / (static_cast<double>(H) * H)))) + 4;
+  const int cols = std::min(W, ((mc + vec - 2) / vec + 1) * vec);
+  const int rows = std::min(H, mr);
+  return rows <= kTabN && cols <= kTabN && rows * cols <= kStashFloats;
+}
+
+inline size_t tune_smem(const char* name) {
+  const char* v = std::getenv(name);
+  return v ? static_cast<size_t>(std::atol(v)) : 0;
+}
+
+template <typename T, int VEC, int GROUP, int REG>
+int launch_fwd_fast_group(const HeadFwdParams& p, const FastGeom& f, cudaStream_t stream) {
+  constexpr int BLOCK = stream_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  HeadFwdFastParams ps;
+  ps.base = p;
+  ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
+  ps.f = f;
+  if (!stash_fits(p.H, p.W, VEC, REG, ps.g.r2_win)) return 1;
+  const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
+  head_fwd_fast_kernel<T, VEC, GROUP, REG><<<grid, BLOCK, 0, stream>>>(ps);
+  return check_launch("head_fwd_fast_kernel");
+}
+
+// returns 1 when the layout does not qualify (caller falls through to the generic kernels)
+template <typename T, int VEC, int REG>
+int try_launch_fwd_fast(const HeadFwdParams& p, cudaStream_t stream) {
+  if constexpr (sizeof(T) * VEC != 16) {
+    return 1;
+  } else {
+    const long nvec = static_cast<long>(p.H) * p.W / VEC;
+    FastGeom f;
+    if (stream_group_is_cta(nvec)) {
+      if (!make_fast_geom(p.H, p.W, VEC, 256, f)) return 1;
+      return launch_fwd_fast_group<T, VEC, 256, REG>(p, f, stream);
+    }
+    if (!make_fast_geom(p.H, p.W, VEC, 32, f)) return 1;
+    return launch_fwd_fast_group<T, VEC, 32, REG>(p, f, stream);
+  }
+}
+
+template <typename T, int VEC, int GROUP, int REG>
+int launch_bwd_fast_group(const HeadBwdParams& p, const FastGeom& f, cudaStream_t stream) {
+  constexpr int BLOCK = stream_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  HeadBwdFastParams ps;
+  ps.base = p;
+  ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
+  ps.f = f;
+  if (!stash_fits(p.H, p.W, VEC, REG, ps.g.r2_win)) return 1;
+  const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
+  static const size_t extra_smem = tune_smem("DSNT_TUNE_BWD_SMEM");   // developer knob: caps CTAs per SM
+  head_bwd_fast_kernel<T, VEC, GROUP, REG><<<grid, BLOCK, extra_smem, stream>>>(ps);
+  return check_launch("head_bwd_fast_kernel");
+}
+
+template <typename T, int VEC, int REG>
+int try_launch_bwd_fast(const HeadBwdParams& p, cudaStream_t stream) {
+  // fp32 with a Gaussian window: the generic kernel's in-loop window arithmetic hides completely under the
+  // 8 B/pixel of traffic (0.98 of HBM peak), while the stash epilogue adds an exposed tail (0.89) -- measured in
+  // profiles/r01_v2_kbench.txt.  bf16 has half the bytes per pixel to hide work under, there the stash wins.
+  if constexpr (sizeof(T) * VEC != 16 || (sizeof(T) == 4 && reg_needs_gauss(REG))) {
+    return 1;
+  } else {
+    const long nvec = static_cast<long>(p.H) * p.W / VEC;
+    FastGeom f;
+    if (stream_group_is_cta(nvec)) {
+      if (!make_fast_geom(p.H, p.W, VEC, 256, f)) return 1;
+      return launch_bwd_fast_group<T, VEC, 256, REG>(p, f, stream);
+    }
+    if (!make_fast_geom(p.H, p.W, VEC, 32, f)) return 1;
+    return launch_bwd_fast_group<T, VEC, 32, REG>(p, f, stream);
+  }
+}
+
 template <typename T, int VEC, int GROUP, int REG>
 int launch_fwd_stream_group(const HeadFwdParams& p, cudaStream_t stream) {
   constexpr int BLOCK = stream_block_threads<GROUP>();
@@ -91,6 +191,17 @@ int launch_fwd_reg(const HeadFwdParams& p, int variant, cudaStream_t stream) {
   } else {
     if constexpr (LOGITS) {
       if (variant == 0) {
+        int rc = 1;
+        switch (p.reg) {
+          case DSNT_REG_NONE: rc = try_launch_fwd_fast<T, VEC, DSNT_REG_NONE>(p, stream); break;
+          case DSNT_REG_VAR: rc = try_launch_fwd_fast<T, VEC, DSNT_REG_VAR>(p, stream); break;
+          case DSNT_REG_KL: rc = try_launch_fwd_fast<T, VEC, DSNT_REG_KL>(p, stream); break;
+          case DSNT_REG_JS: rc = try_launch_fwd_fast<T, VEC, DSNT_REG_JS>(p, stream); break;
+          case DSNT_REG_MSE: rc = try_launch_fwd_fast<T, VEC, DSNT_REG_MSE>(p, stream); break;
+        }
+        if (rc != 1) return rc;
+      }
+      if (variant == 0 || variant == 3) {
         if (p.reg == DSNT_REG_NONE) return launch_fwd_stream<T, VEC, DSNT_REG_NONE>(p, stream);
         if (p.reg == DSNT_REG_VAR) return launch_fwd_stream<T, VEC, DSNT_REG_VAR>(p, stream);
         if (p.reg == DSNT_REG_KL) return launch_fwd_stream<T, VEC, DSNT_REG_KL>(p, stream);
@@ -166,6 +277,17 @@ int launch_bwd_reg(const HeadBwdParams& p, int variant, cudaStream_t stream) {
   } else {
     if constexpr (LOGITS) {
       if (variant == 0) {
+        int rc = 1;
+        switch (p.reg) {
+          case DSNT_REG_NONE: rc = try_launch_bwd_fast<T, VEC, DSNT_REG_NONE>(p, stream); break;
+          case DSNT_REG_VAR: rc = try_launch_bwd_fast<T, VEC, DSNT_REG_VAR>(p, stream); break;
+          case DSNT_REG_KL: rc = try_launch_bwd_fast<T, VEC, DSNT_REG_KL>(p, stream); break;
+          case DSNT_REG_JS: rc = try_launch_bwd_fast<T, VEC, DSNT_REG_JS>(p, stream); break;
+          case DSNT_REG_MSE: rc = try_launch_bwd_fast<T, VEC, DSNT_REG_MSE>(p, stream); break;
+        }
+        if (rc != 1) return rc;
+      }
+      if (variant == 0 || variant == 3) {
         switch (p.reg) {
           case DSNT_REG_NONE: return launch_bwd_stream<T, VEC, DSNT_REG_NONE>(p, stream);
           case DSNT_REG_VAR: return launch_bwd_stream<T, VEC, DSNT_REG_VAR>(p, stream);

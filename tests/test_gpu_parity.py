@@ -141,10 +141,11 @@ def test_assorted_sizes_js_and_var(dp, tp, shape):
 
 
 @pytest.mark.parametrize('reg', REGS)
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1, 2, 3])
 def test_alternative_kernels_agree_with_oracle(dp, tp, reg, variant):
-    """variant=1 forces the two-pass L2 kernel, variant=2 the register-resident kernels (forward and backward)
-    on a 64x64 map; the default (variant 0) is the streaming/windowed path.  All must match the oracle."""
+    """variant=1 forces the two-pass L2 kernel, variant=2 the register-resident kernels (forward and backward),
+    variant=3 the generic streaming kernels (head_stream.cuh) on a 64x64 map; the default (variant 0) is the
+    tuned fast path (head_fast.cuh).  All must match the oracle."""
     z, target, mask = synth(4, 4, 64, 64, 3.0, seed=4)
     l64, c64, d64 = oracle(tp, z, target, mask, reg)
     check(run_head(dp, z, target, mask, reg, variant=variant), l64, c64, d64, 'variant %d 64x64 %s' % (variant, reg))
@@ -167,6 +168,27 @@ def test_gaussian_window_is_exact_for_any_sigma_and_target(dp, tp, reg, hm_sigma
     l64, c64, d64 = oracle(tp, z, target, mask, reg, hm_sigma=hm_sigma)
     check(run_head(dp, z, target, mask, reg, hm_sigma=hm_sigma), l64, c64, d64,
           'window %s sigma=%g %s' % (reg, hm_sigma, where))
+
+
+@pytest.mark.parametrize('reg', ['kl', 'js', 'mse'])
+@pytest.mark.parametrize('shape,hm_sigma', [((2, 3, 64, 64), 1.0), ((2, 3, 64, 64), 2.5), ((1, 2, 128, 128), 1.0),
+                                            ((1, 2, 256, 256), 1.0), ((1, 2, 256, 256), 3.0), ((3, 2, 32, 32), 0.7),
+                                            ((2, 2, 48, 64), 1.0)])
+def test_fast_path_stash_and_fallback(dp, tp, reg, shape, hm_sigma):
+    """The tuned kernels stash the Gaussian window in shared memory; a window that does not fit (large sigma)
+    takes their global-memory fallback.  Both must match the dense reference arithmetic, fp32 and bf16."""
+    z, target, mask = synth(*shape, 2.0, seed=21, trained=(hm_sigma == 1.0 and shape[-1] == 64), tp=tp)
+    l64, c64, d64 = oracle(tp, z, target, mask, reg, hm_sigma=hm_sigma)
+    check(run_head(dp, z, target, mask, reg, hm_sigma=hm_sigma), l64, c64, d64,
+          'fast %s %s sigma=%g' % (shape, reg, hm_sigma))
+    zb = z.to(torch.bfloat16)
+    l64, c64, d64 = oracle(tp, zb.float(), target, mask, reg, hm_sigma=hm_sigma)
+    zz = zb.to(DEV).requires_grad_(True)
+    out = dp.dsnt_head(zz, target.to(DEV), mask.to(DEV), reg=reg, hm_sigma=hm_sigma)
+    out.loss.backward()
+    got = {'loss': out.loss.item(), 'coords': out.coords.detach().cpu().double().numpy(),
+           'dz': zz.grad.float().cpu().double().numpy()}
+    check(got, l64, c64, d64, 'fast bf16 %s %s sigma=%g' % (shape, reg, hm_sigma), dz_tol=4e-3)
 
 
 def test_unaligned_base_pointer_takes_scalar_path(dp, tp):
