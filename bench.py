@@ -30,6 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+RESULT_OUT = sys.stdout
 METRIC = 'dsnt_head_heatmaps_per_sec'
 UNIT = 'heatmaps/s'
 WORKLOADS = {
@@ -135,6 +136,32 @@ class ClockSampler:
                 'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def leave(world, dist, torch):
+    """End of a multi-rank run: flush, meet the other ranks once, and leave WITHOUT tearing NCCL down.
+    destroy_process_group() with a live CUDA graph that captured an NCCL kernel blocked for minutes on the
+    2-GPU box (the communicator waits for work the graph still owns); the process is ending anyway."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:          # noqa: BLE001
+            pass
+        os._exit(0)
+
+
+def start_watchdog(seconds):
+    """A bench run that has not finished after `seconds` is stuck: exit loudly instead of holding the GPU box."""
+    def bark():
+        sys.stderr.write('bench.py: watchdog fired after %d s, exiting\n' % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+    timer = threading.Timer(seconds, bark)
+    timer.daemon = True
+    timer.start()
+
+
 def launches_per_step(step, lib):
     """Kernels of ours enqueued by one step (counted on an eager call; a graph replay launches the same set)."""
     before = lib.launch_count
@@ -213,7 +240,8 @@ def main_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT)
+    RESULT_OUT.flush()
     return 0
 
 
@@ -358,9 +386,7 @@ def main_ours(args):
                        'dL/dZ stays on the device for the backbone backward'}
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        leave(world, dist, torch)
         return 0
 
     # ---------------- roofline of the dominant kernel (live CUDA-event durations from the timed region)
@@ -401,13 +427,23 @@ def main_ours(args):
         'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks, 'e2e': e2e,
         'gpu_launches': launches,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    print(json.dumps(line), file=RESULT_OUT)
+    RESULT_OUT.flush()
+    leave(world, dist, torch)
     return 0
+
+
+def claim_stdout():
+    """Keep file descriptor 1 for the ONE JSON line: libraries (NCCL prints its version banner to stdout) write to
+    stderr from here on; returns the stream the result line is printed to."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, 'w')
 
 
 if __name__ == '__main__':
     a = parse_args()
+    start_watchdog(900)
+    RESULT_OUT = claim_stdout()
     sys.exit(main_reference(a) if a.impl == 'reference' else main_ours(a))
