@@ -29,6 +29,12 @@ SIGNATURES = {
     'dsnt_head_bwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
                                _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int,
                                _c_ptr, _c_int, _c_ptr]),
+    'dsnt_head_fwd_stacked': (_c_int, [_c_ptr, _c_int, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_int, _c_float,
+                                       _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]),
+    'dsnt_head_bwd_stacked': (_c_int, [_c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr,
+                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int,
+                                       _c_int, _c_ptr]),
+    'dsnt_finish_loss_stacked': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_finish_workspace_bytes': (_c_int, []),
     'dsnt_finish_loss': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_combine_loss': (_c_int, [_c_ptr, _c_float, _c_ptr]),
@@ -88,6 +94,14 @@ def call(name, *args, launches=1):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+MAX_STACKS = 16
+
+
+def ptr_array(tensors):
+    """Host array of device pointers for the *_stacked entry points."""
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def stream_of(t):

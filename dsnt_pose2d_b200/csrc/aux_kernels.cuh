@@ -34,8 +34,11 @@ __device__ __forceinline__ void write_loss_tail(float* out, float reg_coeff) {
   out[3] = den; out[4] = eu; out[5] = rg; out[6] = fmaf(reg_coeff, rg, eu); out[7] = 0.f;
 }
 
+// Stacked form: terms holds n = count*n_per rows (stack-major); the mask (one stack long) is shared, the mask
+// count -- the denominator of every per-stack average -- is taken over the first stack only, so
+// out[6] = sum_s (euclid_s + reg_coeff*reg_s) as in src/dsnt/model.py:238-246.
 __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* __restrict__ terms,
-                                                                  const float* __restrict__ mask, long n,
+                                                                  const float* __restrict__ mask, long n, long n_per,
                                                                   float reg_coeff, float* __restrict__ out,
                                                                   float* __restrict__ workspace) {
   __shared__ float red[4 * kFinishBlock / 32];
@@ -45,10 +48,10 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
   float sd = 0.f, sr = 0.f, sm = 0.f, unused = 0.f;
   for (long i = lo + threadIdx.x; i < hi; i += kFinishBlock) {
     const float2 t = __ldg(reinterpret_cast<const float2*>(terms) + i);
-    const float w = mask ? __ldg(mask + i) : 1.0f;
+    const float w = mask ? __ldg(mask + (i % n_per)) : 1.0f;
     sd = fmaf(w, t.x, sd);
     sr = fmaf(w, t.y, sr);
-    sm += w;
+    if (i < n_per) sm += w;
   }
   block_sum4<kFinishBlock>(sd, sr, sm, unused, red);
   unsigned* ticket = reinterpret_cast<unsigned*>(workspace + kFinishMaxCtas * 4);

@@ -60,9 +60,32 @@ DSNT_API int dsnt_b200_version(void) { return DSNT_B200_VERSION; }
 
 DSNT_API const char* dsnt_b200_last_error(void) { return g_err; }
 
-DSNT_API int dsnt_head_fwd(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* target, int reg,
-                  float sigma, float* coords, float* stats, float* terms, int variant, void* stream) {
-  int rc = check_common(z, dtype, n, H, W, reg);
+// Fills the stack view (byte offsets relative to stack 0) and returns the widest vector every stack allows.
+static int fill_stacks(Stacks& st, const void* const* z, void* const* dz, int n_stacks, long n_per, int dtype, int W,
+                       bool need_z, int& vec) {
+  if (n_stacks < 1 || n_stacks > kMaxStacks) { set_error("n_stacks must be in [1, %d], got %d", kMaxStacks, n_stacks); return DSNT_ERR_BAD_ARG; }
+  st.count = n_stacks;
+  st.n_per = n_per;
+  vec = 8;
+  for (int s = 0; s < kMaxStacks; ++s) { st.z_off[s] = 0; st.dz_off[s] = 0; }
+  for (int s = 0; s < n_stacks; ++s) {
+    const void* zs = z ? z[s] : nullptr;
+    void* ds = dz ? dz[s] : nullptr;
+    if ((need_z && !zs) || (dz && !ds)) { set_error("null heatmap pointer (stack %d)", s); return DSNT_ERR_BAD_ARG; }
+    if (zs) st.z_off[s] = static_cast<const char*>(zs) - static_cast<const char*>(z[0]);
+    if (ds) st.dz_off[s] = static_cast<char*>(ds) - static_cast<char*>(dz[0]);
+    const int v = pick_vec(dtype, W, dz ? static_cast<const void*>(ds) : zs, dz && need_z ? zs : nullptr);
+    if (v < vec) vec = v;
+  }
+  return DSNT_OK;
+}
+
+DSNT_API int dsnt_head_fwd_stacked(const void* const* z, int n_stacks, int dtype, int input_is_logits, long n_per_stack,
+                                   int H, int W, const float* target, int reg, float sigma, float* coords, float* stats,
+                                   float* terms, int variant, void* stream) {
+  if (!z) { set_error("null pointer array"); return DSNT_ERR_BAD_ARG; }
+  const long n = n_per_stack * static_cast<long>(n_stacks > 0 ? n_stacks : 1);
+  int rc = check_common(n_per_stack == 0 ? reinterpret_cast<const void*>(1) : z[0], dtype, n, H, W, reg);
   if (rc) return rc;
   if (n == 0) return DSNT_OK;
   if (!coords) { set_error("coords output is required"); return DSNT_ERR_BAD_ARG; }
@@ -72,21 +95,32 @@ DSNT_API int dsnt_head_fwd(const void* z, int dtype, int input_is_logits, long n
     set_error("per-heatmap buffers must be naturally aligned (coords/terms/target 8 B, stats 16 B)");
     return DSNT_ERR_BAD_ARG;
   }
-  if (n == 0) return DSNT_OK;
   HeadFwdParams p;
-  p.z = z; p.target = target; p.coords = coords; p.stats = stats; p.terms = terms;
+  p.z = z[0]; p.target = target; p.coords = coords; p.stats = stats; p.terms = terms;
   p.n = n; p.H = H; p.W = W; p.reg = reg; p.sigma = sigma;
-  const int vec = pick_vec(dtype, W, z, nullptr);
+  int vec = 1;
+  rc = fill_stacks(p.st, z, nullptr, n_stacks, n_per_stack, dtype, W, true, vec);
+  if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dtype == DSNT_DTYPE_F32 ? launch_head_fwd_f32(p, vec, input_is_logits != 0, variant, s)
                                  : launch_head_fwd_bf16(p, vec, input_is_logits != 0, variant, s);
 }
 
-DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* target,
-                  const float* mask, const float* stats, const float* g_coords, const float* g_reg,
-                  const float* g_loss, const float* denom, float reg_coeff, int reg, float sigma, int flags, void* dz,
-                  int variant, void* stream) {
-  int rc = check_common(dz, dtype, n, H, W, reg);
+DSNT_API int dsnt_head_fwd(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* target, int reg,
+                  float sigma, float* coords, float* stats, float* terms, int variant, void* stream) {
+  if (!z && n != 0) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
+  const void* zs[1] = {z};
+  return dsnt_head_fwd_stacked(zs, 1, dtype, input_is_logits, n, H, W, target, reg, sigma, coords, stats, terms, variant, stream);
+}
+
+DSNT_API int dsnt_head_bwd_stacked(const void* const* z, void* const* dz, int n_stacks, int dtype, int input_is_logits,
+                                   long n_per_stack, int H, int W, const float* target, const float* mask,
+                                   const float* stats, const float* g_coords, const float* g_reg, const float* g_loss,
+                                   const float* denom, float reg_coeff, int reg, float sigma, int flags, int variant,
+                                   void* stream) {
+  if (!dz) { set_error("null pointer array"); return DSNT_ERR_BAD_ARG; }
+  const long n = n_per_stack * static_cast<long>(n_stacks > 0 ? n_stacks : 1);
+  int rc = check_common(n_per_stack == 0 ? reinterpret_cast<const void*>(1) : dz[0], dtype, n, H, W, reg);
   if (rc) return rc;
   if (n == 0) return DSNT_OK;
   const bool need_z = input_is_logits || reg_needs_gauss(reg);
@@ -99,29 +133,49 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
     set_error("per-heatmap buffers must be naturally aligned (target/g_coords 8 B, stats 16 B)");
     return DSNT_ERR_BAD_ARG;
   }
-  if (n == 0) return DSNT_OK;
   HeadBwdParams p;
-  p.z = z; p.target = target; p.mask = mask; p.stats = stats; p.g_coords = g_coords; p.g_reg = g_reg;
-  p.g_loss = g_loss; p.denom = denom; p.dz = dz; p.n = n; p.H = H; p.W = W; p.reg = reg; p.flags = flags;
+  p.z = need_z ? z[0] : nullptr; p.target = target; p.mask = mask; p.stats = stats; p.g_coords = g_coords; p.g_reg = g_reg;
+  p.g_loss = g_loss; p.denom = denom; p.dz = dz[0]; p.n = n; p.H = H; p.W = W; p.reg = reg; p.flags = flags;
   p.sigma = sigma; p.reg_coeff = reg_coeff;
-  const int vec = pick_vec(dtype, W, dz, need_z ? z : nullptr);
+  int vec = 1;
+  rc = fill_stacks(p.st, need_z ? z : nullptr, dz, n_stacks, n_per_stack, dtype, W, need_z, vec);
+  if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dtype == DSNT_DTYPE_F32 ? launch_head_bwd_f32(p, vec, input_is_logits != 0, variant, s)
                                  : launch_head_bwd_bf16(p, vec, input_is_logits != 0, variant, s);
 }
 
+DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* target,
+                  const float* mask, const float* stats, const float* g_coords, const float* g_reg,
+                  const float* g_loss, const float* denom, float reg_coeff, int reg, float sigma, int flags, void* dz,
+                  int variant, void* stream) {
+  if (!dz && n != 0) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
+  const void* zs[1] = {z};
+  void* dzs[1] = {dz};
+  return dsnt_head_bwd_stacked(z ? zs : nullptr, dzs, 1, dtype, input_is_logits, n, H, W, target, mask, stats, g_coords,
+                               g_reg, g_loss, denom, reg_coeff, reg, sigma, flags, variant, stream);
+}
+
 DSNT_API int dsnt_finish_workspace_bytes(void) { return static_cast<int>(sizeof(float) * kFinishWorkspaceFloats); }
 
-DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, float reg_coeff, float* out, float* workspace,
-                     void* stream) {
-  if ((!terms && n > 0) || !out || !workspace || n < 0) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
+DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
+                                      float* out, float* workspace, void* stream) {
+  if (n_stacks < 1 || n_per_stack < 0) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  const long n = n_per_stack * n_stacks;
+  if ((!terms && n > 0) || !out || !workspace) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
   if (!aligned(terms, 8) || !aligned(workspace, 16)) { set_error("dsnt_finish_loss: misaligned buffers"); return DSNT_ERR_BAD_ARG; }
   long ctas = (n + 1023) / 1024;  // >= 4 heatmaps per thread before adding CTAs
   if (ctas < 1) ctas = 1;
   if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
   finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      terms, mask, n, reg_coeff, out, workspace);
+      terms, mask, n, n_per_stack > 0 ? n_per_stack : 1, reg_coeff, out, workspace);
   return check_launch("finish_loss_kernel");
+}
+
+DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, float reg_coeff, float* out, float* workspace,
+                     void* stream) {
+  if (n < 0) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  return dsnt_finish_loss_stacked(terms, mask, n, 1, reg_coeff, out, workspace, stream);
 }
 
 DSNT_API int dsnt_combine_loss(float* out, float reg_coeff, void* stream) {

@@ -20,6 +20,36 @@ constexpr float kEps = 1e-24f;  // src/dsnt/nn.py:202,208,214
 
 constexpr int kStatsK = DSNT_STATS_K;
 
+// ---------------------------------------------------------------------------------- stacked launches
+// A stacked-hourglass model emits one heatmap tensor per stack (src/dsnt/hourglass.py:166-177), all with the same
+// shape, target and mask (src/dsnt/model.py:238-246).  One launch covers every stack: heatmap index hm runs over
+// count*n_per, stack s = hm / n_per lives at byte offset z_off[s] from stack 0.  Per-heatmap inputs shared by the
+// stacks (target, mask) are indexed by the position inside the stack, outputs (coords, stats, terms) by hm.
+constexpr int kMaxStacks = DSNT_MAX_STACKS;
+struct Stacks {
+  long n_per;                 // heatmaps per stack
+  long z_off[kMaxStacks];     // byte offsets of the logits of stack s relative to stack 0
+  long dz_off[kMaxStacks];    // same for the gradient output (backward only)
+  int count;
+};
+struct HmRef {
+  long nl;                    // index inside the stack (target / mask)
+  long z_bytes, dz_bytes;     // byte offsets of this heatmap from the stack-0 base pointers
+};
+__device__ __forceinline__ HmRef locate(const Stacks& st, long hm, long hm_bytes) {
+  HmRef r;
+  if (st.count <= 1) {
+    r.nl = hm; r.z_bytes = hm * hm_bytes; r.dz_bytes = r.z_bytes;
+  } else {
+    const unsigned h = static_cast<unsigned>(hm), per = static_cast<unsigned>(st.n_per);
+    const unsigned s = h / per;
+    r.nl = h - s * per;
+    r.z_bytes = st.z_off[s] + r.nl * hm_bytes;
+    r.dz_bytes = st.dz_off[s] + r.nl * hm_bytes;
+  }
+  return r;
+}
+
 // ---------------------------------------------------------------------------------- MUFU wrappers
 __device__ __forceinline__ float ex2(float x) {
   float y;

@@ -31,6 +31,7 @@ struct HeadBwdParams {
   int reg;
   int flags;
   float sigma, reg_coeff;
+  Stacks st;
 };
 
 // Everything a thread needs to know about its heatmap (uniform across the group).
@@ -45,7 +46,7 @@ struct BwdScalars {
 };
 
 template <bool LOGITS>
-__device__ __forceinline__ BwdScalars load_bwd_scalars(const HeadBwdParams& p, long hm, int reg) {
+__device__ __forceinline__ BwdScalars load_bwd_scalars(const HeadBwdParams& p, long hm, long nl, int reg) {
   BwdScalars s;
   const float4* st = reinterpret_cast<const float4*>(p.stats + hm * kStatsK);
   const float4 s0 = __ldg(st), s1 = __ldg(st + 1);
@@ -54,13 +55,13 @@ __device__ __forceinline__ BwdScalars load_bwd_scalars(const HeadBwdParams& p, l
   s.ginv = s1.w;
   s.tx = 0.f; s.ty = 0.f;
   if (p.target) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + nl);
     s.tx = t.x; s.ty = t.y;
   }
   float a = 0.f, b = 0.f, rho = 0.f;
   if (p.g_loss) {
     const float gl = __ldg(p.g_loss);
-    const float w = __fdividef(p.mask ? __ldg(p.mask + hm) : 1.0f, __ldg(p.denom));
+    const float w = __fdividef(p.mask ? __ldg(p.mask + nl) : 1.0f, __ldg(p.denom));
     if (p.target && !(p.flags & DSNT_FLAG_NO_EUCLID)) {
       const float dx = s.mux - s.tx, dy = s.muy - s.ty;
       const float d2 = dx * dx + dy * dy;
@@ -104,9 +105,9 @@ __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_bwd_kernel(co
   const int H = p.H, W = p.W;
   const int wv = W / VEC, nvec = H * wv;
   const int f0 = blockIdx.y * (GROUP * NV) + lane_g;
-  const long base = hm * static_cast<long>(H) * W;
-  const T* zb = static_cast<const T*>(p.z) + base;
-  T* dzb = static_cast<T*>(p.dz) + base;
+  const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
+  const T* zb = reinterpret_cast<const T*>(static_cast<const char*>(p.z) + ref.z_bytes);
+  T* dzb = reinterpret_cast<T*>(static_cast<char*>(p.dz) + ref.dz_bytes);
 
   const bool gauss = reg_needs_gauss(reg);
   const bool need_z = LOGITS || gauss;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_bwd_kernel(co
     }
   }
 
-  const BwdScalars s = load_bwd_scalars<LOGITS>(p, hm, reg);
+  const BwdScalars s = load_bwd_scalars<LOGITS>(p, hm, ref.nl, reg);
 
   // ---- Gaussian tables: tabx[j] = gx_j, taby[i] = gy_i * ginv (the forward saved the normaliser)
   float* tabx = dyn_smem + gid * table_floats(H, W);

@@ -145,11 +145,12 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
   if (hm >= p.n) return;  // GROUP == 32 only; the grid is exact otherwise
 
   const int H = p.H, W = p.W;
-  const char* zb = reinterpret_cast<const char*>(static_cast<const T*>(p.z) + hm * static_cast<long>(H) * W);
+  const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
+  const char* zb = static_cast<const char*>(p.z) + ref.z_bytes;
 
   float tx = 0.f, ty = 0.f;
   if (p.target) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + ref.nl);
     tx = t.x; ty = t.y;
   }
 
@@ -434,11 +435,11 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_fast_k
   if (hm >= p.n) return;  // GROUP == 32 only
 
   const int H = p.H, W = p.W;
-  const long base = hm * static_cast<long>(H) * W;
-  const char* src = reinterpret_cast<const char*>(static_cast<const T*>(p.z) + base) + static_cast<size_t>(lane_g) * 16;
-  char* dst = reinterpret_cast<char*>(static_cast<T*>(p.dz) + base) + static_cast<size_t>(lane_g) * 16;
+  const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
+  const char* src = static_cast<const char*>(p.z) + ref.z_bytes + static_cast<size_t>(lane_g) * 16;
+  char* dst = static_cast<char*>(p.dz) + ref.dz_bytes + static_cast<size_t>(lane_g) * 16;
 
-  const BwdScalars s = load_bwd_scalars<true>(p, hm, REG);
+  const BwdScalars s = load_bwd_scalars<true>(p, hm, ref.nl, REG);
 
   // constant part of (g - c):  -c, plus the out-of-window value of rho*r
   float cbase = -s.c;
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_fast_k
   // ---- epilogue: the pixels where the Gaussian matters
   if constexpr (kWin) {
     if (win.empty()) return;     // uniform over the group
-    T* dzb = static_cast<T*>(p.dz) + base;
+    T* dzb = reinterpret_cast<T*>(static_cast<char*>(p.dz) + ref.dz_bytes);
 
     auto pixel = [&](float z, float G, float x, float y) -> float {
       const float t = fmaf(z, kLog2e, -s.m2);
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_fast_k
       // window too large for the stash: the loop stored the out-of-window value everywhere; overwrite the
       // window pixels (ordered after the loop's stores by the barrier), lane <-> column
       if constexpr (GROUP == 32) __syncwarp(); else __syncthreads();
-      const T* zt = static_cast<const T*>(p.z) + base;
+      const T* zt = reinterpret_cast<const T*>(static_cast<const char*>(p.z) + ref.z_bytes);
       constexpr int NW = GROUP / 32;
       for (int j0 = win.j_lo; j0 <= win.j_hi; j0 += 32) {
         const int j = j0 + lane;

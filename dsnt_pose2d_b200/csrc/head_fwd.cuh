@@ -33,10 +33,11 @@ struct HeadFwdParams {
   float* coords;        // [N,2]
   float* stats;         // [N,8] or null
   float* terms;         // [N,2] or null
-  long n;
+  long n;               // heatmaps in this launch (all stacks)
   int H, W;
   int reg;              // used only by REG < 0 (dynamic) instantiations
   float sigma;
+  Stacks st;
 };
 
 constexpr int kWarpPathBlock = 128;  // 4 heatmaps per CTA on the warp-per-heatmap path
@@ -218,7 +219,8 @@ __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_fwd_kernel(co
 
   const int H = p.H, W = p.W;
   const int wv = W / VEC, nvec = H * wv;
-  const T* zb = static_cast<const T*>(p.z) + hm * static_cast<long>(H) * W;
+  const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
+  const T* zb = reinterpret_cast<const T*>(static_cast<const char*>(p.z) + ref.z_bytes);
 
   // ---- 1. issue every load of this thread up front (NV x 128-bit in flight per thread)
   float v[NV][VEC];
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_fwd_kernel(co
 
   float tx = 0.f, ty = 0.f;
   if (p.target) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + ref.nl);
     tx = t.x; ty = t.y;
   }
 
@@ -337,11 +339,12 @@ __global__ void __launch_bounds__(kLargeBlock) head_fwd_large_kernel(const HeadF
   const long hm = blockIdx.x;
   const int H = p.H, W = p.W;
   const int wv = W / VEC, nvec = H * wv;
-  const T* zb = static_cast<const T*>(p.z) + hm * static_cast<long>(H) * W;
+  const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
+  const T* zb = reinterpret_cast<const T*>(static_cast<const char*>(p.z) + ref.z_bytes);
 
   float tx = 0.f, ty = 0.f;
   if (p.target) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + ref.nl);
     tx = t.x; ty = t.y;
   }
   float* tabx = dyn_smem;

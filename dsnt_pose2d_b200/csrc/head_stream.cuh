@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
 
   const int H = p.H, W = p.W;
   const int nvec = g.nvec;
-  const T* zb = static_cast<const T*>(p.z) + hm * static_cast<long>(H) * W;
+  const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
+  const T* zb = reinterpret_cast<const T*>(static_cast<const char*>(p.z) + ref.z_bytes);
 
   // ---- per-thread geometry
   float xs[VEC];
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
 
   float tx = 0.f, ty = 0.f;
   if (p.target) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p.target) + ref.nl);
     tx = t.x; ty = t.y;
   }
 
@@ -384,11 +385,11 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_stream
 
   const int H = p.H, W = p.W;
   const int nvec = g.nvec;
-  const long base = hm * static_cast<long>(H) * W;
-  const T* zb = static_cast<const T*>(p.z) + base;
-  T* dzb = static_cast<T*>(p.dz) + base;
+  const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
+  const T* zb = reinterpret_cast<const T*>(static_cast<const char*>(p.z) + ref.z_bytes);
+  T* dzb = reinterpret_cast<T*>(static_cast<char*>(p.dz) + ref.dz_bytes);
 
-  const BwdScalars s = load_bwd_scalars<true>(p, hm, REG);
+  const BwdScalars s = load_bwd_scalars<true>(p, hm, ref.nl, REG);
   Window win{1, 0, 1, 0};
   if constexpr (kGauss) win = make_window(g, H, W, s.tx, s.ty);
 

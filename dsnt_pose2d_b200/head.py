@@ -143,14 +143,93 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     return HeadOutput(coords, loss, out8[4], out8[5])
 
 
-def dsnt_head_stacked(zs, target, mask=None, **kwargs):
-    """Hourglass form (src/dsnt/model.py:233-246,286-292): one head per stack, losses summed.
+class _FusedHeadStacked(torch.autograd.Function):
+    """All hourglass stacks in ONE forward launch, one finishing reduction and ONE backward launch
+    (dsnt_head_fwd_stacked / dsnt_finish_loss_stacked / dsnt_head_bwd_stacked, include/dsnt_b200.h)."""
 
-    Returns (list of coords per stack, total loss)."""
-    total = None
-    coords = []
+    @staticmethod
+    def forward(ctx, target, mask, reg_id, sigma, reg_coeff, flags, group, variant, aux, *zs):
+        flat = [_flat_heatmaps(z) for z in zs]
+        zcs = [f[0] for f in flat]
+        n, h, w = flat[0][1], flat[0][2], flat[0][3]
+        s_count = len(zcs)
+        dev = zcs[0].device
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zcs[0])
+            coords = torch.empty(s_count, n, 2, dtype=torch.float32, device=dev)
+            stats = torch.empty(s_count * n, _lib.STATS_K, dtype=torch.float32, device=dev)
+            terms = torch.empty(s_count * n, 2, dtype=torch.float32, device=dev)
+            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            _lib.call('dsnt_head_fwd_stacked', _lib.ptr_array(zcs), s_count, _lib.dtype_id(zcs[0]), 1, n, h, w,
+                      _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(),
+                      variant, stream)
+            ws = _lib.finish_workspace(dev)
+            _lib.call('dsnt_finish_loss_stacked', terms.data_ptr(), _lib.ptr(mask), n, s_count, reg_coeff,
+                      out8.data_ptr(), ws.data_ptr(), stream)
+            if group is not None:
+                all_reduce_sums(out8, group)
+                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+        ctx.save_for_backward(target, mask, stats, out8, *zcs)
+        ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, variant, [z.shape for z in zs])
+        ctx.set_materialize_grads(False)
+        aux['out8'] = out8
+        lead = zs[0].shape[:-2]
+        return (out8[6],) + tuple(coords[i].view(*lead, 2) for i in range(s_count))
+
+    @staticmethod
+    def backward(ctx, g_loss, *g_coords):
+        target, mask, stats, out8 = ctx.saved_tensors[:4]
+        zcs = ctx.saved_tensors[4:]
+        n, h, w, reg_id, sigma, reg_coeff, flags, variant, shapes = ctx.meta
+        s_count = len(zcs)
+        dev = zcs[0].device
+        if g_loss is None and all(g is None for g in g_coords):
+            return (None,) * (9 + s_count)
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zcs[0])
+            gc = None
+            if any(g is not None for g in g_coords):
+                gc = torch.zeros(s_count, n, 2, dtype=torch.float32, device=dev)
+                for i, g in enumerate(g_coords):
+                    if g is not None:
+                        gc[i] = g.reshape(n, 2).to(torch.float32)
+            if g_loss is not None:
+                g_loss = g_loss.to(torch.float32).contiguous()
+            dzs = [torch.empty_like(z) for z in zcs]
+            _lib.call('dsnt_head_bwd_stacked', _lib.ptr_array(zcs), _lib.ptr_array(dzs), s_count,
+                      _lib.dtype_id(zcs[0]), 1, n, h, w, _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(),
+                      _lib.ptr(gc), None, _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
+                      reg_coeff, reg_id, sigma, flags, variant, stream)
+        return (None,) * 9 + tuple(dz.view(shape) for dz, shape in zip(dzs, shapes))
+
+
+def dsnt_head_stacked(zs, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_sigma=None, group=None,
+                      variant=0):
+    """Hourglass form (src/dsnt/model.py:233-246,286-292): every stack's head evaluated by one launch, losses summed.
+
+    zs: list of logits tensors [..., H, W] of identical shape/dtype (one per stack, as hourglass.py:166-177 returns).
+    Returns (list of coords per stack, total loss = sum_s euclid_s + reg_coeff * reg_s)."""
+    zs = list(zs)
+    if not zs:
+        raise ValueError('dsnt_head_stacked needs at least one stack')
+    if len(zs) > _lib.MAX_STACKS:
+        raise ValueError('at most %d stacks per call, got %d' % (_lib.MAX_STACKS, len(zs)))
     for z in zs:
-        out = dsnt_head(z, target, mask, **kwargs)
-        coords.append(out.coords)
-        total = out.loss if total is None else total + out.loss
-    return coords, total
+        _lib.require_cuda(z, 'z')
+        if z.shape != zs[0].shape or z.dtype != zs[0].dtype or z.device != zs[0].device:
+            raise ValueError('all stacks must share shape, dtype and device')
+    if reg not in _lib.REG_IDS:
+        raise ValueError('unrecognised regulariser: %r' % (reg,))
+    h, w = zs[0].shape[-2], zs[0].shape[-1]
+    n = zs[0].numel() // max(h * w, 1)
+    if sigma is None:
+        sigma = 2.0 * (1.0 if hm_sigma is None else hm_sigma) / w
+    if target is not None and target.requires_grad:
+        raise NotImplementedError('dsnt_head_stacked: gradients w.r.t. the target are not implemented')
+    target = _as_f32(target, n, 2, 'target')
+    mask = _as_f32(mask, n, 1, 'mask')
+    flags = _lib.FLAG_STRICT_NAN if STRICT_NAN else 0
+    aux = {}
+    out = _FusedHeadStacked.apply(target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff), flags, group,
+                                  int(variant), aux, *zs)
+    return list(out[1:]), out[0]

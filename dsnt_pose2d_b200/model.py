@@ -22,7 +22,8 @@ import torch
 from torch import nn
 
 from . import nn as dnn
-from .head import dsnt_head
+from . import _lib
+from .head import dsnt_head, dsnt_head_stacked
 
 _FUSED_PREACTS = ('softmax',)
 
@@ -72,10 +73,20 @@ class DSNTHead(nn.Module):
         self._coords.append(coords)
         return coords
 
+    def _stackable(self, zs):
+        return (self.preact in _FUSED_PREACTS and 1 < len(zs) <= _lib.MAX_STACKS
+                and all(z.shape == zs[0].shape and z.dtype == zs[0].dtype and z.device == zs[0].device for z in zs))
+
     def forward_part2(self, x):
         self._logits, self._coords, self._heatmaps = [], [], {}
         if isinstance(x, (list, tuple)):
-            return [self._part2_one(z) for z in x]
+            zs = list(x)
+            if self._stackable(zs):
+                # hourglass: every stack in ONE launch (src/dsnt/model.py:286-292 loops in Python)
+                coords, _ = dsnt_head_stacked(zs, None, None, reg='none')
+                self._logits, self._coords = zs, coords
+                return coords
+            return [self._part2_one(z) for z in zs]
         return self._part2_one(x)
 
     forward = forward_part2
@@ -110,6 +121,11 @@ class DSNTHead(nn.Module):
 
     def forward_loss(self, out_var, target_var, mask_var):
         if isinstance(out_var, (list, tuple)):
+            if (len(out_var) == len(self._coords) and self._stackable(self._logits)
+                    and all(o is c for o, c in zip(out_var, self._coords))):
+                # one fused forward over all stacks, one finishing reduction; backward is one launch too
+                return dsnt_head_stacked(self._logits, target_var, mask_var, reg=self.reg, hm_sigma=self.hm_sigma,
+                                         reg_coeff=self.reg_coeff, group=self.group)[1]
             total = 0
             for i, out in enumerate(out_var):          # sum over stacks (model.py:238-246)
                 total = total + self._loss_one(i, out, target_var, mask_var)

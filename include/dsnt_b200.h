@@ -45,6 +45,8 @@ extern "C" {
 #define DSNT_REG_MSE 4
 
 /* per-heatmap statistics saved by the forward for the reduction-free backward */
+#define DSNT_MAX_STACKS 16 /* stacks (hourglass outputs) one *_stacked call can cover */
+
 #define DSNT_STATS_K 8
 /*   logits input : [0] m*log2(e)  [1] 1/S   [2] mu_x [3] mu_y [4] v_x [5] v_y [6] c_reg = sum P r [7] Gaussian normaliser 1/(sum G^ + 1e-24)
  *   heatmap input: [0] sum P      [1] unused [2..7] as above                                                        */
@@ -98,6 +100,26 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
                   const float* g_coords, const float* g_reg, const float* g_loss, const float* denom,
                   float reg_coeff, int reg, float sigma, int flags,
                   void* dz, int variant, void* stream);
+
+/*
+ * Stacked-hourglass forms: ONE launch for all stacks.
+ *   replaces: the per-stack Python loops of HourglassHumanPoseModel.forward_part2 / forward_loss
+ *             (src/dsnt/model.py:238-246,286-292) over the list hourglass.py:166-177 returns.
+ *   z / dz    HOST arrays of n_stacks DEVICE pointers; every stack is [n_per_stack,H,W] of the same dtype
+ *   target, mask  [n_per_stack,...] shared by the stacks;  coords/stats/terms/g_coords/g_reg  [n_stacks*n_per_stack,...]
+ *   dsnt_finish_loss_stacked: out[6] = sum over stacks of (euclid_s + reg_coeff*reg_s); out[2], out[3] = mask count /
+ *   denominator of ONE stack (every stack shares it).  n_stacks <= DSNT_MAX_STACKS.
+ */
+DSNT_API int dsnt_head_fwd_stacked(const void* const* z, int n_stacks, int dtype, int input_is_logits, long n_per_stack,
+                                   int H, int W, const float* target, int reg, float sigma,
+                                   float* coords, float* stats, float* terms, int variant, void* stream);
+DSNT_API int dsnt_head_bwd_stacked(const void* const* z, void* const* dz, int n_stacks, int dtype, int input_is_logits,
+                                   long n_per_stack, int H, int W, const float* target, const float* mask,
+                                   const float* stats, const float* g_coords, const float* g_reg, const float* g_loss,
+                                   const float* denom, float reg_coeff, int reg, float sigma, int flags, int variant,
+                                   void* stream);
+DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, long n_per_stack, int n_stacks,
+                                      float reg_coeff, float* out, float* workspace, void* stream);
 
 /*
  * Deterministic finishing reduction over the per-heatmap terms (no float atomics, one launch).

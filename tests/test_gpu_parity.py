@@ -85,6 +85,32 @@ def test_stacked_hourglass_loss_matches_golden(dp, golden_stacked):
         assert rel_l2(z.grad.cpu().double().numpy(), g['dz%d' % i]) < TOL
 
 
+@pytest.mark.parametrize('reg', REGS)
+@pytest.mark.parametrize('shape,dtype', [((8, 2, 16, 64, 64), torch.float32), ((3, 2, 5, 28, 28), torch.float32),
+                                         ((2, 1, 3, 7, 7), torch.float32), ((4, 1, 4, 256, 256), torch.float32),
+                                         ((8, 2, 16, 64, 64), torch.bfloat16)])
+def test_stacked_launch_equals_per_stack_calls(dp, reg, shape, dtype):
+    """One launch over all hourglass stacks (cfg 3 has 8) must give exactly what the per-stack calls give:
+    same kernels, same per-heatmap arithmetic -- coords and dZ bitwise, the summed loss to rounding."""
+    stacks, b, c, h, w = shape
+    gen = torch.Generator().manual_seed(31)
+    zs = [(torch.randn(b, c, h, w, generator=gen) * 2).to(dtype).to(DEV) for _ in range(stacks)]
+    target = (torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8).to(DEV)
+    mask = (torch.rand(b, c, generator=gen) > 0.2).float().to(DEV)
+    wts = [torch.randn(b, c, 2, generator=gen).to(DEV) for _ in range(stacks)]
+    za = [z.clone().requires_grad_(True) for z in zs]
+    coords_a, total_a = dp.dsnt_head_stacked(za, target, mask, reg=reg, hm_sigma=1.0, reg_coeff=0.7)
+    (total_a + sum((ca * wt).sum() for ca, wt in zip(coords_a, wts))).backward()
+    zb = [z.clone().requires_grad_(True) for z in zs]
+    outs = [dp.dsnt_head(z, target, mask, reg=reg, hm_sigma=1.0, reg_coeff=0.7) for z in zb]
+    total_b = sum(o.loss for o in outs)
+    (total_b + sum((o.coords * wt).sum() for o, wt in zip(outs, wts))).backward()
+    assert abs(total_a.item() - total_b.item()) <= 2e-6 * abs(total_b.item())
+    for i in range(stacks):
+        assert torch.equal(coords_a[i], outs[i].coords), i
+        assert torch.equal(za[i].grad, zb[i].grad), i
+
+
 # ------------------------------------------------------------------------------------------- synthetic, BASELINE shapes
 def synth(b, c, h, w, scale, seed=0, trained=False, tp=None):
     gen = torch.Generator().manual_seed(seed)
