@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libdsnt_b200.so')
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 REG_IDS = {'none': 0, 'var': 1, 'kl': 2, 'js': 3, 'mse': 4}
+PREACT_IDS = {'softmax': 0, 'thresholded_softmax': 1, 'abs': 2, 'relu': 3, 'sigmoid': 4}
 STATS_K = 8
 FLAG_STRICT_NAN = 1
 FLAG_NO_EUCLID = 2
@@ -34,6 +35,11 @@ SIGNATURES = {
     'dsnt_head_bwd_stacked': (_c_int, [_c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr,
                                        _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int,
                                        _c_int, _c_ptr]),
+    'dsnt_head_preact_fwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_float, _c_float, _c_long, _c_int, _c_int, _c_ptr, _c_int,
+                                      _c_float, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    'dsnt_head_preact_bwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_float, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
+                                      _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int, _c_ptr,
+                                      _c_ptr]),
     'dsnt_finish_loss_stacked': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_finish_workspace_bytes': (_c_int, []),
     'dsnt_finish_loss': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_float, _c_ptr, _c_ptr, _c_ptr]),

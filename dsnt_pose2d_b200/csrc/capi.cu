@@ -5,6 +5,7 @@
 
 #include "aux_kernels.cuh"
 #include "launch.cuh"
+#include "capi_util.cuh"
 
 namespace dsnt {
 
@@ -23,30 +24,6 @@ int check_launch(const char* what) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return DSNT_ERR_LAUNCH;
   }
-  return DSNT_OK;
-}
-
-static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
-
-// Widest vector the layout allows: a vector must not straddle a row (W % VEC == 0) and every heatmap
-// base must be VEC*sizeof aligned (then H*W*sizeof is a multiple of it as well).
-static int pick_vec(int dtype, int W, const void* a, const void* b) {
-  if (dtype == DSNT_DTYPE_F32) {
-    if (W % 4 == 0 && aligned(a, 16) && (!b || aligned(b, 16))) return 4;
-    return 1;
-  }
-  if (W % 8 == 0 && aligned(a, 16) && (!b || aligned(b, 16))) return 8;
-  if (W % 4 == 0 && aligned(a, 8) && (!b || aligned(b, 8))) return 4;
-  return 1;
-}
-
-static int check_common(const void* z, int dtype, long n, int H, int W, int reg) {
-  if (!z && n != 0) { set_error("null heatmap pointer"); return DSNT_ERR_BAD_ARG; }
-  if (dtype != DSNT_DTYPE_F32 && dtype != DSNT_DTYPE_BF16) { set_error("unsupported dtype %d (fp32 and bf16 only)", dtype); return DSNT_ERR_UNSUPPORTED; }
-  if (n < 0 || H <= 0 || W <= 0) { set_error("bad shape n=%ld H=%d W=%d", n, H, W); return DSNT_ERR_BAD_ARG; }
-  if (static_cast<long>(H) * W > (1L << 28)) { set_error("heatmap %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
-  if (n > 0x7fffffffL) { set_error("too many heatmaps: %ld", n); return DSNT_ERR_UNSUPPORTED; }
-  if (reg < DSNT_REG_NONE || reg > DSNT_REG_MSE) { set_error("bad reg %d", reg); return DSNT_ERR_BAD_ARG; }
   return DSNT_OK;
 }
 

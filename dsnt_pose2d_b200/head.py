@@ -107,8 +107,67 @@ class _FusedHead(torch.autograd.Function):
         return (dz.view(shape),) + (None,) * 10
 
 
+class _FusedHeadPreact(torch.autograd.Function):
+    """The fused head for the reference's other pre-activations (src/dsnt/model.py:31-41):
+    forward: dsnt_head_preact_fwd + dsnt_finish_loss;  backward: dsnt_head_preact_bwd (include/dsnt_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, preact_id, threshold, eps, aux):
+        zc, n, h, w = _flat_heatmaps(z)
+        dev = zc.device
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zc)
+            coords = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            stats = torch.empty(n, _lib.STATS_K, dtype=torch.float32, device=dev)
+            terms = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            _lib.call('dsnt_head_preact_fwd', zc.data_ptr(), _lib.dtype_id(zc), preact_id, threshold, eps, n, h, w,
+                      _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), stream)
+            ws = _lib.finish_workspace(dev)
+            _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, reg_coeff, out8.data_ptr(),
+                      ws.data_ptr(), stream)
+            if group is not None:
+                all_reduce_sums(out8, group)
+                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+        ctx.save_for_backward(zc, target, mask, stats, out8)
+        ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, z.shape)
+        ctx.set_materialize_grads(False)
+        aux['out8'] = out8
+        return coords.view(*z.shape[:-2], 2), out8[6]
+
+    @staticmethod
+    def backward(ctx, g_coords, g_loss):
+        zc, target, mask, stats, out8 = ctx.saved_tensors
+        n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, shape = ctx.meta
+        dev = zc.device
+        if g_coords is None and g_loss is None:
+            return (None,) * 12
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zc)
+            if g_coords is not None:
+                g_coords = g_coords.to(torch.float32).contiguous()
+            if g_loss is not None:
+                g_loss = g_loss.to(torch.float32).contiguous()
+            dz = torch.empty_like(zc)
+            _lib.call('dsnt_head_preact_bwd', zc.data_ptr(), _lib.dtype_id(zc), preact_id, threshold, n, h, w,
+                      _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(), _lib.ptr(g_coords), None,
+                      _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
+                      reg_coeff, reg_id, sigma, flags, dz.data_ptr(), stream)
+        return (dz.view(shape),) + (None,) * 11
+
+
+# what HumanPoseModel._hm_preact passes for each `--preact` choice (src/dsnt/model.py:29-41)
+PREACT_DEFAULTS = {
+    'softmax': (float('-inf'), 0.0),
+    'thresholded_softmax': (-0.5, 1e-12),
+    'abs': (0.0, 1e-12),
+    'relu': (0.0, 1e-12),
+    'sigmoid': (0.0, 1e-12),
+}
+
+
 def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_sigma=None, group=None,
-              variant=0, input_is_logits=True):
+              variant=0, input_is_logits=True, preact='softmax', threshold=None, eps=None):
     """Fused head.
 
     Args:
@@ -120,6 +179,9 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
             conversion sigma = 2*hm_sigma/W is applied (src/dsnt/model.py:49).
         reg_coeff: weight of the regulariser (src/dsnt/model.py:145).
         group: torch.distributed process group when the batch is sharded across ranks.
+        preact: how raw heatmaps become a distribution (src/dsnt/model.py:24-45): 'softmax' (the tuned kernels),
+            'thresholded_softmax', 'abs', 'relu', 'sigmoid' (the epsilon-exact kernels of csrc/head_preact.cuh).
+            `threshold` / `eps` default to what the reference passes (-0.5 / 1e-12).
     Returns:
         HeadOutput(coords [..., 2] float32, loss 0-dim float32, euclid 0-dim, reg 0-dim);
         `loss` and `coords` are differentiable w.r.t. `z`.
@@ -137,8 +199,19 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     mask = _as_f32(mask, n, 1, 'mask')
     flags = _lib.FLAG_STRICT_NAN if STRICT_NAN else 0
     aux = {}
-    coords, loss = _FusedHead.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
-                                    flags, group, int(variant), bool(input_is_logits), aux)
+    if preact not in _lib.PREACT_IDS:
+        raise Exception('unrecognised heatmap preactivation function: {}'.format(preact))   # model.py:42-43
+    if preact == 'softmax' and threshold is None and eps is None:
+        coords, loss = _FusedHead.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
+                                        flags, group, int(variant), bool(input_is_logits), aux)
+    else:
+        if not input_is_logits:
+            raise ValueError('preact=%r needs raw heatmaps (input_is_logits=True)' % (preact,))
+        d_thr, d_eps = PREACT_DEFAULTS[preact]
+        coords, loss = _FusedHeadPreact.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
+                                              flags, group, _lib.PREACT_IDS[preact],
+                                              float(d_thr if threshold is None else threshold),
+                                              float(d_eps if eps is None else eps), aux)
     out8 = aux['out8']
     return HeadOutput(coords, loss, out8[4], out8[5])
 

@@ -25,7 +25,8 @@ from . import nn as dnn
 from . import _lib
 from .head import dsnt_head, dsnt_head_stacked
 
-_FUSED_PREACTS = ('softmax',)
+_FUSED_PREACTS = ('softmax', 'thresholded_softmax', 'abs', 'relu', 'sigmoid')   # src/dsnt/model.py:29-41
+_STACKED_PREACTS = ('softmax',)
 
 
 def hm_preact(x, preact):
@@ -66,7 +67,7 @@ class DSNTHead(nn.Module):
     # ---- forward_part2 (src/dsnt/model.py:176-194, 278-307)
     def _part2_one(self, z):
         if self.preact in _FUSED_PREACTS:
-            coords = dsnt_head(z, None, None, reg='none').coords
+            coords = dsnt_head(z, None, None, reg='none', preact=self.preact).coords
         else:
             coords = dnn.dsnt(hm_preact(z, self.preact))
         self._logits.append(z)
@@ -74,7 +75,7 @@ class DSNTHead(nn.Module):
         return coords
 
     def _stackable(self, zs):
-        return (self.preact in _FUSED_PREACTS and 1 < len(zs) <= _lib.MAX_STACKS
+        return (self.preact in _STACKED_PREACTS and 1 < len(zs) <= _lib.MAX_STACKS
                 and all(z.shape == zs[0].shape and z.dtype == zs[0].dtype and z.device == zs[0].device for z in zs))
 
     def forward_part2(self, x):
@@ -109,7 +110,7 @@ class DSNTHead(nn.Module):
     def _loss_one(self, i, out, target, mask):
         if i < len(self._coords) and out is self._coords[i] and self.preact in _FUSED_PREACTS:
             return dsnt_head(self._logits[i], target, mask, reg=self.reg, hm_sigma=self.hm_sigma,
-                             reg_coeff=self.reg_coeff, group=self.group).loss
+                             reg_coeff=self.reg_coeff, group=self.group, preact=self.preact).loss
         # coords that did not come from forward_part2 (or a non-fused preact): the reference's composition
         loss = dnn.euclidean_loss(out, target, mask)
         sigma = 2.0 * self.hm_sigma / self._logits[i].size(-1)

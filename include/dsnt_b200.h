@@ -44,6 +44,13 @@ extern "C" {
 #define DSNT_REG_JS 3
 #define DSNT_REG_MSE 4
 
+/* heatmap pre-activation: src/dsnt/model.py:24-45 ('softmax'|'thresholded_softmax'|'abs'|'relu'|'sigmoid') */
+#define DSNT_PREACT_SOFTMAX 0
+#define DSNT_PREACT_TSOFTMAX 1
+#define DSNT_PREACT_ABS 2
+#define DSNT_PREACT_RELU 3
+#define DSNT_PREACT_SIGMOID 4
+
 /* per-heatmap statistics saved by the forward for the reduction-free backward */
 #define DSNT_MAX_STACKS 16 /* stacks (hourglass outputs) one *_stacked call can cover */
 
@@ -120,6 +127,29 @@ DSNT_API int dsnt_head_bwd_stacked(const void* const* z, void* const* dz, int n_
                                    void* stream);
 DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, long n_per_stack, int n_stacks,
                                       float reg_coeff, float* out, float* workspace, void* stream);
+
+/*
+ * The fused head for the other pre-activations of the reference.
+ *   replaces: HumanPoseModel._hm_preact (src/dsnt/model.py:24-45) -- thresholded_softmax(z, -0.5)
+ *             (src/dsnt/nn.py:119-157), |z|, relu(z), sigmoid(z), each divided by (sum + 1e-12) -- followed by dsnt,
+ *             the per-heatmap Euclidean distance and the regulariser exactly as dsnt_head_fwd/bwd, plus their autograd
+ *             replay (thresholded softmax: the custom backward out*(g - sum g out), src/dsnt/nn.py:131-139).
+ *   P = f(z) / (sum f(z) + eps) is never materialised; P may be exactly 0 and need not sum to 1, so every epsilon
+ *   of the reference (1e-24 inside the logs, eps in the normaliser) is kept.
+ *   preact     DSNT_PREACT_*; DSNT_PREACT_SOFTMAX with eps = 0 is plain softmax with the epsilons kept
+ *   threshold  DSNT_PREACT_TSOFTMAX only: entries below it get probability 0 (the max is over ALL entries)
+ *   eps        added to the normaliser sum (the reference uses 1e-12)
+ *   stats      [N,DSNT_STATS_K]: [0] max*log2(e) [1] 1/(sum+eps) [2..6] as dsnt_head_fwd
+ *              [7] Gaussian normaliser (kl/js/mse) or 1 - sum P (var)
+ * Other arguments as dsnt_head_fwd / dsnt_head_bwd.
+ */
+DSNT_API int dsnt_head_preact_fwd(const void* z, int dtype, int preact, float threshold, float eps, long n, int H, int W,
+                                  const float* target, int reg, float sigma, float* coords, float* stats, float* terms,
+                                  void* stream);
+DSNT_API int dsnt_head_preact_bwd(const void* z, int dtype, int preact, float threshold, long n, int H, int W,
+                                  const float* target, const float* mask, const float* stats, const float* g_coords,
+                                  const float* g_reg, const float* g_loss, const float* denom, float reg_coeff, int reg,
+                                  float sigma, int flags, void* dz, void* stream);
 
 /*
  * Deterministic finishing reduction over the per-heatmap terms (no float atomics, one launch).

@@ -108,6 +108,28 @@ def hm_preact_softmax(z):
     return F.softmax(z.reshape(-1, h * w), dim=-1).view(-1, c, h, w)
 
 
+def hm_preact(z, preact='softmax'):
+    """src/dsnt/model.py:24-45 -- every `--preact` choice; returns normalised heatmaps [-1, C, H, W]."""
+    c, h, w = z.shape[-3], z.shape[-2], z.shape[-1]
+    x = z.reshape(-1, h * w)
+    if preact == 'softmax':
+        x = F.softmax(x, dim=-1)                                      # :29-30
+    elif preact == 'thresholded_softmax':
+        x = thresholded_softmax(x, -0.5)                              # :31-32
+    elif preact == 'abs':
+        x = x.abs()                                                   # :33-35
+        x = x / (x.sum(-1, keepdim=True) + 1e-12)
+    elif preact == 'relu':
+        x = F.relu(x)                                                 # :36-38
+        x = x / (x.sum(-1, keepdim=True) + 1e-12)
+    elif preact == 'sigmoid':
+        x = torch.sigmoid(x)                                          # :39-41
+        x = x / (x.sum(-1, keepdim=True) + 1e-12)
+    else:
+        raise Exception('unrecognised heatmap preactivation function: {}'.format(preact))   # :42-43
+    return x.view(-1, c, h, w)
+
+
 # --------------------------------------------------------------------------- Gaussian target
 def make_gauss(coords, width, height, sigma):
     """src/dsnt/nn.py:168-205 -- normalised 2-D Gaussian, (width, height) argument order."""
@@ -173,22 +195,22 @@ def calculate_reg_loss(target, mask, reg, heatmaps, hm_sigma):
 
 
 # --------------------------------------------------------------------------- the whole head
-def head_forward(z):
-    """src/dsnt/model.py:176-183 (forward_part2, 'dsnt' strategy, softmax preact).
+def head_forward(z, preact='softmax'):
+    """src/dsnt/model.py:176-183 (forward_part2, 'dsnt' strategy).
 
     Returns (coords [B,C,2], heatmaps P [B,C,H,W]).
     """
-    p = hm_preact_softmax(z)
+    p = hm_preact_softmax(z) if preact == 'softmax' else hm_preact(z, preact)
     return dsnt(p), p
 
 
-def head_loss(z, target, mask=None, reg='none', hm_sigma=1.0, reg_coeff=1.0):
+def head_loss(z, target, mask=None, reg='none', hm_sigma=1.0, reg_coeff=1.0, preact='softmax'):
     """forward_part2 followed by forward_loss for one heatmap tensor.
 
     src/dsnt/model.py:138-145: loss = euclidean_loss + reg_coeff * reg_loss.
     Returns (loss, coords, euclid, reg_value).
     """
-    coords, p = head_forward(z)
+    coords, p = head_forward(z, preact)
     euc = euclidean_loss(coords, target, mask)
     rv = calculate_reg_loss(target, mask, reg, p, hm_sigma)
     return euc + reg_coeff * rv, coords, euc, rv
@@ -206,13 +228,13 @@ def head_loss_stacked(zs, target, mask=None, reg='none', hm_sigma=1.0, reg_coeff
 
 
 def head_loss_and_grad(z, target, mask=None, reg='none', hm_sigma=1.0, reg_coeff=1.0,
-                       dtype=torch.float64):
+                       dtype=torch.float64, preact='softmax'):
     """Convenience for parity tests: evaluate in `dtype` on CPU and return
     dict(loss, coords, euclid, reg, dz) as CPU tensors of that dtype."""
     zz = z.detach().to('cpu', dtype).clone().requires_grad_(True)
     tt = target.detach().to('cpu', dtype)
     mm = None if mask is None else mask.detach().to('cpu', dtype)
-    loss, coords, euc, rv = head_loss(zz, tt, mm, reg, hm_sigma, reg_coeff)
+    loss, coords, euc, rv = head_loss(zz, tt, mm, reg, hm_sigma, reg_coeff, preact)
     loss.backward()
     rv_t = rv if torch.is_tensor(rv) else torch.tensor(float(rv), dtype=dtype)
     return {'loss': loss.detach(), 'coords': coords.detach(), 'euclid': euc.detach(),

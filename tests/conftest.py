@@ -82,3 +82,8 @@ def rel_max(a, b):
     b = np.asarray(b, dtype=np.float64)
     den = np.abs(b).max() if b.size else 0.0
     return float(np.abs(a - b).max() / (den if den > 0 else 1.0)) if b.size else 0.0
+
+
+@pytest.fixture(scope='session')
+def golden_preact():
+    return Golden('preact_heads.npz')
