@@ -11,9 +11,10 @@ from . import _lib
 from . import nn
 from .head import HeadOutput, dsnt_head, dsnt_head_stacked
 from .model import DSNTHead, attach_fused_head, install_as_dsnt_nn
+from .inference import MPII_HFLIP_INDICES, flip_tta_coords, predict_flipped
 
 __all__ = ['nn', 'dsnt_head', 'dsnt_head_stacked', 'HeadOutput', 'DSNTHead', 'attach_fused_head',
-           'install_as_dsnt_nn', 'library_version']
+           'install_as_dsnt_nn', 'library_version', 'flip_tta_coords', 'predict_flipped', 'MPII_HFLIP_INDICES']
 
 
 def library_version():

@@ -40,6 +40,8 @@ SIGNATURES = {
     'dsnt_head_preact_bwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_float, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int, _c_ptr,
                                       _c_ptr]),
+    'dsnt_flip_tta_fwd': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_int, _c_ptr, _c_int, _c_float, _c_float,
+                                   _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_finish_loss_stacked': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_finish_workspace_bytes': (_c_int, []),
     'dsnt_finish_loss': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_float, _c_ptr, _c_ptr, _c_ptr]),

@@ -31,9 +31,19 @@ struct PreactCfg {
   float eps;         // added to the normaliser sum (1e-12 in the reference, 0 for plain softmax)
 };
 
+// Flip test-time augmentation fused into the load (src/dsnt/inference.py:36-46): the raw heatmaps of the
+// original images are heatmaps [0, batch*C), those of the mirrored images [batch*C, 2*batch*C); what the head sees is
+//     z'[b,c,i,j] = (z[b,c,i,j] + z[batch+b, perm[c], i, W-1-j]) / 2
+struct FlipCfg {
+  const int* perm;   // [C] joint permutation under a horizontal flip (device), or null = identity
+  void* avg_out;     // optional [batch*C,H,W]: the averaged raw heatmaps, same dtype as z
+  int C;
+};
+
 struct HeadPreactFwdParams {
   HeadFwdParams base;
   PreactCfg pc;
+  FlipCfg fl;
 };
 struct HeadPreactBwdParams {
   HeadBwdParams base;
@@ -81,19 +91,33 @@ __device__ __forceinline__ float preact_r(int reg, float P, float G) {
 }
 
 // Visits the vectors of one heatmap owned by this thread: from registers (NV > 0) or from global memory (NV == 0).
-template <typename T, int VEC, int GROUP, int NV>
+// FLIP: every vector is averaged with the mirrored vector of the partner heatmap zf as it is loaded.
+template <typename T, int VEC, int GROUP, int NV, bool FLIP = false>
 struct HmSweep {
   float v[NV > 0 ? NV : 1][VEC];
   const T* zb;
+  const T* zf;
   int nvec, wv, lane_g;
+
+  __device__ __forceinline__ void load_vec(int f, int row, int cv, float (&out)[VEC]) const {
+    VecIO<T, VEC>::load(zb, static_cast<long>(f) * VEC, out);
+    if constexpr (FLIP) {
+      float o[VEC];
+      VecIO<T, VEC>::load(zf, static_cast<long>(row * wv + (wv - 1 - cv)) * VEC, o);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) out[c] = 0.5f * (out[c] + o[VEC - 1 - c]);
+    }
+  }
 
   __device__ __forceinline__ void load_all() {
     if constexpr (NV > 0) {
+      VecWalker wk(lane_g, GROUP, wv);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int f = lane_g + k * GROUP;
         if (f < nvec) {
-          VecIO<T, VEC>::load(zb, static_cast<long>(f) * VEC, v[k]);
+          load_vec(f, wk.row, wk.cv, v[k]);
+          wk.next();
         } else {
 #pragma unroll
           for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
@@ -115,7 +139,7 @@ struct HmSweep {
     } else {
       for (int f = lane_g; f < nvec; f += GROUP) {
         float t[VEC];
-        VecIO<T, VEC>::load(zb, static_cast<long>(f) * VEC, t);
+        load_vec(f, wk.row, wk.cv, t);
         fn(t, wk.row, wk.cv * VEC);
         wk.next();
       }
@@ -124,7 +148,7 @@ struct HmSweep {
 };
 
 // ================================================================================================ forward
-template <typename T, int VEC, int GROUP, int NV>
+template <typename T, int VEC, int GROUP, int NV, bool FLIP = false>
 __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_preact_fwd_kernel(const HeadPreactFwdParams ps) {
   constexpr int BLOCK = fwd_block_threads<GROUP>();
   constexpr int GPB = BLOCK / GROUP;
@@ -145,8 +169,18 @@ __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_preact_fwd_ke
 
   const int H = p.H, W = p.W;
   const HmRef ref = locate(p.st, hm, static_cast<long>(H) * W * sizeof(T));
-  HmSweep<T, VEC, GROUP, NV> hs;
+  HmSweep<T, VEC, GROUP, NV, FLIP> hs;
   hs.zb = reinterpret_cast<const T*>(static_cast<const char*>(p.z) + ref.z_bytes);
+  hs.zf = nullptr;
+  T* avg_out = nullptr;
+  if constexpr (FLIP) {
+    const int C = ps.fl.C;
+    const long b = hm / C;
+    const int c = static_cast<int>(hm - b * C);
+    const long partner = p.n + b * C + (ps.fl.perm ? __ldg(ps.fl.perm + c) : c);
+    hs.zf = reinterpret_cast<const T*>(p.z) + partner * H * W;
+    if (ps.fl.avg_out) avg_out = reinterpret_cast<T*>(ps.fl.avg_out) + hm * H * W;
+  }
   hs.wv = W / VEC;
   hs.nvec = H * hs.wv;
   hs.lane_g = lane_g;
@@ -180,6 +214,9 @@ __global__ void __launch_bounds__(fwd_block_threads<GROUP>()) head_preact_fwd_ke
   // ---- 2. f = act(z) (kept in the registers when resident), S, sum f x, sum f y
   float S = 0.f, Sx = 0.f, Sy = 0.f, dummy = 0.f;
   hs.sweep([&](float (&z)[VEC], int row, int col0) {
+    if constexpr (FLIP) {
+      if (avg_out) VecIO<T, VEC>::store(avg_out, static_cast<long>(row) * W + col0, z);
+    }
     float rs = 0.f;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {

@@ -152,6 +152,23 @@ DSNT_API int dsnt_head_preact_bwd(const void* z, int dtype, int preact, float th
                                   float sigma, int flags, void* dz, void* stream);
 
 /*
+ * Inference with flip test-time augmentation, fused in front of the forward-only head.
+ *   replaces: src/dsnt/inference.py:36-48 -- hm1, hm2 = heatmaps of [images, mirrored images];
+ *             hm2 = reverse_tensor(hm2, -1).index_select(-3, HFLIP_INDICES) (src/dsnt/util.py:201-210,
+ *             src/dsnt/data.py:97); hm = (hm1 + hm2)/2; coords = forward_part2(hm) (src/dsnt/model.py:176-183)
+ *   z          [2*batch, C, H, W] raw heatmaps: the first `batch` samples are the original images, the last `batch`
+ *              their mirrored versions (the torch.cat order of inference.py:36)
+ *   flip_perm  [C] int32 DEVICE array: joint c of the mirrored image is joint flip_perm[c] (HFLIP_INDICES); NULL = identity
+ *   preact/threshold/eps  as dsnt_head_preact_fwd (softmax: eps 0)
+ *   coords     [batch*C, 2] out
+ *   avg_out    optional [batch, C, H, W] out (same dtype as z): the averaged raw heatmaps `hm`; NULL = not materialised
+ * One launch, both heatmap sets read once (2*H*W*sizeof bytes per output heatmap), no statistics saved.
+ * A forward-only head without the flip is dsnt_head_fwd / dsnt_head_preact_fwd with stats = terms = NULL.
+ */
+DSNT_API int dsnt_flip_tta_fwd(const void* z, int dtype, long batch, int C, int H, int W, const int* flip_perm, int preact,
+                               float threshold, float eps, float* coords, void* avg_out, void* stream);
+
+/*
  * Deterministic finishing reduction over the per-heatmap terms (no float atomics, one launch).
  *   replaces: masked_average (src/dsnt/nn.py:81-94) and loss = euclid + reg_coeff*reg (src/dsnt/model.py:145).
  *   terms [N,2] from dsnt_head_fwd; mask [N] or NULL (then every weight is 1 and count = N)

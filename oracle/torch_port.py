@@ -239,3 +239,30 @@ def head_loss_and_grad(z, target, mask=None, reg='none', hm_sigma=1.0, reg_coeff
     rv_t = rv if torch.is_tensor(rv) else torch.tensor(float(rv), dtype=dtype)
     return {'loss': loss.detach(), 'coords': coords.detach(), 'euclid': euc.detach(),
             'reg': rv_t.detach(), 'dz': zz.grad.detach()}
+
+
+# --------------------------------------------------------------------------- inference: flip test-time augmentation
+# joint permutation under a horizontal flip for the MPII joint order (torchdata.mpii.MPII_Joint_Horizontal_Flips,
+# bound to MPIIDataset.HFLIP_INDICES at src/dsnt/data.py:97)
+MPII_HFLIP_INDICES = (5, 4, 3, 2, 1, 0, 6, 7, 8, 9, 15, 14, 13, 12, 11, 10)
+
+
+def reverse_tensor(tensor, dim):
+    """src/dsnt/util.py:207-210."""
+    idx = torch.arange(tensor.size(dim) - 1, -1, -1, device=tensor.device)
+    return tensor.index_select(dim, idx)
+
+
+def flip_tta_heatmaps(hm_pair, hflip_indices=MPII_HFLIP_INDICES):
+    """src/dsnt/inference.py:43-46 -- `hm_pair` holds the raw heatmaps of [images, mirrored images] (the cat of
+    :36); the reference does this for one image (`split(1)`), the same lines are applied per half here."""
+    hm1, hm2 = hm_pair.chunk(2, 0)                                    # :43 (split(1) when the batch is one image)
+    hm2 = reverse_tensor(hm2, -1)                                     # :44
+    hm2 = hm2.index_select(-3, torch.as_tensor(hflip_indices, dtype=torch.long, device=hm2.device))   # :45
+    return (hm1 + hm2) / 2                                            # :46
+
+
+def flip_tta_coords(hm_pair, hflip_indices=MPII_HFLIP_INDICES, preact='softmax'):
+    """src/dsnt/inference.py:43-48: averaged heatmaps -> forward_part2 ('dsnt') -> coords [B,C,2]."""
+    hm = flip_tta_heatmaps(hm_pair, hflip_indices)
+    return head_forward(hm, preact)[0], hm

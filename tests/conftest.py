@@ -87,3 +87,8 @@ def rel_max(a, b):
 @pytest.fixture(scope='session')
 def golden_preact():
     return Golden('preact_heads.npz')
+
+
+@pytest.fixture(scope='session')
+def golden_flip():
+    return Golden('flip_tta.npz')

@@ -98,6 +98,35 @@ def make_preact(ref_nn, ref_model, gen):
     print('preact_heads.npz: %d arrays' % len(out))
 
 
+MPII_FLIPS = [5, 4, 3, 2, 1, 0, 6, 7, 8, 9, 15, 14, 13, 12, 11, 10]   # torchdata.mpii.MPII_Joint_Horizontal_Flips
+
+
+def make_flip(ref_nn, ref_model, gen):
+    """src/dsnt/inference.py:36-48 with the reference's own reverse_tensor / type_as_index / _hm_preact / dsnt
+    (inference.py itself needs progressbar + tele, absent here; these are its lines 43-48 verbatim in effect)."""
+    import dsnt.util as ref_util
+    hpm = ref_model.HumanPoseModel
+    out = {}
+    names = []
+    for name, (c, h, w), flips in (('f16x32', (16, 32, 32), MPII_FLIPS), ('f16x28', (16, 28, 28), MPII_FLIPS), ('f2x64', (2, 64, 64), [1, 0]),
+                                   ('f3x7x9', (3, 7, 9), [2, 1, 0]), ('f4x6x10', (4, 6, 10), [1, 0, 3, 2])):
+        hm_var = torch.randn(2, c, h, w, generator=gen).float().double() * 2     # one image + its mirror image
+        hm1, hm2 = hm_var.split(1)                                                 # :43
+        hm2 = ref_util.reverse_tensor(hm2, -1)                                     # :44
+        hm2 = hm2.index_select(-3, ref_util.type_as_index(torch.LongTensor(flips), hm2))   # :45
+        hm = (hm1 + hm2) / 2                                                       # :46
+        out[name + '/hm_pair'] = hm_var.float().numpy()
+        out[name + '/flips'] = np.array(flips, dtype=np.int64)
+        out[name + '/hm'] = hm.numpy()
+        for preact in PREACTS:
+            coords = ref_nn.dsnt(hpm._hm_preact(None, hm, preact))                 # :47 forward_part2
+            out['%s/%s/coords' % (name, preact)] = coords.numpy()
+        names.append(name)
+    out['__cases__'] = np.array(names)
+    np.savez_compressed(os.path.join(OUT_DIR, 'flip_tta.npz'), **out)
+    print('flip_tta.npz: %d arrays' % len(out))
+
+
 def main():
     torch.set_default_dtype(torch.float64)          # tests/common.py:18
     warnings.simplefilter('ignore')
