@@ -42,6 +42,9 @@ SIGNATURES = {
                                       _c_ptr]),
     'dsnt_flip_tta_fwd': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_int, _c_ptr, _c_int, _c_float, _c_float,
                                    _c_ptr, _c_ptr, _c_ptr]),
+    'dsnt_draw_gaussians': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, ctypes.c_double, ctypes.c_double, _c_int,
+                                     _c_ptr, _c_ptr]),
+    'dsnt_decode_heatmaps': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_int, _c_ptr, _c_ptr]),
     'dsnt_finish_loss_stacked': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_finish_workspace_bytes': (_c_int, []),
     'dsnt_finish_loss': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_float, _c_ptr, _c_ptr, _c_ptr]),

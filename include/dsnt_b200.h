@@ -214,6 +214,25 @@ DSNT_API int dsnt_make_gauss_fwd(const float* mu, long n, int W, int H, float si
 DSNT_API int dsnt_make_gauss_bwd(const float* mu, const float* g, long n, int W, int H, float sigma, float* dmu,
                         void* stream);
 
+/*
+ * The 'gauss' output strategy helpers, float32 arithmetic identical to the reference's.
+ *
+ * dsnt_draw_gaussians   replaces: encode_heatmaps (src/dsnt/util.py:129-148) and draw_gaussian (:70-126)
+ *   centres   [N,2] float32 DEVICE: normalised (x, y) coords (centres_are_pixels == 0: converted and rounded to the
+ *             nearest pixel exactly as util.py:133-144) or pixel coordinates (centres_are_pixels != 0: int() truncation)
+ *   sigma     std-dev in pixels;  clip_size: side of the square draw region (encode_heatmaps uses 7), <= 0 = unclipped
+ *   normalize divide the drawn region by its sum (util.py:122-125)
+ *   out       [N,H,W] float32: the Gaussian inside the draw window, 0 elsewhere (encode_heatmaps starts from zeros)
+ *
+ * dsnt_decode_heatmaps  replaces: get_preds + decode_heatmaps (src/dsnt/util.py:151-198)
+ *   hm [N,H,W] (fp32 or bf16) -> coords [N,2] float32 normalised; arg-max with the first maximum winning, (0,0) pixel
+ *   when the maximum is <= 0, y = idx / H as in util.py:163, optional quarter-pixel offset toward the higher neighbour.
+ */
+DSNT_API int dsnt_draw_gaussians(const float* centres, int centres_are_pixels, long n, int W, int H, double sigma,
+                                 double clip_size, int normalize, float* out, void* stream);
+DSNT_API int dsnt_decode_heatmaps(const void* hm, int dtype, long n, int H, int W, int use_neighbours, float* coords,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

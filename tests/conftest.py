@@ -92,3 +92,8 @@ def golden_preact():
 @pytest.fixture(scope='session')
 def golden_flip():
     return Golden('flip_tta.npz')
+
+
+@pytest.fixture(scope='session')
+def golden_gauss():
+    return Golden('gauss_util.npz')

@@ -127,6 +127,61 @@ def make_flip(ref_nn, ref_model, gen):
     print('flip_tta.npz: %d arrays' % len(out))
 
 
+def make_gauss_util(gen):
+    """src/dsnt/util.py:70-198 through the reference's own functions."""
+    import dsnt.util as ref_util
+    torch.set_default_dtype(torch.float32)      # these helpers work on FloatTensors (util.py:140)
+    # torch 0.3.1 (the reference's pin) returns a Python float when a FloatTensor is indexed down to one element, so
+    # `round(coords[i, j, 0])` (util.py:142-143) is Python's round-half-to-even on a float.  torch 2.x returns a 0-dim
+    # tensor, which has no __round__: give it the pinned version's meaning.  The reference source is untouched.
+    torch.Tensor.__round__ = lambda self, ndigits=None: round(self.item())
+    out = {}
+    # encode_heatmaps: random coords incl. out-of-frame joints, half-pixel ties, corners
+    for name, (b, c, h, w), sigma in (('e5x5', (1, 1, 5, 5), 1), ('e64', (2, 16, 64, 64), 1), ('e28', (3, 16, 28, 28), 2),
+                                      ('e7x12', (2, 5, 7, 12), 1.5)):
+        coords = (torch.rand(b, c, 2, generator=gen) * 2.6 - 1.3).float()
+        coords[0, 0] = torch.tensor([-0.8, 0.8])                                  # tests/test_util.py:39
+        if c > 4:
+            coords[0, 1] = torch.tensor([-1.0 + 2.0 / w, 1.0 - 1.0 / h])        # lands exactly on x.5 / pixel centre
+            coords[0, 2] = torch.tensor([-1.0, -1.0])                            # corner of the frame
+            coords[0, 3] = torch.tensor([1.5, 0.0])                              # far outside: nothing drawn
+            coords[0, 4] = torch.tensor([1.0 + 5.0 / w, 0.2])                    # outside but within the clip radius
+        out[name + '/coords'] = coords.numpy().copy()
+        out[name + '/sigma'] = np.float64(sigma)
+        out[name + '/hm'] = ref_util.encode_heatmaps(coords.clone(), w, h, sigma).numpy()
+    # draw_gaussian: unclipped + normalised + clipped
+    for name, (h, w), (x, y), sigma, normalize, clip in (('d9', (9, 9), (4, 4), 1, False, None),
+                                                         ('d5clip', (5, 5), (0, 4), 1, False, 7),
+                                                         ('d12norm', (10, 12), (7.9, 2.2), 1.7, True, None),
+                                                         ('d12clipnorm', (10, 12), (11, 9), 2.0, True, 5),
+                                                         ('d_out', (6, 6), (-9, 2), 1, False, 7)):
+        img = torch.zeros(1, h, w).float()
+        ref_util.draw_gaussian(img, x, y, sigma, normalize=normalize, clip_size=clip)
+        out[name + '/img'] = img.numpy()
+        out[name + '/args'] = np.array([x, y, sigma, float(normalize), -1.0 if clip is None else clip], dtype=np.float64)
+    # decode_heatmaps
+    for name, (b, c, h, w) in (('g64', (2, 4, 64, 64)), ('g28', (2, 8, 28, 28)), ('g6x9', (2, 4, 6, 9)),
+                               ('g9x6', (2, 4, 9, 6)), ('g2x2', (1, 3, 2, 2))):
+        hm = torch.randn(b, c, h, w, generator=gen).float()
+        hm[0, 0] = -hm[0, 0].abs() - 0.1                      # max <= 0 -> coords (0, 0) before normalisation
+        hm[0, 1] = 0.0                                        # all equal: first index wins, max == 0 -> (0, 0)
+        if h > 3 and w > 3:
+            hm[0, 2, 2, 2] = 9.0                              # interior peak with EQUAL neighbours: sign(0) = 0
+            hm[0, 2, 2, 1] = hm[0, 2, 2, 3] = 1.0
+            hm[0, 3, 0, w - 1] = 9.0                          # peak on the border: no neighbour offset
+            hm[1, 0, 1, 1] = hm[1, 0, h - 2, w - 2] = 7.0     # tie: the first maximum wins
+        out[name + '/hm'] = hm.numpy()
+        out[name + '/coords_nb'] = ref_util.decode_heatmaps(hm.clone(), use_neighbours=True).numpy()
+        out[name + '/coords'] = ref_util.decode_heatmaps(hm.clone(), use_neighbours=False).numpy()
+    # round trip of the two helpers
+    coords = (torch.rand(2, 16, 2, generator=gen) * 1.8 - 0.9).float()
+    out['rt/coords'] = coords.numpy().copy()
+    out['rt/decoded'] = ref_util.decode_heatmaps(ref_util.encode_heatmaps(coords.clone(), 64, 64, 1)).numpy()
+    torch.set_default_dtype(torch.float64)
+    np.savez_compressed(os.path.join(OUT_DIR, 'gauss_util.npz'), **out)
+    print('gauss_util.npz: %d arrays' % len(out))
+
+
 def main():
     torch.set_default_dtype(torch.float64)          # tests/common.py:18
     warnings.simplefilter('ignore')
