@@ -43,6 +43,17 @@ __device__ __forceinline__ void unpack16(const uint4& r, float (&v)[VEC]) {
   }
 }
 
+template <typename T, int VEC>
+__device__ __forceinline__ uint4 pack16(const float (&o)[VEC]) {
+  uint4 r;
+  if constexpr (sizeof(T) == 4) {
+    r.x = __float_as_uint(o[0]); r.y = __float_as_uint(o[1]); r.z = __float_as_uint(o[2]); r.w = __float_as_uint(o[3]);
+  } else {
+    r.x = pack_bf16(o[0], o[1]); r.y = pack_bf16(o[2], o[3]); r.z = pack_bf16(o[4], o[5]); r.w = pack_bf16(o[6], o[7]);
+  }
+  return r;
+}
+
 // max over the elements of U raw vectors (bf16: packed HMNMX2 on pairs, widened once at the end)
 template <typename T, int U>
 __device__ __forceinline__ float raw_max(const uint4 (&raw)[U]) {
@@ -96,7 +107,10 @@ struct HeadFwdFastParams {
   HeadFwdParams base;
   Geom g;
   FastGeom f;
+  FlipCfg fl;   // FLIP instantiations only (dsnt_flip_tta_fwd)
 };
+
+constexpr int kFlipU = 4;   // FLIP loads two vectors per slot: 4 slots = the same 128 B (fp32) in flight per thread
 
 // Per-heatmap window bookkeeping for the stash.
 struct StashWin {
@@ -119,13 +133,16 @@ __device__ __forceinline__ StashWin make_stash_window(const Window& w) {
 }
 
 // ================================================================================================ forward
-template <typename T, int VEC, int GROUP, int REG>
+// FLIP (inference, src/dsnt/inference.py:36-46): heatmap hm = (b, c) is averaged on the fly with the mirrored heatmap
+// (batch + b, perm[c]) of the same tensor; REG must be NONE then (no target at inference).
+template <typename T, int VEC, int GROUP, int REG, bool FLIP = false>
 __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_kernel(const HeadFwdFastParams ps) {
   static_assert(sizeof(T) * VEC == 16, "fast path = 16-byte vectors");
+  static_assert(!FLIP || REG == DSNT_REG_NONE, "flip test-time augmentation is forward-only, no regulariser");
   constexpr int BLOCK = stream_block_threads<GROUP>();
   constexpr int GPB = BLOCK / GROUP;
   constexpr int NW = GROUP / 32;
-  constexpr int U = kFastU;
+  constexpr int U = FLIP ? kFlipU : kFastU;
   constexpr bool kKL = REG == DSNT_REG_KL;
   constexpr bool kJS = REG == DSNT_REG_JS;
   constexpr bool kVar = REG == DSNT_REG_VAR;
@@ -189,12 +206,49 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
 #pragma unroll
   for (int c = 0; c < VEC; ++c) E[c] = 0.f;
   const char* src = zb + static_cast<size_t>(lane_g) * 16;
+  const char* srcf = nullptr;   // FLIP: the mirrored vector of the partner heatmap, same row
+  char* avg = nullptr;          // FLIP: optional averaged raw heatmaps
+  if constexpr (FLIP) {
+    const int C = ps.fl.C;
+    const long bi = hm / C;
+    const int ci = static_cast<int>(hm - bi * C);
+    const long partner = p.n + bi * C + (ps.fl.perm ? __ldg(ps.fl.perm + ci) : ci);
+    const int wv = 1 << fg.wv_shift;
+    srcf = static_cast<const char*>(p.z) + partner * (static_cast<long>(H) * W * sizeof(T)) +
+           static_cast<size_t>((row0 << fg.wv_shift) + (wv - 1 - cv)) * 16;
+    if (ps.fl.avg_out)
+      avg = static_cast<char*>(ps.fl.avg_out) + hm * (static_cast<long>(H) * W * sizeof(T)) + static_cast<size_t>(lane_g) * 16;
+  }
   for (int b = 0; b < fg.nbatch; ++b) {
     uint4 raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) raw[u] = ld_raw16(src + static_cast<size_t>(u) * (GROUP * 16));
     src += static_cast<size_t>(U) * (GROUP * 16);
-    const float bm2 = raw_max<T, U>(raw) * kLog2e;
+    float fv[FLIP ? U : 1][VEC];
+    float bm2;
+    if constexpr (FLIP) {
+      uint4 rawf[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) rawf[u] = ld_raw16(srcf + static_cast<size_t>(u) * (GROUP * 16));
+      srcf += static_cast<size_t>(U) * (GROUP * 16);
+      float bm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float a[VEC], m[VEC];
+        unpack16<T, VEC>(raw[u], a);
+        unpack16<T, VEC>(rawf[u], m);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          fv[u][c] = 0.5f * (a[c] + m[VEC - 1 - c]);      // (hm1 + reversed hm2) / 2, inference.py:44-46
+          bm = fmaxf(bm, fv[u][c]);
+        }
+        if (avg) *reinterpret_cast<uint4*>(avg + static_cast<size_t>(u) * (GROUP * 16)) = pack16<T, VEC>(fv[u]);
+      }
+      if (avg) avg += static_cast<size_t>(U) * (GROUP * 16);
+      bm2 = bm * kLog2e;
+    } else {
+      bm2 = raw_max<T, U>(raw) * kLog2e;
+    }
     if (bm2 > mt2) {  // rare after the first batches: rescale the running sums to the new maximum
       const float sc = ex2(mt2 - bm2);
       if (kKL) Tt = S > 0.f ? sc * fmaf(mt2 - bm2, S, Tt) : 0.f;  // sum e'(t - d) = sc (T - d S)
@@ -208,7 +262,12 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float v[VEC];
-      unpack16<T, VEC>(raw[u], v);
+      if constexpr (FLIP) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) v[c] = fv[u][c];
+      } else {
+        unpack16<T, VEC>(raw[u], v);
+      }
       if constexpr (kWin) {
         // stash the raw logits of window vectors (unsigned compare = 0 <= r < nrw)
         const int r = srow + u * fg.rstep;
@@ -394,17 +453,6 @@ struct HeadBwdFastParams {
 };
 
 __device__ __forceinline__ void st_vec16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
-
-template <typename T, int VEC>
-__device__ __forceinline__ uint4 pack16(const float (&o)[VEC]) {
-  uint4 r;
-  if constexpr (sizeof(T) == 4) {
-    r.x = __float_as_uint(o[0]); r.y = __float_as_uint(o[1]); r.z = __float_as_uint(o[2]); r.w = __float_as_uint(o[3]);
-  } else {
-    r.x = pack_bf16(o[0], o[1]); r.y = pack_bf16(o[2], o[3]); r.z = pack_bf16(o[4], o[5]); r.w = pack_bf16(o[6], o[7]);
-  }
-  return r;
-}
 
 template <typename T>
 __device__ __forceinline__ void st_scalar(T* p, float v);

@@ -40,6 +40,15 @@ struct HeadFwdParams {
   Stacks st;
 };
 
+// Flip test-time augmentation fused into the load (src/dsnt/inference.py:36-46): the raw heatmaps of the
+// original images are heatmaps [0, batch*C), those of the mirrored images [batch*C, 2*batch*C); what the head sees is
+//     z'[b,c,i,j] = (z[b,c,i,j] + z[batch+b, perm[c], i, W-1-j]) / 2
+struct FlipCfg {
+  const int* perm;   // [C] joint permutation under a horizontal flip (device), or null = identity
+  void* avg_out;     // optional [batch*C,H,W]: the averaged raw heatmaps, same dtype as z
+  int C;
+};
+
 constexpr int kWarpPathBlock = 128;  // 4 heatmaps per CTA on the warp-per-heatmap path
 
 template <int GROUP>

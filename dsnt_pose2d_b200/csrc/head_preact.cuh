@@ -31,15 +31,6 @@ struct PreactCfg {
   float eps;         // added to the normaliser sum (1e-12 in the reference, 0 for plain softmax)
 };
 
-// Flip test-time augmentation fused into the load (src/dsnt/inference.py:36-46): the raw heatmaps of the
-// original images are heatmaps [0, batch*C), those of the mirrored images [batch*C, 2*batch*C); what the head sees is
-//     z'[b,c,i,j] = (z[b,c,i,j] + z[batch+b, perm[c], i, W-1-j]) / 2
-struct FlipCfg {
-  const int* perm;   // [C] joint permutation under a horizontal flip (device), or null = identity
-  void* avg_out;     // optional [batch*C,H,W]: the averaged raw heatmaps, same dtype as z
-  int C;
-};
-
 struct HeadPreactFwdParams {
   HeadFwdParams base;
   PreactCfg pc;

@@ -3,6 +3,7 @@
 // of the two raw heatmap sets, then forward_part2) with ONE launch that reads both heatmap sets once.
 #include "capi_util.cuh"
 #include "head_preact.cuh"
+#include "launch.cuh"
 
 namespace dsnt {
 
@@ -53,6 +54,13 @@ DSNT_API int dsnt_flip_tta_fwd(const void* z, int dtype, long batch, int C, int 
   ps.fl.perm = flip_perm; ps.fl.avg_out = avg_out; ps.fl.C = C;
   const int vec = pick_vec(dtype, W, z, avg_out);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // plain softmax (every model of the reference's experiments): the tuned streaming forward with the flip fused in
+  if (preact == DSNT_PREACT_SOFTMAX && eps == 0.f && threshold == -INFINITY) {
+    rc = 1;
+    if (dtype == DSNT_DTYPE_F32 && vec == 4) rc = try_launch_fwd_fast_flip<float, 4>(p, ps.fl, s);
+    if (dtype == DSNT_DTYPE_BF16 && vec == 8) rc = try_launch_fwd_fast_flip<bf16_t, 8>(p, ps.fl, s);
+    if (rc != 1) return rc;
+  }
   if (dtype == DSNT_DTYPE_F32)
     return vec == 4 ? launch_flip_shape<float, 4>(ps, s) : launch_flip_shape<float, 1>(ps, s);
   return vec == 8   ? launch_flip_shape<bf16_t, 8>(ps, s)

@@ -62,17 +62,17 @@ int launch_fwd_shape(const HeadFwdParams& p, int variant, cudaStream_t stream) {
 inline bool stream_group_is_cta(long nvec) { return nvec > 2048; }
 
 // ---- tuned kernels (head_fast.cuh): variant 0 picks them whenever the layout qualifies; variant 3 forces v1
-inline bool make_fast_geom(int H, int W, int vec, int group, FastGeom& f) {
+inline bool make_fast_geom(int H, int W, int vec, int group, FastGeom& f, int u = kFastU) {
   const int wv = W / vec;
   if (wv <= 0 || (wv & (wv - 1)) != 0 || group % wv != 0) return false;
   const long nvec = static_cast<long>(H) * wv;
-  if (nvec % (static_cast<long>(group) * kFastU) != 0) return false;
+  if (nvec % (static_cast<long>(group) * u) != 0) return false;
   f.wv_shift = 0;
   while ((1 << f.wv_shift) < wv) ++f.wv_shift;
-  f.nbatch = static_cast<int>(nvec / (static_cast<long>(group) * kFastU));
+  f.nbatch = static_cast<int>(nvec / (static_cast<long>(group) * u));
   f.rstep = group / wv;
   f.dy_step = static_cast<float>(f.rstep) * (2.0f / static_cast<float>(H));
-  f.dy_batch = static_cast<float>(kFastU) * f.dy_step;
+  f.dy_batch = static_cast<float>(u) * f.dy_step;
   return true;
 }
 
@@ -101,6 +101,7 @@ int launch_fwd_fast_group(const HeadFwdParams& p, const FastGeom& f, cudaStream_
   ps.base = p;
   ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
   ps.f = f;
+  ps.fl = FlipCfg{nullptr, nullptr, 0};
   if (!stash_fits(p.H, p.W, VEC, REG, ps.g.r2_win)) return 1;
   const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
   head_fwd_fast_kernel<T, VEC, GROUP, REG><<<grid, BLOCK, 0, stream>>>(ps);
@@ -121,6 +122,37 @@ int try_launch_fwd_fast(const HeadFwdParams& p, cudaStream_t stream) {
     }
     if (!make_fast_geom(p.H, p.W, VEC, 32, f)) return 1;
     return launch_fwd_fast_group<T, VEC, 32, REG>(p, f, stream);
+  }
+}
+
+// flip test-time augmentation on the tuned forward (infer.cu); returns 1 when the layout does not qualify
+template <typename T, int VEC, int GROUP>
+int launch_fwd_fast_flip_group(const HeadFwdParams& p, const FlipCfg& fl, const FastGeom& f, cudaStream_t stream) {
+  constexpr int BLOCK = stream_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  HeadFwdFastParams ps;
+  ps.base = p;
+  ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, DSNT_REG_NONE);
+  ps.f = f;
+  ps.fl = fl;
+  const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
+  head_fwd_fast_kernel<T, VEC, GROUP, DSNT_REG_NONE, true><<<grid, BLOCK, 0, stream>>>(ps);
+  return check_launch("head_fwd_fast_kernel<flip>");
+}
+
+template <typename T, int VEC>
+int try_launch_fwd_fast_flip(const HeadFwdParams& p, const FlipCfg& fl, cudaStream_t stream) {
+  if constexpr (sizeof(T) * VEC != 16) {
+    return 1;
+  } else {
+    const long nvec = static_cast<long>(p.H) * p.W / VEC;
+    FastGeom f;
+    if (stream_group_is_cta(nvec)) {
+      if (!make_fast_geom(p.H, p.W, VEC, 256, f, kFlipU)) return 1;
+      return launch_fwd_fast_flip_group<T, VEC, 256>(p, fl, f, stream);
+    }
+    if (!make_fast_geom(p.H, p.W, VEC, 32, f, kFlipU)) return 1;
+    return launch_fwd_fast_flip_group<T, VEC, 32>(p, fl, f, stream);
   }
 }
 
