@@ -36,10 +36,10 @@ SIGNATURES = {
                                        _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int,
                                        _c_int, _c_ptr]),
     'dsnt_head_preact_fwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_float, _c_float, _c_long, _c_int, _c_int, _c_ptr, _c_int,
-                                      _c_float, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+                                      _c_float, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]),
     'dsnt_head_preact_bwd': (_c_int, [_c_ptr, _c_int, _c_int, _c_float, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int, _c_float, _c_int, _c_ptr,
-                                      _c_ptr]),
+                                      _c_int, _c_ptr]),
     'dsnt_flip_tta_fwd': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_int, _c_ptr, _c_int, _c_float, _c_float,
                                    _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_draw_gaussians': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, ctypes.c_double, ctypes.c_double, _c_int,

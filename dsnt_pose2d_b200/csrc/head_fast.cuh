@@ -108,6 +108,7 @@ struct HeadFwdFastParams {
   Geom g;
   FastGeom f;
   FlipCfg fl;   // FLIP instantiations only (dsnt_flip_tta_fwd)
+  PreactCfg pc; // PA != DSNT_PREACT_SOFTMAX instantiations only (dsnt_head_preact_fwd)
 };
 
 constexpr int kFlipU = 4;   // FLIP loads two vectors per slot: 4 slots = the same 128 B (fp32) in flight per thread
@@ -135,10 +136,15 @@ __device__ __forceinline__ StashWin make_stash_window(const Window& w) {
 // ================================================================================================ forward
 // FLIP (inference, src/dsnt/inference.py:36-46): heatmap hm = (b, c) is averaged on the fly with the mirrored heatmap
 // (batch + b, perm[c]) of the same tensor; REG must be NONE then (no target at inference).
-template <typename T, int VEC, int GROUP, int REG, bool FLIP = false>
+// PA != SOFTMAX: P = f(z)/(sum f + eps) for the reference's other pre-activations.  P may be exactly 0 and sum P may
+// differ from 1 (eps), which the closed forms below carry as sumP / om; stats[7] holds om = 1 - sum P for `var`.
+template <typename T, int VEC, int GROUP, int REG, bool FLIP = false, int PA = DSNT_PREACT_SOFTMAX>
 __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_kernel(const HeadFwdFastParams ps) {
   static_assert(sizeof(T) * VEC == 16, "fast path = 16-byte vectors");
   static_assert(!FLIP || REG == DSNT_REG_NONE, "flip test-time augmentation is forward-only, no regulariser");
+  constexpr bool kSM = preact_is_softmax(PA);       // needs the running maximum
+  constexpr bool kPlain = PA == DSNT_PREACT_SOFTMAX;
+  const float thr = ps.pc.threshold;
   constexpr int BLOCK = stream_block_threads<GROUP>();
   constexpr int GPB = BLOCK / GROUP;
   constexpr int NW = GROUP / 32;
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
   }
 
   // ---- streaming pass: online softmax statistics, one accumulator per column
-  float mt2 = -INFINITY, S = 0.f, Sy = 0.f, Tt = 0.f, Q = 0.f;
+  float mt2 = kSM ? -INFINITY : 0.f, S = 0.f, Sy = 0.f, Tt = 0.f, Q = 0.f;
   float E[VEC];
   float my = 0.f, M2y = 0.f;
 #pragma unroll
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
     for (int u = 0; u < U; ++u) raw[u] = ld_raw16(src + static_cast<size_t>(u) * (GROUP * 16));
     src += static_cast<size_t>(U) * (GROUP * 16);
     float fv[FLIP ? U : 1][VEC];
-    float bm2;
+    float bm2 = 0.f;
     if constexpr (FLIP) {
       uint4 rawf[U];
 #pragma unroll
@@ -246,10 +252,10 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
       }
       if (avg) avg += static_cast<size_t>(U) * (GROUP * 16);
       bm2 = bm * kLog2e;
-    } else {
+    } else if constexpr (kSM) {
       bm2 = raw_max<T, U>(raw) * kLog2e;
     }
-    if (bm2 > mt2) {  // rare after the first batches: rescale the running sums to the new maximum
+    if (kSM && bm2 > mt2) {  // rare after the first batches: rescale the running sums to the new maximum
       const float sc = ex2(mt2 - bm2);
       if (kKL) Tt = S > 0.f ? sc * fmaf(mt2 - bm2, S, Tt) : 0.f;  // sum e'(t - d) = sc (T - d S)
       S *= sc; Sy *= sc;
@@ -282,8 +288,8 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
 #pragma unroll
       for (int c = 0; c < VEC; ++c) {
         const float t = fmaf(v[c], kLog2e, -mt2);
-        ev[c] = ex2(t);
-        if (kKL) Tt = fmaf(ev[c], t, Tt);
+        ev[c] = act_fast<PA>(v[c], t, thr);
+        if (kKL) Tt = fmaf(ev[c], act_log2<PA>(ev[c], t), Tt);
         if (kMSE) Q = fmaf(ev[c], ev[c], Q);
         E[c] += ev[c];
       }
@@ -333,8 +339,11 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
   const float S_loc = S;
   group_sum4<GROUP>(S, Sx, Sy, Tt, red_a + gid * NW * 4, warp_g, lane);
   if constexpr (GROUP == 32) __syncwarp();   // stash writes of the other lanes are visible from here on
-  const float invS = 1.0f / S;
+  const float invS = kPlain ? 1.0f / S : 1.0f / (S + ps.pc.eps);
   const float mux = Sx * invS, muy = Sy * invS;
+  // sum P and 1 - sum P = eps/(S + eps): 1 and 0 for plain softmax; an all-masked / all-negative map has sum P = 0
+  const float sumP = kPlain ? 1.0f : S * invS;
+  const float om = kPlain ? 0.f : ps.pc.eps * invS;
 
   float D = 0.f, creg = 0.f, ginv = 0.f, vx = 0.f, vy = 0.f;
 
@@ -346,6 +355,11 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
     const float s2 = p.sigma * p.sigma, ex = vx - s2, ey = vy - s2;
     D = ex * ex + ey * ey;
     creg = 2.f * (ex * vx + ey * vy);
+    if constexpr (!kPlain) {
+      // d v_x/dP = (x - mu_x)^2 - 2 x mu_x (1 - sum P): the second term survives when sum P != 1
+      creg = 2.f * (ex * (vx - 2.f * mux * mux * om) + ey * (vy - 2.f * muy * muy * om));
+      ginv = om;   // stats[7] (no Gaussian for `var`): the backward needs 1 - sum P
+    }
   }
 
   if constexpr (kWin) {
@@ -372,14 +386,15 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
       }
       ginv = 1.0f / (sx * sy + kEps);
       const float l2ginv = log2f(ginv);
-      const float l2is = -log2f(S);         // log2 P = t + l2is
+      const float l2is = kPlain ? -log2f(S) : log2f(invS);   // log2 P = log2 f + l2is
       const float tlm1 = l2is - 1.0f;
       const float hinvS = 0.5f * invS;
 
       auto pixel = [&](float z, float lgG) {
         const float G = ex2(lgG);
-        const float t = fmaf(z, kLog2e, -m2);
-        const float e = ex2(t);
+        const float t0 = fmaf(z, kLog2e, -m2);
+        const float e = act_fast<PA>(z, t0, thr);
+        const float t = act_log2<PA>(e, t0);                     // log2 f (0 where f = 0: the term is weighted by f)
         if (kJS) {
           const float Mp = fmaf(e, hinvS, fmaf(0.5f, G, kEps));  // M + eps
           const float L = lg2(Mp);
@@ -432,12 +447,13 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
     } else {
       group_sum2<GROUP>(qa, qb, red_b + gid * NW * 4, warp_g, lane);
       if (kJS) {
-        creg = 0.5f * kLn2 * (1.0f + qa);        // 1/2 sum P (ln P - ln M')
+        creg = 0.5f * kLn2 * (sumP + qa);        // 1/2 sum P (ln P - ln M'); outside the window every term is ln 2
         D = fmaf(0.5f * kLn2, qb, creg);         // + 1/2 sum G (ln G - ln M')
       } else {
-        const float plnp = fmaf(kLn2 * invS, Tt, -logf(S));  // sum P ln P
-        D = plnp - kLnEps - kLn2 * qa;
-        creg = D + 1.0f;
+        // sum P ln P = (ln2 sum f log2 f)/(S + eps) + sum P ln(1/(S + eps))
+        const float plnp = kPlain ? fmaf(kLn2 * invS, Tt, -logf(S)) : fmaf(kLn2 * invS, Tt, sumP * logf(invS));
+        D = plnp - sumP * kLnEps - kLn2 * qa;
+        creg = D + sumP;                         // + sum P^2/(P + eps) = sum P (P is 0 or >> eps)
       }
     }
   }

@@ -49,6 +49,17 @@ struct FlipCfg {
   int C;
 };
 
+// How raw heatmaps become a distribution (src/dsnt/model.py:24-45): P = f(z) / (sum f(z) + eps).
+struct PreactCfg {
+  int preact;        // DSNT_PREACT_*
+  float threshold;   // thresholded softmax: keep z >= threshold
+  float eps;         // added to the normaliser sum (1e-12 in the reference, 0 for plain softmax)
+};
+
+__host__ __device__ constexpr bool preact_is_softmax(int pa) {
+  return pa == DSNT_PREACT_SOFTMAX || pa == DSNT_PREACT_TSOFTMAX;
+}
+
 constexpr int kWarpPathBlock = 128;  // 4 heatmaps per CTA on the warp-per-heatmap path
 
 template <int GROUP>

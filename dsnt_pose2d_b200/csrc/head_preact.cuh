@@ -25,12 +25,6 @@
 
 namespace dsnt {
 
-struct PreactCfg {
-  int preact;        // DSNT_PREACT_*
-  float threshold;   // thresholded softmax: keep z >= threshold
-  float eps;         // added to the normaliser sum (1e-12 in the reference, 0 for plain softmax)
-};
-
 struct HeadPreactFwdParams {
   HeadFwdParams base;
   PreactCfg pc;
@@ -40,10 +34,6 @@ struct HeadPreactBwdParams {
   HeadBwdParams base;
   PreactCfg pc;
 };
-
-__host__ __device__ constexpr bool preact_is_softmax(int pa) {
-  return pa == DSNT_PREACT_SOFTMAX || pa == DSNT_PREACT_TSOFTMAX;
-}
 
 // f(z).  m2 = max(z) * log2(e) for the softmax family.
 __device__ __forceinline__ float preact_f(const PreactCfg& pc, float z, float m2) {

@@ -35,6 +35,32 @@ constexpr float kThetaKL = 3e-32f;   // G + 1e-24 == 1e-24 exactly in fp32 below
 constexpr float kLog2Eps = -79.726274277296700f;   // log2(1e-24)
 constexpr float kLnEps = -55.262042231857095f;     // ln(1e-24)
 
+// f(z) for the other pre-activations of the reference (src/dsnt/model.py:31-41) on the tuned kernels.  PA is a
+// template parameter, so the softmax instantiations are unchanged.  Softmax family: t = z log2e - max log2e is given
+// and e = 2^t (masked below the threshold); the others return f and leave t alone (see act_log2).
+template <int PA>
+__device__ __forceinline__ float act_fast(float z, float t, float thr) {
+  if constexpr (PA == DSNT_PREACT_SOFTMAX) return ex2(t);
+  else if constexpr (PA == DSNT_PREACT_TSOFTMAX) return z >= thr ? ex2(t) : 0.f;
+  else if constexpr (PA == DSNT_PREACT_ABS) return fabsf(z);
+  else if constexpr (PA == DSNT_PREACT_RELU) return fmaxf(z, 0.f);
+  else return rcp(1.0f + ex2(-z * kLog2e));
+}
+// log2 f(z): free for the softmax family (it is t), one MUFU otherwise; 0 where f = 0 (every use is weighted by f)
+template <int PA>
+__device__ __forceinline__ float act_log2(float e, float t) {
+  if constexpr (preact_is_softmax(PA)) return t;
+  else return e > 0.f ? lg2(e) : 0.f;
+}
+// f'(z) given f(z) (thresholded softmax: the reference's custom backward uses out itself, src/dsnt/nn.py:131-139)
+template <int PA>
+__device__ __forceinline__ float act_grad(float z, float e) {
+  if constexpr (preact_is_softmax(PA)) return e;
+  else if constexpr (PA == DSNT_PREACT_ABS) return z > 0.f ? 1.0f : (z < 0.f ? -1.0f : 0.f);
+  else if constexpr (PA == DSNT_PREACT_RELU) return z > 0.f ? 1.0f : 0.f;
+  else return e * (1.0f - e);
+}
+
 // Launch-uniform geometry, computed on the host (no divisions in the kernels).
 struct Geom {
   float two_over_w, bias_w, two_over_h, bias_h;  // x_j = j*two_over_w + bias_w  (src/dsnt/nn.py:30-37)
@@ -367,10 +393,14 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
 struct HeadBwdStreamParams {
   HeadBwdParams base;
   Geom g;
+  PreactCfg pc;   // PA != DSNT_PREACT_SOFTMAX instantiations only (dsnt_head_preact_bwd)
 };
 
-template <typename T, int VEC, int GROUP, int REG, bool FIXC>
+// PA != SOFTMAX (act_fast / act_log2 / act_grad above): dz = f'(z)/(S+eps) (g - c) for the reference's other
+// pre-activations; where f' = 0 (masked, clipped or z = 0) the gradient is exactly 0 whatever the log terms say.
+template <typename T, int VEC, int GROUP, int REG, bool FIXC, int PA = DSNT_PREACT_SOFTMAX>
 __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_stream_kernel(const HeadBwdStreamParams ps) {
+  constexpr bool kPlain = PA == DSNT_PREACT_SOFTMAX;
   constexpr int BLOCK = stream_block_threads<GROUP>();
   constexpr int GPB = BLOCK / GROUP;
   constexpr int U = VEC == 8 ? 4 : 8;
@@ -392,6 +422,10 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_stream
   const BwdScalars s = load_bwd_scalars<true>(p, hm, ref.nl, REG);
   Window win{1, 0, 1, 0};
   if constexpr (kGauss) win = make_window(g, H, W, s.tx, s.ty);
+  // var with sum P != 1 (eps in the normaliser; stats[7] = 1 - sum P): d v/dP gains -2 x mu (1 - sum P)
+  const float cx2 = (!kPlain && REG == DSNT_REG_VAR) ? -2.f * s.mux * s.ginv : 0.f;
+  const float cy2 = (!kPlain && REG == DSNT_REG_VAR) ? -2.f * s.muy * s.ginv : 0.f;
+  const float thr = ps.pc.threshold;
 
   // constant part of (g - c):  -c, plus the out-of-window value of rho*r
   float cbase = -s.c;
@@ -412,6 +446,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_stream
       if (REG == DSNT_REG_VAR) {
         const float dx = x - s.mux;
         a = fmaf(s.kx * dx, dx, a);
+        if constexpr (!kPlain) a = fmaf(s.kx * x, cx2, a);
       }
       acol[c] = a;
       gxs[c] = 0.f;
@@ -455,6 +490,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_stream
         if (REG == DSNT_REG_VAR) {
           const float dy = y - s.muy;
           rowc = fmaf(s.ky * dy, dy, rowc);
+          if constexpr (!kPlain) rowc = fmaf(s.ky * y, cy2, rowc);
         }
         float gyn = 0.f;
         bool heavy = false;
@@ -468,8 +504,10 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_stream
         float out[VEC];
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
-          const float t = fmaf(v[u][c], kLog2e, -s.m2);
-          const float P = ex2(t) * s.invS;
+          const float t0 = fmaf(v[u][c], kLog2e, -s.m2);
+          const float e = act_fast<PA>(v[u][c], t0, thr);
+          const float t = REG == DSNT_REG_KL ? act_log2<PA>(e, t0) : t0;   // log2 f
+          const float P = e * s.invS;
           float gmc = acol[c] + rowc;
           if (REG == DSNT_REG_KL) gmc = fmaf(rho_t, t, gmc);
           if (REG == DSNT_REG_MSE) gmc = fmaf(rho_p, P, gmc);
@@ -485,7 +523,12 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_stream
               gmc = fmaf(-rho_p, G, gmc);
             }
           }
-          out[c] = P * gmc;
+          if constexpr (kPlain) {
+            out[c] = P * gmc;
+          } else {
+            const float fp = act_grad<PA>(v[u][c], e);
+            out[c] = fp != 0.f ? fp * s.invS * gmc : 0.f;
+          }
         }
         VecIO<T, VEC>::store(dzb, static_cast<long>(f0 + u * GROUP) * VEC, out);
       }

@@ -102,6 +102,7 @@ int launch_fwd_fast_group(const HeadFwdParams& p, const FastGeom& f, cudaStream_
   ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
   ps.f = f;
   ps.fl = FlipCfg{nullptr, nullptr, 0};
+  ps.pc = PreactCfg{DSNT_PREACT_SOFTMAX, 0.f, 0.f};
   if (!stash_fits(p.H, p.W, VEC, REG, ps.g.r2_win)) return 1;
   const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
   head_fwd_fast_kernel<T, VEC, GROUP, REG><<<grid, BLOCK, 0, stream>>>(ps);
@@ -135,6 +136,7 @@ int launch_fwd_fast_flip_group(const HeadFwdParams& p, const FlipCfg& fl, const 
   ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, DSNT_REG_NONE);
   ps.f = f;
   ps.fl = fl;
+  ps.pc = PreactCfg{DSNT_PREACT_SOFTMAX, 0.f, 0.f};
   const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
   head_fwd_fast_kernel<T, VEC, GROUP, DSNT_REG_NONE, true><<<grid, BLOCK, 0, stream>>>(ps);
   return check_launch("head_fwd_fast_kernel<flip>");
@@ -254,6 +256,110 @@ int launch_fwd_reg(const HeadFwdParams& p, int variant, cudaStream_t stream) {
   }
 }
 
+// ---- the tuned kernels for the other pre-activations (preact_*.cu); return 1 = layout does not qualify, the caller
+// then runs the generic kernels of head_preact.cuh
+int launch_preact_fast_fwd_f32(const HeadFwdParams& p, const PreactCfg& pc, int vec, cudaStream_t stream);
+int launch_preact_fast_fwd_bf16(const HeadFwdParams& p, const PreactCfg& pc, int vec, cudaStream_t stream);
+int launch_preact_fast_bwd_f32(const HeadBwdParams& p, const PreactCfg& pc, int vec, cudaStream_t stream);
+int launch_preact_fast_bwd_bf16(const HeadBwdParams& p, const PreactCfg& pc, int vec, cudaStream_t stream);
+
+template <typename T, int VEC, int GROUP, int REG, int PA>
+int launch_preact_fwd_fast_group(const HeadFwdParams& p, const PreactCfg& pc, const FastGeom& f, cudaStream_t stream) {
+  constexpr int BLOCK = stream_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  HeadFwdFastParams ps;
+  ps.base = p;
+  ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
+  ps.f = f;
+  ps.fl = FlipCfg{nullptr, nullptr, 0};
+  ps.pc = pc;
+  if (!stash_fits(p.H, p.W, VEC, REG, ps.g.r2_win)) return 1;
+  const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
+  head_fwd_fast_kernel<T, VEC, GROUP, REG, false, PA><<<grid, BLOCK, 0, stream>>>(ps);
+  return check_launch("head_fwd_fast_kernel<preact>");
+}
+
+template <typename T, int VEC, int REG, int PA>
+int try_launch_preact_fwd_fast(const HeadFwdParams& p, const PreactCfg& pc, cudaStream_t stream) {
+  const long nvec = static_cast<long>(p.H) * p.W / VEC;
+  FastGeom f;
+  if (stream_group_is_cta(nvec)) {
+    if (!make_fast_geom(p.H, p.W, VEC, 256, f)) return 1;
+    return launch_preact_fwd_fast_group<T, VEC, 256, REG, PA>(p, pc, f, stream);
+  }
+  if (!make_fast_geom(p.H, p.W, VEC, 32, f)) return 1;
+  return launch_preact_fwd_fast_group<T, VEC, 32, REG, PA>(p, pc, f, stream);
+}
+
+template <typename T, int VEC, int PA>
+int launch_preact_fwd_fast_reg(const HeadFwdParams& p, const PreactCfg& pc, cudaStream_t stream) {
+  switch (p.reg) {
+    case DSNT_REG_NONE: return try_launch_preact_fwd_fast<T, VEC, DSNT_REG_NONE, PA>(p, pc, stream);
+    case DSNT_REG_VAR: return try_launch_preact_fwd_fast<T, VEC, DSNT_REG_VAR, PA>(p, pc, stream);
+    case DSNT_REG_KL: return try_launch_preact_fwd_fast<T, VEC, DSNT_REG_KL, PA>(p, pc, stream);
+    case DSNT_REG_JS: return try_launch_preact_fwd_fast<T, VEC, DSNT_REG_JS, PA>(p, pc, stream);
+    case DSNT_REG_MSE: return try_launch_preact_fwd_fast<T, VEC, DSNT_REG_MSE, PA>(p, pc, stream);
+  }
+  return 1;
+}
+
+template <typename T, int VEC>
+int launch_preact_fwd_fast(const HeadFwdParams& p, const PreactCfg& pc, cudaStream_t stream) {
+  switch (pc.preact) {
+    case DSNT_PREACT_TSOFTMAX: return launch_preact_fwd_fast_reg<T, VEC, DSNT_PREACT_TSOFTMAX>(p, pc, stream);
+    case DSNT_PREACT_ABS: return launch_preact_fwd_fast_reg<T, VEC, DSNT_PREACT_ABS>(p, pc, stream);
+    case DSNT_PREACT_RELU: return launch_preact_fwd_fast_reg<T, VEC, DSNT_PREACT_RELU>(p, pc, stream);
+    case DSNT_PREACT_SIGMOID: return launch_preact_fwd_fast_reg<T, VEC, DSNT_PREACT_SIGMOID>(p, pc, stream);
+  }
+  return 1;   // DSNT_PREACT_SOFTMAX with an epsilon: the generic epsilon-exact kernel
+}
+
+template <typename T, int VEC, int GROUP, int REG, int PA>
+int launch_preact_bwd_stream_group(const HeadBwdParams& p, const PreactCfg& pc, cudaStream_t stream) {
+  constexpr int BLOCK = stream_block_threads<GROUP>();
+  constexpr int GPB = BLOCK / GROUP;
+  HeadBwdStreamParams ps;
+  ps.base = p;
+  ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
+  ps.pc = pc;
+  const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
+  if (GROUP % ps.g.wv == 0)
+    head_bwd_stream_kernel<T, VEC, GROUP, REG, true, PA><<<grid, BLOCK, 0, stream>>>(ps);
+  else
+    head_bwd_stream_kernel<T, VEC, GROUP, REG, false, PA><<<grid, BLOCK, 0, stream>>>(ps);
+  return check_launch("head_bwd_stream_kernel<preact>");
+}
+
+template <typename T, int VEC, int REG, int PA>
+int launch_preact_bwd_stream(const HeadBwdParams& p, const PreactCfg& pc, cudaStream_t stream) {
+  const long nvec = static_cast<long>(p.H) * p.W / VEC;
+  return stream_group_is_cta(nvec) ? launch_preact_bwd_stream_group<T, VEC, 256, REG, PA>(p, pc, stream)
+                                   : launch_preact_bwd_stream_group<T, VEC, 32, REG, PA>(p, pc, stream);
+}
+
+template <typename T, int VEC, int PA>
+int launch_preact_bwd_fast_reg(const HeadBwdParams& p, const PreactCfg& pc, cudaStream_t stream) {
+  switch (p.reg) {
+    case DSNT_REG_NONE: return launch_preact_bwd_stream<T, VEC, DSNT_REG_NONE, PA>(p, pc, stream);
+    case DSNT_REG_VAR: return launch_preact_bwd_stream<T, VEC, DSNT_REG_VAR, PA>(p, pc, stream);
+    case DSNT_REG_KL: return launch_preact_bwd_stream<T, VEC, DSNT_REG_KL, PA>(p, pc, stream);
+    case DSNT_REG_JS: return launch_preact_bwd_stream<T, VEC, DSNT_REG_JS, PA>(p, pc, stream);
+    case DSNT_REG_MSE: return launch_preact_bwd_stream<T, VEC, DSNT_REG_MSE, PA>(p, pc, stream);
+  }
+  return 1;
+}
+
+template <typename T, int VEC>
+int launch_preact_bwd_fast(const HeadBwdParams& p, const PreactCfg& pc, cudaStream_t stream) {
+  switch (pc.preact) {
+    case DSNT_PREACT_TSOFTMAX: return launch_preact_bwd_fast_reg<T, VEC, DSNT_PREACT_TSOFTMAX>(p, pc, stream);
+    case DSNT_PREACT_ABS: return launch_preact_bwd_fast_reg<T, VEC, DSNT_PREACT_ABS>(p, pc, stream);
+    case DSNT_PREACT_RELU: return launch_preact_bwd_fast_reg<T, VEC, DSNT_PREACT_RELU>(p, pc, stream);
+    case DSNT_PREACT_SIGMOID: return launch_preact_bwd_fast_reg<T, VEC, DSNT_PREACT_SIGMOID>(p, pc, stream);
+  }
+  return 1;
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 template <typename T, int VEC, int GROUP, int NV, int REG, bool LOGITS>
 int launch_bwd_one(const HeadBwdParams& p, cudaStream_t stream) {
@@ -287,6 +393,7 @@ int launch_bwd_stream_group(const HeadBwdParams& p, cudaStream_t stream) {
   HeadBwdStreamParams ps;
   ps.base = p;
   ps.g = make_geom(p.H, p.W, VEC, GROUP, p.sigma, REG);
+  ps.pc = PreactCfg{DSNT_PREACT_SOFTMAX, 0.f, 0.f};
   const unsigned grid = static_cast<unsigned>((p.n + GPB - 1) / GPB);
   if (GROUP % ps.g.wv == 0)
     head_bwd_stream_kernel<T, VEC, GROUP, REG, true><<<grid, BLOCK, 0, stream>>>(ps);

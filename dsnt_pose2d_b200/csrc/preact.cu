@@ -1,6 +1,7 @@
 // preact.cu -- launchers and extern "C" entry points of the fused head for the non-softmax pre-activations.
 #include "capi_util.cuh"
 #include "head_preact.cuh"
+#include "launch.cuh"
 
 namespace dsnt {
 
@@ -73,7 +74,7 @@ extern "C" {
 
 DSNT_API int dsnt_head_preact_fwd(const void* z, int dtype, int preact, float threshold, float eps, long n, int H, int W,
                                   const float* target, int reg, float sigma, float* coords, float* stats, float* terms,
-                                  void* stream) {
+                                  int variant, void* stream) {
   int rc = check_common(z, dtype, n, H, W, reg);
   if (rc) return rc;
   rc = check_preact(preact, eps);
@@ -94,6 +95,11 @@ DSNT_API int dsnt_head_preact_fwd(const void* z, int dtype, int preact, float th
   ps.pc.preact = preact; ps.pc.threshold = threshold; ps.pc.eps = eps;
   const int vec = pick_vec(dtype, W, z, nullptr);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ps.fl = FlipCfg{nullptr, nullptr, 0};
+  if (variant == 0) {   // the tuned streaming kernels whenever the layout qualifies (returns 1 otherwise)
+    rc = dtype == DSNT_DTYPE_F32 ? launch_preact_fast_fwd_f32(p, ps.pc, vec, s) : launch_preact_fast_fwd_bf16(p, ps.pc, vec, s);
+    if (rc != 1) return rc;
+  }
   if (dtype == DSNT_DTYPE_F32)
     return vec == 4 ? launch_preact_fwd_shape<float, 4>(ps, s) : launch_preact_fwd_shape<float, 1>(ps, s);
   return vec == 8   ? launch_preact_fwd_shape<bf16_t, 8>(ps, s)
@@ -104,7 +110,7 @@ DSNT_API int dsnt_head_preact_fwd(const void* z, int dtype, int preact, float th
 DSNT_API int dsnt_head_preact_bwd(const void* z, int dtype, int preact, float threshold, long n, int H, int W,
                                   const float* target, const float* mask, const float* stats, const float* g_coords,
                                   const float* g_reg, const float* g_loss, const float* denom, float reg_coeff, int reg,
-                                  float sigma, int flags, void* dz, void* stream) {
+                                  float sigma, int flags, void* dz, int variant, void* stream) {
   int rc = check_common(dz, dtype, n, H, W, reg);
   if (rc) return rc;
   rc = check_preact(preact, 0.f);
@@ -128,6 +134,10 @@ DSNT_API int dsnt_head_preact_bwd(const void* z, int dtype, int preact, float th
   ps.pc.preact = preact; ps.pc.threshold = threshold; ps.pc.eps = 0.f;
   const int vec = pick_vec(dtype, W, dz, z);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (variant == 0) {
+    rc = dtype == DSNT_DTYPE_F32 ? launch_preact_fast_bwd_f32(p, ps.pc, vec, s) : launch_preact_fast_bwd_bf16(p, ps.pc, vec, s);
+    if (rc != 1) return rc;
+  }
   if (dtype == DSNT_DTYPE_F32)
     return vec == 4 ? launch_preact_bwd_shape<float, 4>(ps, s) : launch_preact_bwd_shape<float, 1>(ps, s);
   return vec == 8   ? launch_preact_bwd_shape<bf16_t, 8>(ps, s)

@@ -112,7 +112,7 @@ class _FusedHeadPreact(torch.autograd.Function):
     forward: dsnt_head_preact_fwd + dsnt_finish_loss;  backward: dsnt_head_preact_bwd (include/dsnt_b200.h)."""
 
     @staticmethod
-    def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, preact_id, threshold, eps, aux):
+    def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, preact_id, threshold, eps, variant, aux):
         zc, n, h, w = _flat_heatmaps(z)
         dev = zc.device
         with torch.cuda.device(dev):
@@ -122,7 +122,8 @@ class _FusedHeadPreact(torch.autograd.Function):
             terms = torch.empty(n, 2, dtype=torch.float32, device=dev)
             out8 = torch.empty(8, dtype=torch.float32, device=dev)
             _lib.call('dsnt_head_preact_fwd', zc.data_ptr(), _lib.dtype_id(zc), preact_id, threshold, eps, n, h, w,
-                      _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), stream)
+                      _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), variant,
+                      stream)
             ws = _lib.finish_workspace(dev)
             _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, reg_coeff, out8.data_ptr(),
                       ws.data_ptr(), stream)
@@ -130,7 +131,7 @@ class _FusedHeadPreact(torch.autograd.Function):
                 all_reduce_sums(out8, group)
                 _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
         ctx.save_for_backward(zc, target, mask, stats, out8)
-        ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, z.shape)
+        ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, variant, z.shape)
         ctx.set_materialize_grads(False)
         aux['out8'] = out8
         return coords.view(*z.shape[:-2], 2), out8[6]
@@ -138,10 +139,10 @@ class _FusedHeadPreact(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_coords, g_loss):
         zc, target, mask, stats, out8 = ctx.saved_tensors
-        n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, shape = ctx.meta
+        n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, variant, shape = ctx.meta
         dev = zc.device
         if g_coords is None and g_loss is None:
-            return (None,) * 12
+            return (None,) * 13
         with torch.cuda.device(dev):
             stream = _lib.stream_of(zc)
             if g_coords is not None:
@@ -152,8 +153,8 @@ class _FusedHeadPreact(torch.autograd.Function):
             _lib.call('dsnt_head_preact_bwd', zc.data_ptr(), _lib.dtype_id(zc), preact_id, threshold, n, h, w,
                       _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(), _lib.ptr(g_coords), None,
                       _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
-                      reg_coeff, reg_id, sigma, flags, dz.data_ptr(), stream)
-        return (dz.view(shape),) + (None,) * 11
+                      reg_coeff, reg_id, sigma, flags, dz.data_ptr(), variant, stream)
+        return (dz.view(shape),) + (None,) * 12
 
 
 # what HumanPoseModel._hm_preact passes for each `--preact` choice (src/dsnt/model.py:29-41)
@@ -211,7 +212,7 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
         coords, loss = _FusedHeadPreact.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
                                               flags, group, _lib.PREACT_IDS[preact],
                                               float(d_thr if threshold is None else threshold),
-                                              float(d_eps if eps is None else eps), aux)
+                                              float(d_eps if eps is None else eps), int(variant), aux)
     out8 = aux['out8']
     return HeadOutput(coords, loss, out8[4], out8[5])
 

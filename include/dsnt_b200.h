@@ -141,15 +141,17 @@ DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, lon
  *   eps        added to the normaliser sum (the reference uses 1e-12)
  *   stats      [N,DSNT_STATS_K]: [0] max*log2(e) [1] 1/(sum+eps) [2..6] as dsnt_head_fwd
  *              [7] Gaussian normaliser (kl/js/mse) or 1 - sum P (var)
+ *   variant    0 = automatic: the tuned streaming kernels (the ones dsnt_head_fwd/bwd use, instantiated per
+ *              pre-activation) when the layout qualifies, else the generic epsilon-exact kernels; 1 forces the generic ones
  * Other arguments as dsnt_head_fwd / dsnt_head_bwd.
  */
 DSNT_API int dsnt_head_preact_fwd(const void* z, int dtype, int preact, float threshold, float eps, long n, int H, int W,
                                   const float* target, int reg, float sigma, float* coords, float* stats, float* terms,
-                                  void* stream);
+                                  int variant, void* stream);
 DSNT_API int dsnt_head_preact_bwd(const void* z, int dtype, int preact, float threshold, long n, int H, int W,
                                   const float* target, const float* mask, const float* stats, const float* g_coords,
                                   const float* g_reg, const float* g_loss, const float* denom, float reg_coeff, int reg,
-                                  float sigma, int flags, void* dz, void* stream);
+                                  float sigma, int flags, void* dz, int variant, void* stream);
 
 /*
  * Inference with flip test-time augmentation, fused in front of the forward-only head.

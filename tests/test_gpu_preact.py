@@ -29,13 +29,13 @@ def tp():
     return torch_port
 
 
-def run_head(dp, z, target, mask, preact, reg, hm_sigma=1.0, coeff=1.0):
+def run_head(dp, z, target, mask, preact, reg, hm_sigma=1.0, coeff=1.0, variant=0):
     zz = z.detach().clone().to(DEV).requires_grad_(True)
     tt = None if target is None else target.to(DEV)
     mm = None if mask is None else mask.to(DEV)
     # eps=... forces the epsilon-exact kernels for 'softmax' too (the default routes softmax to the tuned kernels)
     kw = {'eps': 0.0} if preact == 'softmax' else {}
-    out = dp.dsnt_head(zz, tt, mm, reg=reg, hm_sigma=hm_sigma, reg_coeff=coeff, preact=preact, **kw)
+    out = dp.dsnt_head(zz, tt, mm, reg=reg, hm_sigma=hm_sigma, reg_coeff=coeff, preact=preact, variant=variant, **kw)
     out.loss.backward()
     torch.cuda.synchronize()
     return {'loss': out.loss.item(), 'euclid': out.euclid.item(), 'reg': out.reg.item(),
@@ -54,16 +54,18 @@ def check(got, ref_loss, ref_coords, ref_dz, what, tol=TOL, dz_tol=None):
     assert e_l2 < dz_tol and e_max < dz_tol * 4, (what, 'dz', e_l2, e_max)
 
 
+# variant 0 = the tuned streaming kernels where the layout qualifies (64x64 here), 1 = the generic epsilon-exact kernels
+@pytest.mark.parametrize('variant', [0, 1])
 @pytest.mark.parametrize('reg', REGS)
 @pytest.mark.parametrize('preact', PREACTS)
-def test_preact_head_matches_reference_golden(dp, golden_preact, preact, reg):
+def test_preact_head_matches_reference_golden(dp, golden_preact, preact, reg, variant):
     g = golden_preact
     for name in g.cases:
         b, c, h, w, hm_sigma, coeff, with_mask = head_case_params(g, name)
         z = torch.from_numpy(g[name + '/z'])
         target = torch.from_numpy(g[name + '/target'])
         mask = torch.from_numpy(g[name + '/mask']) if with_mask else None
-        got = run_head(dp, z, target, mask, preact, reg, hm_sigma, coeff)
+        got = run_head(dp, z, target, mask, preact, reg, hm_sigma, coeff, variant)
         key = '%s/%s/%s' % (name, preact, reg)
         check(got, float(g[key + '/loss']), g['%s/%s/coords' % (name, preact)], g[key + '/dz'].astype(np.float64),
               'golden %s %s %s' % (name, preact, reg))
@@ -71,11 +73,20 @@ def test_preact_head_matches_reference_golden(dp, golden_preact, preact, reg):
         assert abs(got['reg'] - float(g[key + '/reg'])) < TOL * max(1.0, abs(got['reg']))
 
 
+@pytest.mark.parametrize('shape', [(6, 6), (64, 64)])
 @pytest.mark.parametrize('preact', ['thresholded_softmax', 'relu'])
-def test_dead_heatmaps_give_zero_probability_and_zero_gradient(dp, golden_preact, preact):
+def test_dead_heatmaps_give_zero_probability_and_zero_gradient(dp, tp, golden_preact, preact, shape):
     g = golden_preact
     z = torch.from_numpy(g['dead/z'])
     target = torch.from_numpy(g['dead/target'])
+    if shape != (6, 6):      # the same situation at a size the tuned kernels take: checked against the fp64 oracle
+        z = -(torch.rand(1, 2, *shape, generator=torch.Generator().manual_seed(5)) + 1.0)
+        for reg in REGS:
+            ref = tp.head_loss_and_grad(z, target, None, reg, 1.0, 1.0, dtype=torch.float64, preact=preact)
+            got = run_head(dp, z, target, None, preact, reg)
+            assert abs(got['loss'] - ref['loss'].item()) <= TOL * max(abs(ref['loss'].item()), 1e-3), (reg, got['loss'])
+            assert np.abs(got['dz']).max() == 0.0 and np.abs(got['coords']).max() == 0.0
+        return
     for reg in REGS:
         got = run_head(dp, z, target, None, preact, reg)
         ref = float(g['dead/%s/%s/loss' % (preact, reg)])
@@ -84,11 +95,13 @@ def test_dead_heatmaps_give_zero_probability_and_zero_gradient(dp, golden_preact
         assert np.abs(got['coords']).max() == 0.0
 
 
+@pytest.mark.parametrize('variant', [0, 1])
 @pytest.mark.parametrize('reg', REGS)
 @pytest.mark.parametrize('preact', ['thresholded_softmax', 'abs', 'relu', 'sigmoid'])
-@pytest.mark.parametrize('shape,scale', [((32, 16, 64, 64), 1.0), ((64, 16, 28, 28), 1.0), ((2, 3, 7, 7), 2.0),
-                                         ((2, 2, 130, 132), 1.0), ((1, 2, 256, 256), 1.0), ((2, 2, 33, 31), 1.0)])
-def test_preact_head_matches_fp64_oracle(dp, tp, preact, reg, shape, scale):
+@pytest.mark.parametrize('shape,scale', [((32, 16, 64, 64), 1.0), ((8, 16, 64, 64), 5.0), ((64, 16, 28, 28), 1.0),
+                                         ((2, 3, 7, 7), 2.0), ((2, 2, 130, 132), 1.0), ((1, 2, 256, 256), 1.0),
+                                         ((2, 2, 33, 31), 1.0), ((2, 4, 128, 128), 3.0), ((4, 4, 32, 32), 1.0)])
+def test_preact_head_matches_fp64_oracle(dp, tp, preact, reg, shape, scale, variant):
     """BASELINE head shapes (cfg 1, cfg 2), an odd scalar-path size, a streaming-path size (> 128x128) and 256x256."""
     b, c, h, w = shape
     gen = torch.Generator().manual_seed(11)
@@ -96,9 +109,27 @@ def test_preact_head_matches_fp64_oracle(dp, tp, preact, reg, shape, scale):
     target = torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8
     mask = (torch.rand(b, c, generator=gen) > 0.1).float()
     ref = tp.head_loss_and_grad(z, target, mask, reg, 1.0, 1.0, dtype=torch.float64, preact=preact)
-    got = run_head(dp, z, target, mask, preact, reg)
+    got = run_head(dp, z, target, mask, preact, reg, variant=variant)
     check(got, ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(),
-          '%s %s %s' % ('x'.join(map(str, shape)), preact, reg))
+          '%s %s %s v%d' % ('x'.join(map(str, shape)), preact, reg, variant))
+
+
+@pytest.mark.parametrize('preact', ['thresholded_softmax', 'abs', 'relu', 'sigmoid'])
+def test_preact_trained_like_heatmaps_and_any_sigma(dp, tp, preact):
+    """Peaked 'trained network' maps (positive peak near the target, negative tails -> many exact zeros for relu /
+    threshold) and Gaussian targets from sub-pixel to image-wide: the window optimisation must not show."""
+    gen = torch.Generator().manual_seed(14)
+    b, c, h, w = 4, 8, 64, 64
+    target = torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8
+    g = tp.make_gauss(target + 0.05 * torch.randn(b, c, 2, generator=gen), w, h, 2.0 / w)
+    z = (g + 1e-6).log() + 8.0 + 0.1 * torch.randn(b, c, h, w, generator=gen)
+    mask = (torch.rand(b, c, generator=gen) > 0.1).float()
+    for reg in ('js', 'kl', 'mse'):
+        for hm_sigma in (0.4, 1.0, 3.0, 20.0):
+            ref = tp.head_loss_and_grad(z, target, mask, reg, hm_sigma, 1.0, dtype=torch.float64, preact=preact)
+            got = run_head(dp, z, target, mask, preact, reg, hm_sigma=hm_sigma)
+            check(got, ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(),
+                  'trained %s %s sigma %.1f' % (preact, reg, hm_sigma))
 
 
 @pytest.mark.parametrize('preact', ['thresholded_softmax', 'relu', 'sigmoid'])

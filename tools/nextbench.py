@@ -69,6 +69,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--batch', type=int, default=4096)
+    ap.add_argument('--variant', type=int, default=0, help='1 = force the generic pre-activation kernels')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     peak, how = peak_gbs()
@@ -99,12 +100,12 @@ def main():
                 def fwd(i):
                     _lib.call('dsnt_head_preact_fwd', z.data_ptr(), _lib.dtype_id(z), pid, thr, eps, n, h, w,
                               target.data_ptr(), rid, 2.0 / w, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(),
-                              stream)
+                              args.variant, stream)
 
                 def bwd(i):
                     _lib.call('dsnt_head_preact_bwd', z.data_ptr(), _lib.dtype_id(z), pid, thr, n, h, w,
                               target.data_ptr(), mask.data_ptr(), stats.data_ptr(), None, None, gl.data_ptr(),
-                              out8[3:4].data_ptr(), 1.0, rid, 2.0 / w, 0, dz.data_ptr(), stream)
+                              out8[3:4].data_ptr(), 1.0, rid, 2.0 / w, 0, dz.data_ptr(), args.variant, stream)
                 tf = time_calls(fwd, args.iters)
                 _lib.call('dsnt_finish_loss', terms.data_ptr(), mask.data_ptr(), n, 1.0, out8.data_ptr(), ws.data_ptr(),
                           stream)
