@@ -7,7 +7,11 @@ Workload (BASELINE.json configs[3], the one the metric is quoted on): per GPU a 
 MPII joints x 64x64 fp32 logits, Euclidean loss + JS regulariser (sigma = 1 px), joint mask; weak scaling
 (every rank owns a fixed 4096-sample shard of a 4096*N batch, three floats are all-reduced per step).
 
-A "step" is one pass of the hot path over one batch: fused forward (coords, loss) + backward (dL/dZ).
+A "step" is one pass of the hot path over one batch: fused forward (coords, loss) + backward (dL/dZ), through the
+public autograd API (`dsnt_head(...).loss.backward()`).  --path one-pass (default) lets the forward also write dL/dZ
+while the heatmap is on chip (dsnt_head_step: 2*H*W*sizeof algorithmic bytes per heatmap); --path two-kernel is the
+forward kernel + the streaming backward kernel (3*H*W*sizeof).  Heatmaps too large for the one-pass kernel
+(256x256) take the two-kernel path either way; config.path says which ran.
   value  whole-job heatmaps/s with Z already resident in HBM (CUDA events, barrier + sync both sides, max
          over ranks).  Z is 1 GiB per step, far larger than the 126 MB L2, so no flush is needed.
   e2e    the same step through the public API with HOST buffers: pinned Z/target/mask -> device copies
@@ -55,6 +59,7 @@ def parse_args():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--path', default='one-pass', choices=['one-pass', 'two-kernel'])
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='time eager autograd calls instead of replaying the captured step (CUDA graph)')
     return ap.parse_args()
@@ -273,9 +278,12 @@ def main_ours(args):
     target = torch.rand(bsz, joints, 2, device=dev) * 1.6 - 0.8
     mask = (torch.rand(bsz, joints, device=dev) > 0.1).float()
 
+    from dsnt_pose2d_b200.head import step_supported
+    one_pass = args.path == 'one-pass' and step_supported(z)
+
     def step():
         z.grad = None
-        out = dp.dsnt_head(z, target, mask, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group)
+        out = dp.dsnt_head(z, target, mask, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group, one_pass=one_pass)
         out.loss.backward()
         return out
 
@@ -333,7 +341,8 @@ def main_ours(args):
 
     # ---------------- pass 2 (same steps, still inside the clock-sampled window): CUDA events around every launch of
     # our kernels, on the stream they are enqueued on, for the per-kernel roofline
-    _lib.event_log = {'dsnt_head_fwd': [], 'dsnt_head_bwd': [], 'dsnt_finish_loss': []}
+    _lib.event_log = {'dsnt_head_fwd': [], 'dsnt_head_bwd': [], 'dsnt_head_step': [], 'dsnt_finish_loss': [],
+                      'dsnt_mask_count': [], 'dsnt_scale_unless_one': []}
     for _ in range(args.steps):
         step()
     barrier()
@@ -358,7 +367,7 @@ def main_ours(args):
             td.copy_(th, non_blocking=True)
             md.copy_(mh, non_blocking=True)
             zin = zd.detach().requires_grad_(True)
-            out = dp.dsnt_head(zin, td, md, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group)
+            out = dp.dsnt_head(zin, td, md, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group, one_pass=one_pass)
             out.loss.backward()
             loss_h.copy_(out.loss.detach(), non_blocking=True)
             coords_h.copy_(out.coords.detach(), non_blocking=True)
@@ -393,19 +402,22 @@ def main_ours(args):
     peak, peak_how = measured_peak()
     hw = h * w
     alg = {'dsnt_head_fwd': n_local * (hw * esize + 56),        # read Z; target 8 r, coords 8 w, stats 32 w, terms 8 w
-           'dsnt_head_bwd': n_local * (2 * hw * esize + 44)}    # read Z, write dZ; stats 32 r, target 8 r, mask 4 r
-    dominant = max(('dsnt_head_fwd', 'dsnt_head_bwd'), key=lambda k: kernel_ms[k] or 0.0)
+           'dsnt_head_bwd': n_local * (2 * hw * esize + 44),    # read Z, write dZ; stats 32 r, target 8 r, mask 4 r
+           'dsnt_head_step': n_local * (2 * hw * esize + 68)}   # read Z, write dZ; target 8 r, mask 4 r, coords/stats/terms 56 w
+    ran = [k for k in alg if kernel_ms.get(k)]
+    dominant = max(ran, key=lambda k: kernel_ms[k])
     per_kernel = {}
-    for k in ('dsnt_head_fwd', 'dsnt_head_bwd'):
+    for k in ran:
         ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
         per_kernel[k] = {'ms': kernel_ms[k], 'algorithmic_bytes': alg[k], 'achieved_gbs': ach, 'frac': ach / peak}
-    step_bytes = alg['dsnt_head_fwd'] + alg['dsnt_head_bwd']
+    small = {k: kernel_ms[k] for k in ('dsnt_finish_loss', 'dsnt_mask_count', 'dsnt_scale_unless_one') if kernel_ms.get(k)}
+    step_bytes = sum(alg[k] for k in ran)
     step_gbs = step_bytes * world / (elapsed_ms / args.steps * 1e-3) / 1e9
     traffic = committed_traffic(args.workload)
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': per_kernel[dominant]['achieved_gbs'], 'peak': peak,
                 'unit': 'GB/s', 'frac': per_kernel[dominant]['frac'],
                 'traffic': (traffic or {}).get(dominant) if isinstance(traffic, dict) else None,
-                'peak_source': peak_how, 'kernels': per_kernel,
+                'peak_source': peak_how, 'kernels': per_kernel, 'small_kernels_ms': small,
                 'step': {'algorithmic_bytes_per_gpu': step_bytes, 'achieved_gbs_per_gpu': step_gbs / world,
                          'frac': step_gbs / world / peak}}
 
@@ -423,6 +435,10 @@ def main_ours(args):
                    'parallelism': 'batch-sharded x%d, 3-float all-reduce per step' % world,
                    'l2_policy': 'inputs larger than L2 (%.0f MiB of logits per step vs 126 MB L2)'
                                 % (n_local * hw * esize / 2 ** 20),
+                   'path': ('one-pass: dsnt_mask_count + dsnt_head_step (forward and dL/dZ while the heatmap is in shared '
+                            'memory, 2*H*W*sizeof algorithmic bytes) + dsnt_finish_loss; backward only scales in place '
+                            'when d(loss) != 1') if one_pass else
+                           'two-kernel: dsnt_head_fwd + dsnt_finish_loss + dsnt_head_bwd (3*H*W*sizeof algorithmic bytes)',
                    'launch': graph_note},
         'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks, 'e2e': e2e,
         'gpu_launches': launches,

@@ -45,6 +45,11 @@ SIGNATURES = {
     'dsnt_draw_gaussians': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, ctypes.c_double, ctypes.c_double, _c_int,
                                      _c_ptr, _c_ptr]),
     'dsnt_decode_heatmaps': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_int, _c_ptr, _c_ptr]),
+    'dsnt_head_step_supported': (_c_int, [_c_int, _c_int, _c_int]),
+    'dsnt_head_step': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int,
+                                _c_float, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    'dsnt_mask_count': (_c_int, [_c_ptr, _c_long, _c_ptr, _c_ptr, _c_ptr]),
+    'dsnt_scale_unless_one': (_c_int, [_c_ptr, _c_int, _c_long, _c_ptr, _c_ptr]),
     'dsnt_finish_loss_stacked': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_finish_workspace_bytes': (_c_int, []),
     'dsnt_finish_loss': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_float, _c_ptr, _c_ptr, _c_ptr]),

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
   const long lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
   float sd = 0.f, sr = 0.f, sm = 0.f, unused = 0.f;
   for (long i = lo + threadIdx.x; i < hi; i += kFinishBlock) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(terms) + i);
+    const float2 t = terms ? __ldg(reinterpret_cast<const float2*>(terms) + i) : make_float2(0.f, 0.f);   // null: mask count only
     const float w = mask ? __ldg(mask + (i % n_per)) : 1.0f;
     sd = fmaf(w, t.x, sd);
     sr = fmaf(w, t.y, sr);
@@ -75,6 +75,32 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
       out[0] = a; out[1] = b; out[2] = c;
       write_loss_tail(out, reg_coeff);
       *ticket = 0u;
+    }
+  }
+}
+
+// x *= *g unless *g == 1 (then nothing is read or written): lets the one-pass step hand out the gradient it already
+// computed for d(loss) = 1 and stay exact -- and CUDA-graph capturable -- for any other upstream gradient.
+template <typename T>
+__global__ void __launch_bounds__(256) scale_unless_one_kernel(T* __restrict__ x, long nvec16, long numel,
+                                                               const float* __restrict__ g) {
+  const float s = __ldg(g);
+  if (s == 1.0f) return;
+  constexpr int PER = 16 / sizeof(T);
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec16; i += stride) {
+    float v[PER];
+    VecIO<T, PER>::load(x, i * PER, v);
+#pragma unroll
+    for (int c = 0; c < PER; ++c) v[c] *= s;
+    VecIO<T, PER>::store(x, i * PER, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long i = nvec16 * PER; i < numel; ++i) {
+      float v[1];
+      VecIO<T, 1>::load(x, i, v);
+      v[0] *= s;
+      VecIO<T, 1>::store(x, i, v);
     }
   }
 }

@@ -155,6 +155,31 @@ DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, flo
   return dsnt_finish_loss_stacked(terms, mask, n, 1, reg_coeff, out, workspace, stream);
 }
 
+DSNT_API int dsnt_mask_count(const float* mask, long n, float* out, float* workspace, void* stream) {
+  if (n < 0 || !out || !workspace || !aligned(workspace, 16)) { set_error("dsnt_mask_count: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  long ctas = (n + 4095) / 4096;
+  if (ctas < 1) ctas = 1;
+  if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
+  finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      nullptr, mask, n, n > 0 ? n : 1, 0.f, out, workspace);
+  return check_launch("finish_loss_kernel<count>");
+}
+
+DSNT_API int dsnt_scale_unless_one(void* x, int dtype, long numel, const float* g, void* stream) {
+  if (numel < 0 || !g || (!x && numel > 0)) { set_error("dsnt_scale_unless_one: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (numel == 0) return DSNT_OK;
+  const bool al = aligned(x, 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == DSNT_DTYPE_F32) {
+    const long nv = al ? numel / 4 : 0;
+    scale_unless_one_kernel<float><<<148 * 8, 256, 0, s>>>(static_cast<float*>(x), nv, numel, g);
+  } else if (dtype == DSNT_DTYPE_BF16) {
+    const long nv = al ? numel / 8 : 0;
+    scale_unless_one_kernel<__nv_bfloat16><<<148 * 8, 256, 0, s>>>(static_cast<__nv_bfloat16*>(x), nv, numel, g);
+  } else { set_error("unsupported dtype %d", dtype); return DSNT_ERR_UNSUPPORTED; }
+  return check_launch("scale_unless_one_kernel");
+}
+
 DSNT_API int dsnt_combine_loss(float* out, float reg_coeff, void* stream) {
   if (!out) { set_error("dsnt_combine_loss: null"); return DSNT_ERR_BAD_ARG; }
   combine_loss_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out, reg_coeff);

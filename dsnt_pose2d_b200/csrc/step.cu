@@ -1,0 +1,139 @@
+// step.cu -- launcher and extern "C" entry point of the one-pass training step (head_step.cuh).
+#include <cstdlib>
+
+#include "capi_util.cuh"
+#include "head_step.cuh"
+
+namespace dsnt {
+
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+template <typename T, int VEC, int REG, bool FIXC, int NBUF, int GROUP>
+static int launch_step_nbuf(HeadStepParams p, cudaStream_t stream) {
+  auto kern = head_step_kernel<T, VEC, REG, FIXC, NBUF, GROUP>;
+  p.nwarps = kStepSmemBudget / (p.buf_bytes * NBUF);   // groups per CTA
+  constexpr int kMaxGroups = kStepMaxWarps * 32 / GROUP;
+  if (p.nwarps > kMaxGroups) p.nwarps = kMaxGroups;
+  const size_t smem = static_cast<size_t>(p.nwarps) * NBUF * p.buf_bytes;
+  static size_t configured = 0;     // per instantiation: the opt-in only ever needs to grow
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return check_launch("head_step_kernel (shared-memory opt-in)");
+    configured = smem;
+  }
+  long ctas = (p.n + p.nwarps - 1) / p.nwarps;
+  if (ctas > sm_count()) ctas = sm_count();   // persistent: one CTA per SM, every warp loops over heatmaps
+  kern<<<static_cast<unsigned>(ctas), p.nwarps * GROUP, smem, stream>>>(p);
+  return check_launch("head_step_kernel");
+}
+
+static int step_direct_store() {
+  static const int v = [] { const char* e = std::getenv("DSNT_TUNE_STEP_STG"); return e ? std::atoi(e) : 1; }();
+  return v;
+}
+
+static int step_nbuf() {
+  static const int v = [] { const char* e = std::getenv("DSNT_TUNE_STEP_NBUF"); return e ? std::atoi(e) : 0; }();
+  return v;
+}
+
+static int step_group() {
+  static const int v = [] { const char* e = std::getenv("DSNT_TUNE_STEP_GROUP"); return e ? std::atoi(e) : 0; }();
+  return v;
+}
+
+// Measured on B200 at cfg 4 (profiles/r01_v4_step_sweep.txt): one warp per heatmap, one buffer per warp and direct
+// 128-bit stores is the best all-round setting (JS 369 us, none 387 us for 65 536 heatmaps of 64x64 fp32); two buffers
+// per warp reach 0.97 of HBM peak without a regulariser (332 us) but leave too few warps for the divergence arithmetic.
+// DSNT_TUNE_STEP_NBUF / _GROUP / _STG override for experiments.
+template <typename T, int VEC, int REG, bool FIXC, int GROUP>
+static int launch_step_one(const HeadStepParams& p, cudaStream_t stream) {
+  int nb = step_nbuf();
+  if (nb != 1 && nb != 2) nb = 1;
+  return nb == 2 ? launch_step_nbuf<T, VEC, REG, FIXC, 2, GROUP>(p, stream) : launch_step_nbuf<T, VEC, REG, FIXC, 1, GROUP>(p, stream);
+}
+
+// one warp per heatmap by default (DSNT_TUNE_STEP_GROUP=64 selects two)
+template <typename T, int VEC, int REG>
+static int launch_step_fixc(HeadStepParams p, cudaStream_t stream) {
+  if (step_group() != 64) {
+    p.g = make_geom(p.H, p.W, VEC, 32, p.sigma > 0.f ? p.sigma : 1.f, REG);
+    return (32 % p.g.wv == 0) ? launch_step_one<T, VEC, REG, true, 32>(p, stream) : launch_step_one<T, VEC, REG, false, 32>(p, stream);
+  }
+  p.g = make_geom(p.H, p.W, VEC, 64, p.sigma > 0.f ? p.sigma : 1.f, REG);
+  return (64 % p.g.wv == 0) ? launch_step_one<T, VEC, REG, true, 64>(p, stream) : launch_step_one<T, VEC, REG, false, 64>(p, stream);
+}
+
+template <typename T, int VEC>
+static int launch_step_reg(const HeadStepParams& p, int reg, cudaStream_t stream) {
+  switch (reg) {
+    case DSNT_REG_NONE: return launch_step_fixc<T, VEC, DSNT_REG_NONE>(p, stream);
+    case DSNT_REG_VAR: return launch_step_fixc<T, VEC, DSNT_REG_VAR>(p, stream);
+    case DSNT_REG_KL: return launch_step_fixc<T, VEC, DSNT_REG_KL>(p, stream);
+    case DSNT_REG_JS: return launch_step_fixc<T, VEC, DSNT_REG_JS>(p, stream);
+    case DSNT_REG_MSE: return launch_step_fixc<T, VEC, DSNT_REG_MSE>(p, stream);
+  }
+  set_error("bad reg %d", reg);
+  return DSNT_ERR_BAD_ARG;
+}
+
+}  // namespace dsnt
+
+using namespace dsnt;
+
+extern "C" {
+
+DSNT_API int dsnt_head_step_supported(int dtype, int H, int W) {
+  if (dtype != DSNT_DTYPE_F32 && dtype != DSNT_DTYPE_BF16) return 0;
+  if (H <= 0 || W <= 0) return 0;
+  const int vec = dtype == DSNT_DTYPE_F32 ? 4 : 8;
+  const long bytes = static_cast<long>(H) * W * (dtype == DSNT_DTYPE_F32 ? 4 : 2);
+  if (W % vec != 0 || bytes % 16 != 0) return 0;
+  const long buf = (bytes + 127) / 128 * 128;
+  return kStepSmemBudget / buf >= 4 ? 1 : 0;
+}
+
+DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                            const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
+                            float* coords, float* stats, float* terms, void* dz, void* stream) {
+  int rc = check_common(z, dtype, n, H, W, reg);
+  if (rc) return rc;
+  if (n == 0) return DSNT_OK;
+  if (!dz || !coords || !denom) { set_error("dsnt_head_step: z, dz, coords and denom are required"); return DSNT_ERR_BAD_ARG; }
+  if (reg_needs_gauss(reg) && !target) { set_error("reg %d needs a target", reg); return DSNT_ERR_BAD_ARG; }
+  if (reg != DSNT_REG_NONE && !(sigma > 0.f)) { set_error("sigma must be > 0"); return DSNT_ERR_BAD_ARG; }
+  if (!aligned(coords, 8) || (stats && !aligned(stats, 16)) || (terms && !aligned(terms, 8)) || (target && !aligned(target, 8))) {
+    set_error("per-heatmap buffers must be naturally aligned (coords/terms/target 8 B, stats 16 B)");
+    return DSNT_ERR_BAD_ARG;
+  }
+  if (!dsnt_head_step_supported(dtype, H, W) || !aligned(z, 16) || !aligned(dz, 16)) {
+    set_error("dsnt_head_step: heatmap %dx%d (dtype %d) does not fit the one-pass kernel (needs W %% %d == 0, 16-byte "
+              "aligned bases and at least 4 heatmaps in shared memory); use dsnt_head_fwd + dsnt_head_bwd",
+              H, W, dtype, dtype == DSNT_DTYPE_F32 ? 4 : 8);
+    return DSNT_ERR_UNSUPPORTED;
+  }
+  const int es = dtype == DSNT_DTYPE_F32 ? 4 : 2;
+  const int vec = dtype == DSNT_DTYPE_F32 ? 4 : 8;
+  HeadStepParams p;
+  p.z = z; p.dz = dz; p.target = target; p.mask = mask; p.denom = denom; p.g_loss = g_loss;
+  p.coords = coords; p.stats = stats; p.terms = terms;
+  p.n = n; p.H = H; p.W = W; p.flags = flags; p.sigma = sigma; p.reg_coeff = reg_coeff;
+  p.g = make_geom(H, W, vec, 32, sigma > 0.f ? sigma : 1.f, reg);
+  p.buf_bytes = (H * W * es + 127) / 128 * 128;
+  p.nwarps = 0;   // chosen with the number of buffers per warp at launch
+  p.direct_store = step_direct_store();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dtype == DSNT_DTYPE_F32 ? launch_step_reg<float, 4>(p, reg, s) : launch_step_reg<__nv_bfloat16, 8>(p, reg, s);
+}
+
+}  // extern "C"

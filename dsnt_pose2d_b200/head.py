@@ -168,7 +168,7 @@ PREACT_DEFAULTS = {
 
 
 def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_sigma=None, group=None,
-              variant=0, input_is_logits=True, preact='softmax', threshold=None, eps=None):
+              variant=0, input_is_logits=True, preact='softmax', threshold=None, eps=None, one_pass=False):
     """Fused head.
 
     Args:
@@ -183,6 +183,11 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
         preact: how raw heatmaps become a distribution (src/dsnt/model.py:24-45): 'softmax' (the tuned kernels),
             'thresholded_softmax', 'abs', 'relu', 'sigmoid' (the epsilon-exact kernels of csrc/head_preact.cuh).
             `threshold` / `eps` default to what the reference passes (-0.5 / 1e-12).
+        one_pass: evaluate forward AND the gradient for d(loss) = 1 in one pass over the logits (`dsnt_head_step`,
+            8 instead of 12 bytes per fp32 pixel); `loss.backward()` then only hands the stored gradient out.  Needs
+            the softmax pre-activation and heatmaps of which at least four fit in shared memory (`step_supported`);
+            otherwise the two-kernel path is taken silently.  Costs one extra heatmap-sized buffer if backward is
+            never called, so leave it off for inference.
     Returns:
         HeadOutput(coords [..., 2] float32, loss 0-dim float32, euclid 0-dim, reg 0-dim);
         `loss` and `coords` are differentiable w.r.t. `z`.
@@ -202,7 +207,11 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     aux = {}
     if preact not in _lib.PREACT_IDS:
         raise Exception('unrecognised heatmap preactivation function: {}'.format(preact))   # model.py:42-43
-    if preact == 'softmax' and threshold is None and eps is None:
+    if (one_pass and preact == 'softmax' and threshold is None and eps is None and input_is_logits
+            and z.requires_grad and torch.is_grad_enabled() and step_supported(z)):
+        coords, loss = _FusedHeadStep.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
+                                            flags, group, aux)
+    elif preact == 'softmax' and threshold is None and eps is None:
         coords, loss = _FusedHead.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
                                         flags, group, int(variant), bool(input_is_logits), aux)
     else:
@@ -215,6 +224,76 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
                                               float(d_eps if eps is None else eps), int(variant), aux)
     out8 = aux['out8']
     return HeadOutput(coords, loss, out8[4], out8[5])
+
+
+def step_supported(z):
+    """True when `dsnt_head_step` (one pass over the logits) can take heatmaps of this dtype and size."""
+    if z.dtype not in (torch.float32, torch.bfloat16) or z.dim() < 2 or z.numel() == 0:
+        return False
+    return bool(_lib.LIB.dsnt_head_step_supported(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1])))
+
+
+class _FusedHeadStep(torch.autograd.Function):
+    """One pass over the logits for the whole training step (include/dsnt_b200.h: dsnt_mask_count + dsnt_head_step +
+    dsnt_finish_loss).  The forward already writes dL/dz for d(loss) = 1; the backward hands it out, scaled in place by
+    the actual d(loss) (`dsnt_scale_unless_one`: no traffic when it is 1, as in `loss.backward()`).  A gradient
+    w.r.t. the coordinates, if anybody asks for one, goes through the regular backward kernel on the saved statistics."""
+
+    @staticmethod
+    def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, aux):
+        zc, n, h, w = _flat_heatmaps(z)
+        dev = zc.device
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zc)
+            coords = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            stats = torch.empty(n, _lib.STATS_K, dtype=torch.float32, device=dev)
+            terms = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            cnt8 = torch.empty(8, dtype=torch.float32, device=dev)
+            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            dz = torch.empty_like(zc)
+            ws = _lib.finish_workspace(dev)
+            # the denominator of masked_average depends on the mask alone: known before the forward
+            _lib.call('dsnt_mask_count', _lib.ptr(mask), n, cnt8.data_ptr(), ws.data_ptr(), stream)
+            if group is not None:
+                all_reduce_sums(cnt8, group)
+                _lib.call('dsnt_combine_loss', cnt8.data_ptr(), reg_coeff, stream)
+            _lib.call('dsnt_head_step', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
+                      cnt8[3:4].data_ptr(), None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(),
+                      terms.data_ptr(), dz.data_ptr(), stream)
+            _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, reg_coeff, out8.data_ptr(),
+                      ws.data_ptr(), stream)
+            if group is not None:
+                all_reduce_sums(out8, group)
+                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+        ctx.save_for_backward(zc, target, mask, stats, out8, dz)
+        ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, z.shape)
+        ctx.set_materialize_grads(False)
+        aux['out8'] = out8
+        aux['dz'] = dz
+        return coords.view(*z.shape[:-2], 2), out8[6]
+
+    @staticmethod
+    def backward(ctx, g_coords, g_loss):
+        zc, target, mask, stats, out8, dz = ctx.saved_tensors
+        n, h, w, reg_id, sigma, reg_coeff, flags, shape = ctx.meta
+        dev = zc.device
+        if g_coords is None and g_loss is None:
+            return (None,) * 9
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zc)
+            if g_loss is not None:
+                g_loss = g_loss.to(torch.float32).contiguous()
+            if g_coords is None:
+                # the usual case (train.py:381): the gradient is already there
+                _lib.call('dsnt_scale_unless_one', dz.data_ptr(), _lib.dtype_id(dz), dz.numel(), g_loss.data_ptr(), stream)
+                return (dz.view(shape),) + (None,) * 8
+            g_coords = g_coords.to(torch.float32).contiguous()
+            full = torch.empty_like(zc)
+            _lib.call('dsnt_head_bwd', zc.data_ptr(), _lib.dtype_id(zc), 1, n, h, w,
+                      _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(), g_coords.data_ptr(), None,
+                      _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
+                      reg_coeff, reg_id, sigma, flags, full.data_ptr(), 0, stream)
+        return (full.view(shape),) + (None,) * 8
 
 
 class _FusedHeadStacked(torch.autograd.Function):

@@ -51,7 +51,8 @@ class DSNTHead(nn.Module):
     Args mirror `ResNetHumanPoseModel` / `HourglassHumanPoseModel` (src/dsnt/model.py:90-99,205-215).
     """
 
-    def __init__(self, n_chans=16, preact='softmax', reg='none', reg_coeff=1.0, hm_sigma=1.0, group=None):
+    def __init__(self, n_chans=16, preact='softmax', reg='none', reg_coeff=1.0, hm_sigma=1.0, group=None,
+                 one_pass=True):
         super().__init__()
         self.n_chans = n_chans
         self.output_strat = 'dsnt'
@@ -60,6 +61,7 @@ class DSNTHead(nn.Module):
         self.reg_coeff = reg_coeff
         self.hm_sigma = hm_sigma
         self.group = group
+        self.one_pass = one_pass   # forward_loss also writes dL/dZ (dsnt_head_step): backward re-reads nothing
         self._logits = []          # raw heatmap tensors of the last forward_part2 (one per stack)
         self._coords = []          # what forward_part2 returned for them
         self._heatmaps = {}        # lazily materialised P per stack
@@ -110,7 +112,8 @@ class DSNTHead(nn.Module):
     def _loss_one(self, i, out, target, mask):
         if i < len(self._coords) and out is self._coords[i] and self.preact in _FUSED_PREACTS:
             return dsnt_head(self._logits[i], target, mask, reg=self.reg, hm_sigma=self.hm_sigma,
-                             reg_coeff=self.reg_coeff, group=self.group, preact=self.preact).loss
+                             reg_coeff=self.reg_coeff, group=self.group, preact=self.preact,
+                             one_pass=self.one_pass).loss
         # coords that did not come from forward_part2 (or a non-fused preact): the reference's composition
         loss = dnn.euclidean_loss(out, target, mask)
         sigma = 2.0 * self.hm_sigma / self._logits[i].size(-1)

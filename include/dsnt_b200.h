@@ -109,6 +109,30 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
                   void* dz, int variant, void* stream);
 
 /*
+ * The whole training step of the head in ONE pass over the logits (csrc/head_step.cuh): every heatmap is brought
+ * into shared memory by a TMA bulk copy, reduced (forward), overwritten with dL/dz (backward) and bulk-stored --
+ * 2*H*W*sizeof bytes per heatmap instead of the 3*H*W*sizeof of dsnt_head_fwd + dsnt_head_bwd.
+ *   replaces: forward_part2 + forward_loss + loss.backward() of one step (src/dsnt/bin/train.py:355-381) for the
+ *             softmax pre-activation; the backward's only cross-heatmap input, the denominator of masked_average
+ *             (src/dsnt/nn.py:88-92), depends on the mask alone and is computed first by dsnt_mask_count.
+ *   denom     DEVICE scalar max(sum mask, 1) (out[3] of dsnt_mask_count; all-reduce out[2] + dsnt_combine_loss first
+ *             when the batch is sharded);  g_loss: DEVICE scalar d(loss) or NULL = 1
+ *   dz        [N,H,W] out = g_loss * d(euclid + reg_coeff*reg)/dz, same dtype as z;  coords/stats/terms as dsnt_head_fwd
+ *             (feed terms to dsnt_finish_loss for the loss value; stats allow a later dsnt_head_bwd with other gradients)
+ *   returns DSNT_ERR_UNSUPPORTED when fewer than 4 heatmaps fit in shared memory or the layout has no 16-byte vectors
+ *   (dsnt_head_step_supported tells in advance); the caller then uses the two-kernel path.
+ * dsnt_mask_count: out[2] = sum mask (n when mask is NULL), out[3] = max(out[2], 1); workspace as dsnt_finish_loss.
+ */
+DSNT_API int dsnt_head_step_supported(int dtype, int H, int W);
+DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                            const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
+                            float* coords, float* stats, float* terms, void* dz, void* stream);
+DSNT_API int dsnt_mask_count(const float* mask, long n, float* out, float* workspace, void* stream);
+/* x[0..numel) *= *g, skipped entirely (no traffic) when *g == 1: applies an upstream d(loss) != 1 to the gradient
+ * dsnt_head_step already wrote, without a host read of *g. */
+DSNT_API int dsnt_scale_unless_one(void* x, int dtype, long numel, const float* g, void* stream);
+
+/*
  * Stacked-hourglass forms: ONE launch for all stacks.
  *   replaces: the per-stack Python loops of HourglassHumanPoseModel.forward_part2 / forward_loss
  *             (src/dsnt/model.py:238-246,286-292) over the list hourglass.py:166-177 returns.

@@ -1,0 +1,211 @@
+"""GPU parity of the one-pass training step (dsnt_head_step: TMA bulk load -> forward -> dL/dz in place -> bulk store)
+against the reference golden vectors, the fp64 oracle, and the two-kernel path it replaces.  Tolerances as in
+test_gpu_parity.py: 1e-5 (coords max-abs, loss relative, dZ L2-relative), bf16 dZ 4e-3."""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import head_case_params, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+REGS = ['none', 'var', 'kl', 'js', 'mse']
+TOL = 1e-5
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def dp():
+    import dsnt_pose2d_b200
+    return dsnt_pose2d_b200
+
+
+@pytest.fixture(scope='module')
+def tp():
+    from oracle import torch_port
+    return torch_port
+
+
+def run_step(dp, z, target, mask, reg, hm_sigma=1.0, coeff=1.0, g=None, one_pass=True):
+    from dsnt_pose2d_b200 import _lib
+    zz = z.detach().clone().to(DEV).requires_grad_(True)
+    tt = None if target is None else target.to(DEV)
+    mm = None if mask is None else mask.to(DEV)
+    before = dict(_lib_counts(_lib))
+    out = dp.dsnt_head(zz, tt, mm, reg=reg, hm_sigma=hm_sigma, reg_coeff=coeff, one_pass=one_pass)
+    (out.loss if g is None else out.loss * g).backward()
+    torch.cuda.synchronize()
+    return {'loss': out.loss.item(), 'euclid': out.euclid.item(), 'reg': out.reg.item(),
+            'coords': out.coords.detach().cpu().double().numpy(), 'dz': zz.grad.detach().cpu().double().numpy()}
+
+
+def _lib_counts(_lib):
+    return {'n': _lib.launch_count}
+
+
+def check(got, ref_loss, ref_coords, ref_dz, what, tol=TOL, dz_tol=None):
+    dz_tol = tol if dz_tol is None else dz_tol
+    e_loss = abs(got['loss'] - ref_loss) / max(abs(ref_loss), 1e-30)
+    e_coords = float(np.abs(got['coords'] - ref_coords).max())
+    e_l2 = rel_l2(got['dz'], ref_dz)
+    e_max = rel_max(got['dz'], ref_dz)
+    print('%-46s loss %.2e coords %.2e dz L2 %.2e max %.2e' % (what, e_loss, e_coords, e_l2, e_max))
+    assert e_loss < tol, (what, 'loss', got['loss'], ref_loss)
+    assert e_coords < tol, (what, 'coords', e_coords)
+    assert e_l2 < dz_tol and e_max < dz_tol * 4, (what, 'dz', e_l2, e_max)
+
+
+def test_step_is_taken_only_where_supported(dp):
+    from dsnt_pose2d_b200 import head
+    assert head.step_supported(torch.empty(1, 1, 64, 64, device=DEV))
+    assert head.step_supported(torch.empty(1, 1, 28, 28, device=DEV))
+    assert head.step_supported(torch.empty(1, 1, 128, 128, device=DEV, dtype=torch.bfloat16))
+    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV))     # 256 KiB: two-kernel path
+    assert not head.step_supported(torch.empty(1, 1, 7, 7, device=DEV))         # no 16-byte vectors
+
+
+@pytest.mark.parametrize('reg', REGS)
+def test_step_matches_reference_golden(dp, golden_head, reg):
+    from dsnt_pose2d_b200 import head
+    ran = 0
+    for name in golden_head.cases:
+        b, c, h, w, hm_sigma, coeff, with_mask = head_case_params(golden_head, name)
+        z = torch.from_numpy(golden_head[name + '/z'])
+        if not head.step_supported(z.to(DEV)):
+            continue
+        ran += 1
+        target = torch.from_numpy(golden_head[name + '/target'])
+        mask = torch.from_numpy(golden_head[name + '/mask']) if with_mask else None
+        got = run_step(dp, z, target, mask, reg, hm_sigma, coeff)
+        check(got, float(golden_head['%s/%s/loss' % (name, reg)]), golden_head[name + '/coords'],
+              golden_head['%s/%s/dz' % (name, reg)].astype(np.float64), 'golden %s %s' % (name, reg))
+        assert abs(got['euclid'] - float(golden_head['%s/%s/euclid' % (name, reg)])) < TOL
+    assert ran >= 4
+
+
+@pytest.mark.parametrize('reg', REGS)
+@pytest.mark.parametrize('shape,scale', [((32, 16, 64, 64), 1.0), ((8, 16, 64, 64), 5.0), ((64, 16, 28, 28), 1.0),
+                                         ((4, 16, 56, 56), 1.0), ((3, 5, 32, 32), 2.0), ((2, 3, 12, 20), 1.0),
+                                         ((2, 2, 96, 96), 1.0), ((600, 16, 64, 64), 1.0)])
+def test_step_matches_fp64_oracle(dp, tp, reg, shape, scale):
+    """cfg 1 / cfg 2 head shapes, ResNet dilate=3 (56x56), non-square, and more heatmaps than one wave of warps."""
+    b, c, h, w = shape
+    gen = torch.Generator().manual_seed(51)
+    z = torch.randn(b, c, h, w, generator=gen) * scale
+    target = torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8
+    mask = (torch.rand(b, c, generator=gen) > 0.1).float()
+    n_chk = min(b, 16)                      # the oracle needs the global mask count but only a slice of the heatmaps
+    got = run_step(dp, z, target, mask, reg)
+    if n_chk == b:
+        ref = tp.head_loss_and_grad(z, target, mask, reg, 1.0, 1.0, dtype=torch.float64)
+        check(got, ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(), '%s %s' % ('x'.join(map(str, shape)), reg))
+    else:
+        two = run_step(dp, z, target, mask, reg, one_pass=False)       # already oracle-checked in test_gpu_parity.py
+        check(got, two['loss'], two['coords'], two['dz'], 'vs two-kernel %s %s' % ('x'.join(map(str, shape)), reg), tol=2e-6)
+
+
+@pytest.mark.parametrize('reg', ['js', 'kl', 'mse'])
+def test_step_trained_like_heatmaps_and_any_sigma(dp, tp, reg):
+    gen = torch.Generator().manual_seed(52)
+    b, c, h, w = 4, 8, 64, 64
+    target = torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8
+    g = tp.make_gauss(target + 0.05 * torch.randn(b, c, 2, generator=gen), w, h, 2.0 / w)
+    z = (g + 1e-6).log() + 0.1 * torch.randn(b, c, h, w, generator=gen)
+    # KL on peaked maps is where fp32 itself runs out: the reference's own fp32 result is 7e-6..4e-5 from fp64 there
+    # (SURVEY.md 7.5), so the oracle bar is 2e-5 for KL and the one-pass result must sit on the two-kernel result.
+    for hm_sigma in (0.4, 1.0, 3.0, 20.0):
+        ref = tp.head_loss_and_grad(z, target, None, reg, hm_sigma, 1.0, dtype=torch.float64)
+        got = run_step(dp, z, target, None, reg, hm_sigma=hm_sigma)
+        check(got, ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(), 'trained %s sigma %.1f' % (reg, hm_sigma),
+              dz_tol=2e-5 if reg == 'kl' else None)
+        two = run_step(dp, z, target, None, reg, hm_sigma=hm_sigma, one_pass=False)
+        assert rel_l2(got["dz"], two["dz"]) < 1e-5 and abs(got["loss"] - two["loss"]) < 2e-6 * abs(two["loss"])
+
+
+@pytest.mark.parametrize('reg', ['js', 'var', 'kl'])
+def test_step_bf16(dp, tp, reg):
+    gen = torch.Generator().manual_seed(53)
+    z = torch.randn(16, 16, 64, 64, generator=gen).to(torch.bfloat16)
+    target = torch.rand(16, 16, 2, generator=gen) * 1.6 - 0.8
+    mask = (torch.rand(16, 16, generator=gen) > 0.1).float()
+    ref = tp.head_loss_and_grad(z.float(), target, mask, reg, 1.0, 1.0, dtype=torch.float64)
+    got = run_step(dp, z, target, mask, reg)
+    check(got, ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(), 'bf16 %s' % reg, dz_tol=4e-3)
+
+
+def test_step_upstream_gradient_scaling_and_coords_gradient(dp, tp):
+    """d(loss) != 1 scales the stored gradient in place; a gradient w.r.t. coords takes the regular backward."""
+    gen = torch.Generator().manual_seed(54)
+    z = torch.randn(4, 16, 64, 64, generator=gen)
+    target = torch.rand(4, 16, 2, generator=gen) * 1.6 - 0.8
+    mask = (torch.rand(4, 16, generator=gen) > 0.1).float()
+    ref = tp.head_loss_and_grad(z, target, mask, 'js', 1.0, 1.0, dtype=torch.float64)
+    got = run_step(dp, z, target, mask, 'js', g=-2.5)
+    assert rel_l2(got['dz'], -2.5 * ref['dz'].numpy()) < TOL
+    # loss + a function of the coordinates
+    wts = torch.randn(4, 16, 2, generator=gen)
+    zz = z.clone().to(DEV).requires_grad_(True)
+    out = dp.dsnt_head(zz, target.to(DEV), mask.to(DEV), reg='js', one_pass=True)
+    (out.loss + (out.coords * wts.to(DEV)).sum()).backward()
+    z64 = z.double().requires_grad_(True)
+    loss, coords, _, _ = tp.head_loss(z64, target.double(), mask.double(), 'js', 1.0, 1.0)
+    (loss + (coords * wts.double()).sum()).backward()
+    assert rel_l2(zz.grad.cpu().double().numpy(), z64.grad.numpy()) < TOL
+
+
+def test_step_edge_cases(dp, tp):
+    gen = torch.Generator().manual_seed(55)
+    z = torch.randn(2, 16, 64, 64, generator=gen)
+    target = torch.rand(2, 16, 2, generator=gen) * 1.6 - 0.8
+    # all-zero mask: loss 0, gradient 0 (denominator clamped to 1, src/dsnt/nn.py:88-92)
+    got = run_step(dp, z, target, torch.zeros(2, 16), 'js')
+    assert got['loss'] == 0.0 and np.abs(got['dz']).max() == 0.0
+    # mask=None: mean over all heatmaps
+    ref = tp.head_loss_and_grad(z, target, None, 'var', 1.0, 1.0, dtype=torch.float64)
+    check(run_step(dp, z, target, None, 'var'), ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(), 'no mask')
+    # size-independent properties at a large size: sum dZ = 0 per heatmap, determinism
+    zb = torch.randn(2048, 16, 64, 64, generator=gen)
+    tb = torch.rand(2048, 16, 2, generator=gen) * 1.6 - 0.8
+    a = run_step(dp, zb, tb, None, 'js')
+    b = run_step(dp, zb, tb, None, 'js')
+    assert np.array_equal(a['dz'], b['dz']) and a['loss'] == b['loss']
+    per_hm = a['dz'].reshape(2048 * 16, -1)
+    assert np.abs(per_hm.sum(-1)).max() <= 1e-6 * np.abs(per_hm).sum(-1).max()
+
+
+def test_step_in_cuda_graph_and_model_head(dp, tp):
+    gen = torch.Generator().manual_seed(56)
+    z = torch.randn(8, 16, 64, 64, generator=gen).to(DEV)
+    target = (torch.rand(8, 16, 2, generator=gen) * 1.6 - 0.8).to(DEV)
+    mask = (torch.rand(8, 16, generator=gen) > 0.1).float().to(DEV)
+    zz = z.clone().requires_grad_(True)
+
+    def step():
+        zz.grad = None
+        out = dp.dsnt_head(zz, target, mask, reg='js', one_pass=True)
+        out.loss.backward()
+        return out.loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    eager_grad = zz.grad.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        loss = step()
+    zz.grad.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(zz.grad, eager_grad)
+    ref = tp.head_loss_and_grad(z, target, mask, 'js', 1.0, 1.0, dtype=torch.float64)
+    assert abs(loss.item() - ref['loss'].item()) < TOL * abs(ref['loss'].item())
+    # the model-level head takes the one-pass step by default
+    head = dp.DSNTHead(reg='js', reg_coeff=1.0, hm_sigma=1.0)
+    z2 = z.clone().requires_grad_(True)
+    out = head.forward_part2(z2)
+    head.forward_loss(out, target, mask).backward()
+    assert rel_l2(z2.grad.cpu().double().numpy(), ref['dz'].numpy()) < TOL

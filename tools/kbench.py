@@ -103,12 +103,25 @@ def main():
                     except RuntimeError as e:
                         print('%-6s %-5s %-5s %3d | FAILED %s' % (cfg, dt, reg, variant, e))
                         continue
+                    ts = None
+                    if _lib.LIB.dsnt_head_step_supported(_lib.dtype_id(zs[0]), h, w):
+                        cnt8 = torch.empty(8, device=dev)
+                        _lib.call('dsnt_mask_count', mask.data_ptr(), n, cnt8.data_ptr(), ws.data_ptr(), stream)
+
+                        def step(i):
+                            _lib.call('dsnt_head_step', zs[i % nbuf].data_ptr(), _lib.dtype_id(zs[0]), n, h, w,
+                                      target.data_ptr(), mask.data_ptr(), cnt8[3:4].data_ptr(), None, 1.0, rid, sigma, 0,
+                                      coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), dzs[i % len(dzs)].data_ptr(),
+                                      stream)
+                        ts, _ = time_calls(step, args.iters)
                     gf = nbytes / tf / 1e6
                     gb = 2 * nbytes / tb / 1e6
                     tot = (3 * nbytes + 96 * n) / (tf + tb) / 1e6
                     print('%-6s %-5s %-5s %3d | %9.1f %8.0f %6.3f | %9.1f %8.0f %6.3f | %8.2f %6.3f' % (
                         cfg, dt, reg, variant, tf * 1e3, gf, gf / peak, tb * 1e3, gb, gb / peak,
-                        n / (tf + tb) / 1e3, tot / peak))
+                        n / (tf + tb) / 1e3, tot / peak) + (
+                        '' if ts is None else ' || one-pass step %7.1f us %6.0f GB/s %5.3f %8.2f Mhm/s' % (
+                            ts * 1e3, 2 * nbytes / ts / 1e6, 2 * nbytes / ts / 1e6 / peak, n / ts / 1e3)))
             del zs, dzs
             torch.cuda.empty_cache()
 
