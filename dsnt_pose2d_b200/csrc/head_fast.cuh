@@ -401,7 +401,10 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
           qa = fmaf(e * invS, (t + tlm1) - L, qa);                // P (log2 P - log2 M' - 1)
           qb = fmaf(G, lgG - L, qb);                             // G (log2 G - log2 M')
         } else if (kKL) {
-          qa = fmaf(e * invS, lg2(G + kEps) - kLog2Eps, qa);     // P (log2(G+eps) - log2 eps)
+          // sum_win P log2(G+eps) and sum_win P separately: folding the out-of-window constant log2(eps) = -79.7 into
+          // every term (P (log2(G+eps) - log2 eps)) made D the difference of two ~55-sized numbers
+          qa = fmaf(e * invS, lg2(G + kEps), qa);
+          qb += e * invS;
         } else {
           const float P = e * invS, df = P - G;
           qa = fmaf(df, df, qa);                                 // (P - G)^2
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
       } else {
         // sum P ln P = (ln2 sum f log2 f)/(S + eps) + sum P ln(1/(S + eps))
         const float plnp = kPlain ? fmaf(kLn2 * invS, Tt, -logf(S)) : fmaf(kLn2 * invS, Tt, sumP * logf(invS));
-        D = plnp - sumP * kLnEps - kLn2 * qa;
+        D = plnp - kLn2 * fmaf(kLog2Eps, sumP - qb, qa);   // outside the window G + eps = eps exactly
         creg = D + sumP;                         // + sum P^2/(P + eps) = sum P (P is 0 or >> eps)
       }
     }

@@ -23,6 +23,7 @@
 namespace dsnt {
 
 constexpr int kStepMaxWarps = 16;
+constexpr int kStepMaxBufs = 32;
 constexpr int kStepSmemBudget = 224 * 1024;   // of the 227 KiB a CTA may opt in to
 
 struct HeadStepParams {
@@ -41,7 +42,8 @@ struct HeadStepParams {
   float sigma, reg_coeff;
   Geom g;
   int buf_bytes;         // one buffer (heatmap bytes rounded up to 128)
-  int nwarps;            // warps per CTA; each owns NBUF buffers
+  int nwarps;            // groups (of GROUP/32 warps) per CTA
+  int nbufs;             // shared-memory buffers per CTA, >= nwarps: a ring shared by the groups
   int direct_store;      // 1: dz goes to global memory with 128-bit stores straight from registers; 0: in place + bulk store
 };
 
@@ -158,8 +160,11 @@ __device__ __forceinline__ void step_group_sum4(float& a, float& b, float& c, fl
 
 // ================================================================================================ the step kernel
 // FIXC: 32 lanes cover a whole number of rows (W/VEC divides 32), so a lane always sees the same VEC columns.
-// NBUF: buffers per warp.  2 = the next heatmap's load is in flight while this one is reduced and rewritten.
-template <typename T, int VEC, int REG, bool FIXC, int NBUF, int GROUP>
+// The CTA's heatmaps ("tiles" t = 0, 1, ...; heatmap = t * gridDim.x + blockIdx.x) go round a RING of nbufs buffers:
+// tile t lives in buffer t % nbufs and is processed by group t % nwarps; whoever finishes tile t refills its buffer with
+// tile t + nbufs.  nbufs == nwarps: every group owns one buffer (its next load starts when it is done); nbufs > nwarps:
+// nbufs - nwarps further loads are in flight while every group computes.
+template <typename T, int VEC, int REG, bool FIXC, int GROUP>
 __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const HeadStepParams p) {
   constexpr bool kKL = REG == DSNT_REG_KL;
   constexpr bool kJS = REG == DSNT_REG_JS;
@@ -167,7 +172,11 @@ __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const 
   constexpr bool kMSE = REG == DSNT_REG_MSE;
   constexpr bool kWin = kKL || kJS || kMSE;
   extern __shared__ __align__(128) unsigned char step_smem[];
-  __shared__ __align__(8) unsigned long long bars[kStepMaxWarps * NBUF];
+  __shared__ __align__(8) unsigned long long bars[kStepMaxBufs];
+  // loads issued into each buffer so far.  A parity wait cannot tell "round r+1 not armed yet" from "done" when the
+  // waiter is a whole phase ahead, and with nbufs > nwarps the group that consumes round r+1 of a buffer is not the one
+  // that consumed round r -- so it first waits (on this counter) until that group has re-armed the barrier.
+  __shared__ volatile int issued[kStepMaxBufs];
   __shared__ float scr_all[kStepMaxWarps][3][8];   // cross-warp reductions of a group: three rotating slots
 
   // p.nwarps counts GROUPS (of GROUP/32 warps) here
@@ -178,22 +187,26 @@ __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const 
   const int H = p.H, W = p.W;
   const int wv = g.wv, nvec = g.nvec;
   const uint32_t hm_bytes = static_cast<uint32_t>(H) * W * sizeof(T);
-  unsigned char* warp_smem = step_smem + static_cast<size_t>(grp) * NBUF * p.buf_bytes;
-  const uint32_t buf0_s = smem_u32(warp_smem), bar0_s = smem_u32(&bars[grp * NBUF]);
-  if (tg == 0) {
-#pragma unroll
-    for (int i = 0; i < NBUF; ++i) mbar_init(bar0_s + 8 * i, 1);
-  }
-  step_group_bar<GROUP>(grp);
-
-  const long stride = static_cast<long>(gridDim.x) * p.nwarps;
-  long hm = static_cast<long>(blockIdx.x) * p.nwarps + grp;
+  const int NW = p.nwarps, NB = p.nbufs;
+  const uint32_t smem0_s = smem_u32(step_smem), bars0_s = smem_u32(&bars[0]);
   const char* zsrc = static_cast<const char*>(p.z);
   char* dzdst = static_cast<char*>(p.dz);
-  if (hm < p.n && tg == 0) {
-    mbar_expect_tx(bar0_s, hm_bytes);
-    bulk_load(buf0_s, zsrc + hm * hm_bytes, hm_bytes, bar0_s);
+  // tiles of this CTA
+  const long ntiles = p.n > blockIdx.x ? (p.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // the group that will process tile t < nbufs also arms its barrier and issues its first load
+  if (tg == 0) {
+    for (int t = grp; t < NB; t += NW) {
+      const uint32_t bar = bars0_s + 8 * t;
+      mbar_init(bar, 1);
+      if (t < ntiles) {
+        mbar_expect_tx(bar, hm_bytes);
+        bulk_load(smem0_s + static_cast<uint32_t>(t) * p.buf_bytes, zsrc + (t * static_cast<long>(gridDim.x) + blockIdx.x) * hm_bytes,
+                  hm_bytes, bar);
+      }
+      issued[t] = 1;
+    }
   }
+  __syncthreads();   // every barrier is initialised before any group looks at a buffer another group armed
   const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
   const float inv_denom = 1.0f / __ldg(p.denom);
   const float s2 = p.sigma * p.sigma;
@@ -208,22 +221,13 @@ __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const 
     for (int c = 0; c < VEC; ++c) xs[c] = axis_coord(cv0 * VEC + c, g.two_over_w, g.bias_w);
   }
 
-  for (uint32_t it = 0; hm < p.n; hm += stride, ++it) {
-    const uint32_t bi = NBUF == 2 ? (it & 1u) : 0u;
-    const uint32_t phase = NBUF == 2 ? ((it >> 1) & 1u) : (it & 1u);
-    T* buf = reinterpret_cast<T*>(warp_smem + static_cast<size_t>(bi) * p.buf_bytes);
-    const uint32_t buf_s = buf0_s + bi * static_cast<uint32_t>(p.buf_bytes), bar_s = bar0_s + 8 * bi;
-    if constexpr (NBUF == 2) {
-      // prefetch the next heatmap into the other buffer; its last store (issued one iteration ago) has had a whole
-      // load latency to read the buffer out, so this wait is normally free
-      const long nxt = hm + stride;
-      if (tg == 0 && nxt < p.n) {
-        bulk_wait_read();
-        const uint32_t ob = buf0_s + (bi ^ 1u) * static_cast<uint32_t>(p.buf_bytes), obar = bar0_s + 8 * (bi ^ 1u);
-        mbar_expect_tx(obar, hm_bytes);
-        bulk_load(ob, zsrc + nxt * hm_bytes, hm_bytes, obar);
-      }
-    }
+  for (long t = grp; t < ntiles; t += NW) {
+    const long hm = t * static_cast<long>(gridDim.x) + blockIdx.x;
+    const uint32_t round = static_cast<uint32_t>(t / NB);
+    const uint32_t bi = static_cast<uint32_t>(t - static_cast<long>(round) * NB);
+    const uint32_t phase = round & 1u;
+    T* buf = reinterpret_cast<T*>(step_smem + static_cast<size_t>(bi) * p.buf_bytes);
+    const uint32_t buf_s = smem0_s + bi * static_cast<uint32_t>(p.buf_bytes), bar_s = bars0_s + 8 * bi;
     // per-heatmap scalars while the load is in flight
     float tx = 0.f, ty = 0.f;
     if (p.target) {
@@ -234,6 +238,9 @@ __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const 
     Window win{1, 0, 1, 0};
     if constexpr (kWin) win = make_window(g, H, W, tx, ty);
 
+    if (NB != NW) {
+      while (issued[bi] < static_cast<int>(round) + 1) { }   // armed for this round by the consumer of the previous one
+    }
     mbar_wait(bar_s, phase);
 
     // ---------------------------------------------------------------- forward: max
@@ -363,7 +370,8 @@ __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const 
             qa = fmaf(e * invS, (t + tlm1) - L, qa);
             qb = fmaf(G, lgG - L, qb);
           } else if (kKL) {
-            qa = fmaf(e * invS, lg2(G + kEps) - kLog2Eps, qa);
+            qa = fmaf(e * invS, lg2(G + kEps), qa);     // see head_fast.cuh: keeps D free of the -79.7 offset
+            qb += e * invS;
           } else {
             const float P = e * invS, df = P - G;
             qa = fmaf(df, df, qa);
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const 
         D = fmaf(0.5f * kLn2, qb, creg);
       } else {
         const float plnp = fmaf(kLn2 * invS, Tt, -logf(S));
-        D = plnp - kLnEps - kLn2 * qa;
+        D = plnp - kLn2 * fmaf(kLog2Eps, 1.0f - qb, qa);   // outside the window G + eps = eps exactly
         creg = D + 1.0f;
       }
     }
@@ -492,14 +500,16 @@ __global__ void __launch_bounds__(kStepMaxWarps * 32, 1) head_step_kernel(const 
     if (!p.direct_store) fence_async_smem();      // this lane's generic-proxy writes -> visible to the async proxy
     step_group_bar<GROUP>(grp);
     if (tg == 0) {
-      if (!p.direct_store) bulk_store(dzdst + hm * hm_bytes, buf_s, hm_bytes);
-      if constexpr (NBUF == 1) {
-        if (!p.direct_store) bulk_wait_read();      // the buffer has been read out: it may be refilled
-        const long nxt = hm + stride;
-        if (nxt < p.n) {
-          mbar_expect_tx(bar_s, hm_bytes);
-          bulk_load(buf_s, zsrc + nxt * hm_bytes, hm_bytes, bar_s);
-        }
+      if (!p.direct_store) {
+        bulk_store(dzdst + hm * hm_bytes, buf_s, hm_bytes);
+        bulk_wait_read();      // the buffer has been read out: it may be refilled
+      }
+      const long nt = t + NB;  // the tile that takes this buffer over
+      if (nt < ntiles) {
+        mbar_expect_tx(bar_s, hm_bytes);
+        bulk_load(buf_s, zsrc + (nt * static_cast<long>(gridDim.x) + blockIdx.x) * hm_bytes, hm_bytes, bar_s);
+        __threadfence_block();
+        issued[bi] = static_cast<int>(round) + 2;
       }
     }
     step_group_bar<GROUP>(grp);

@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
                 qa = fmaf(e * invS, (t + tlm1) - L, qa);                // P (log2 P - log2 M' - 1)
                 qb = fmaf(G, lgG - L, qb);                             // G (log2 G - log2 M')
               } else if (kKL) {
-                qa = fmaf(e * invS, lg2(G + kEps) - kLog2Eps, qa);     // P (log2(G+eps) - log2 eps)
+                qa = fmaf(e * invS, lg2(G + kEps), qa);                // see head_fast.cuh: D stays free of the -79.7 offset
+                qb += e * invS;
               } else {
                 const float P = e * invS, df = P - G;
                 qa = fmaf(df, df, qa);                                 // (P - G)^2
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_stream
         D = fmaf(0.5f * kLn2, qb, creg);         // + 1/2 sum G (ln G - ln M')
       } else {
         const float plnp = fmaf(kLn2 * invS, Tt, -logf(S));  // sum P ln P
-        D = plnp - kLnEps - kLn2 * qa;
+        D = plnp - kLn2 * fmaf(kLog2Eps, 1.0f - qb, qa);   // outside the window G + eps = eps exactly
         creg = D + 1.0f;
       }
     }

@@ -18,49 +18,36 @@ static int sm_count() {
   return cached;
 }
 
-template <typename T, int VEC, int REG, bool FIXC, int NBUF, int GROUP>
-static int launch_step_nbuf(HeadStepParams p, cudaStream_t stream) {
-  auto kern = head_step_kernel<T, VEC, REG, FIXC, NBUF, GROUP>;
-  p.nwarps = kStepSmemBudget / (p.buf_bytes * NBUF);   // groups per CTA
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+static int step_direct_store() { static const int v = env_int("DSNT_TUNE_STEP_STG", 1); return v; }
+static int step_group() { static const int v = env_int("DSNT_TUNE_STEP_GROUP", 32); return v; }
+static int step_warps() { static const int v = env_int("DSNT_TUNE_STEP_WARPS", 0); return v; }
+
+// Measured on B200 at cfg 4 (profiles/r01_v4_step_sweep.txt, r01_v5_step_ring.txt): one warp per heatmap and direct
+// 128-bit stores; DSNT_TUNE_STEP_{WARPS,GROUP,STG} override for experiments.
+template <typename T, int VEC, int REG, bool FIXC, int GROUP>
+static int launch_step_one(HeadStepParams p, cudaStream_t stream) {
+  auto kern = head_step_kernel<T, VEC, REG, FIXC, GROUP>;
   constexpr int kMaxGroups = kStepMaxWarps * 32 / GROUP;
+  p.nbufs = kStepSmemBudget / p.buf_bytes;
+  if (p.nbufs > kStepMaxBufs) p.nbufs = kStepMaxBufs;
+  // two spare buffers keep loads in flight while every group computes (64x64 fp32: 14 buffers, 12 warps)
+  p.nwarps = step_warps() > 0 ? step_warps() : (p.nbufs > 4 ? p.nbufs - 2 : p.nbufs);
   if (p.nwarps > kMaxGroups) p.nwarps = kMaxGroups;
-  const size_t smem = static_cast<size_t>(p.nwarps) * NBUF * p.buf_bytes;
+  if (p.nwarps > p.nbufs) p.nwarps = p.nbufs;
+  const size_t smem = static_cast<size_t>(p.nbufs) * p.buf_bytes;
   static size_t configured = 0;     // per instantiation: the opt-in only ever needs to grow
   if (smem > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return check_launch("head_step_kernel (shared-memory opt-in)");
     configured = smem;
   }
-  long ctas = (p.n + p.nwarps - 1) / p.nwarps;
-  if (ctas > sm_count()) ctas = sm_count();   // persistent: one CTA per SM, every warp loops over heatmaps
+  long ctas = p.n < sm_count() ? p.n : sm_count();   // persistent: one CTA per SM, tiles interleaved across CTAs
   kern<<<static_cast<unsigned>(ctas), p.nwarps * GROUP, smem, stream>>>(p);
   return check_launch("head_step_kernel");
-}
-
-static int step_direct_store() {
-  static const int v = [] { const char* e = std::getenv("DSNT_TUNE_STEP_STG"); return e ? std::atoi(e) : 1; }();
-  return v;
-}
-
-static int step_nbuf() {
-  static const int v = [] { const char* e = std::getenv("DSNT_TUNE_STEP_NBUF"); return e ? std::atoi(e) : 0; }();
-  return v;
-}
-
-static int step_group() {
-  static const int v = [] { const char* e = std::getenv("DSNT_TUNE_STEP_GROUP"); return e ? std::atoi(e) : 0; }();
-  return v;
-}
-
-// Measured on B200 at cfg 4 (profiles/r01_v4_step_sweep.txt): one warp per heatmap, one buffer per warp and direct
-// 128-bit stores is the best all-round setting (JS 369 us, none 387 us for 65 536 heatmaps of 64x64 fp32); two buffers
-// per warp reach 0.97 of HBM peak without a regulariser (332 us) but leave too few warps for the divergence arithmetic.
-// DSNT_TUNE_STEP_NBUF / _GROUP / _STG override for experiments.
-template <typename T, int VEC, int REG, bool FIXC, int GROUP>
-static int launch_step_one(const HeadStepParams& p, cudaStream_t stream) {
-  int nb = step_nbuf();
-  if (nb != 1 && nb != 2) nb = 1;
-  return nb == 2 ? launch_step_nbuf<T, VEC, REG, FIXC, 2, GROUP>(p, stream) : launch_step_nbuf<T, VEC, REG, FIXC, 1, GROUP>(p, stream);
 }
 
 // one warp per heatmap by default (DSNT_TUNE_STEP_GROUP=64 selects two)
@@ -130,7 +117,7 @@ DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, cons
   p.n = n; p.H = H; p.W = W; p.flags = flags; p.sigma = sigma; p.reg_coeff = reg_coeff;
   p.g = make_geom(H, W, vec, 32, sigma > 0.f ? sigma : 1.f, reg);
   p.buf_bytes = (H * W * es + 127) / 128 * 128;
-  p.nwarps = 0;   // chosen with the number of buffers per warp at launch
+  p.nwarps = 0; p.nbufs = 0;   // chosen at launch
   p.direct_store = step_direct_store();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dtype == DSNT_DTYPE_F32 ? launch_step_reg<float, 4>(p, reg, s) : launch_step_reg<__nv_bfloat16, 8>(p, reg, s);

@@ -120,7 +120,10 @@ def test_step_trained_like_heatmaps_and_any_sigma(dp, tp, reg):
         check(got, ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(), 'trained %s sigma %.1f' % (reg, hm_sigma),
               dz_tol=2e-5 if reg == 'kl' else None)
         two = run_step(dp, z, target, None, reg, hm_sigma=hm_sigma, one_pass=False)
-        assert rel_l2(got["dz"], two["dz"]) < 1e-5 and abs(got["loss"] - two["loss"]) < 2e-6 * abs(two["loss"])
+        check(two, ref['loss'].item(), ref['coords'].numpy(), ref['dz'].numpy(), '  two-kernel %s sigma %.1f' % (reg, hm_sigma),
+              dz_tol=2e-5 if reg == 'kl' else None)
+        assert rel_l2(got["dz"], two["dz"]) < (2e-5 if reg == 'kl' else 3e-6)
+        assert abs(got["loss"] - two["loss"]) < 2e-6 * abs(two["loss"])
 
 
 @pytest.mark.parametrize('reg', ['js', 'var', 'kl'])
