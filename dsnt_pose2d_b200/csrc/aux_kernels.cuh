@@ -46,9 +46,10 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
   const long chunk = (n + gridDim.x - 1) / gridDim.x;
   const long lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
   float sd = 0.f, sr = 0.f, sm = 0.f, unused = 0.f;
+  const bool one_stack = n_per >= n;     // no 64-bit modulo per element in the common single-tensor case
   for (long i = lo + threadIdx.x; i < hi; i += kFinishBlock) {
     const float2 t = terms ? __ldg(reinterpret_cast<const float2*>(terms) + i) : make_float2(0.f, 0.f);   // null: mask count only
-    const float w = mask ? __ldg(mask + (i % n_per)) : 1.0f;
+    const float w = mask ? __ldg(mask + (one_stack ? i : i % n_per)) : 1.0f;
     sd = fmaf(w, t.x, sd);
     sr = fmaf(w, t.y, sr);
     if (i < n_per) sm += w;
@@ -65,10 +66,19 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
   if (!is_last) return;
   __threadfence();
   if (threadIdx.x < 32) {
-    const volatile float4* part = reinterpret_cast<const volatile float4*>(workspace);
+    // L2 loads (the partials were written by other SMs; ld.cg never looks at this SM's L1), all issued before the first
+    // is consumed: a volatile float4 is four dependent round trips per partial
+    const float4* part = reinterpret_cast<const float4*>(workspace);
+    float4 v[kFinishMaxCtas / 32];
+#pragma unroll
+    for (int k = 0; k < kFinishMaxCtas / 32; ++k) {
+      const int i = threadIdx.x + 32 * k;
+      v[k] = i < static_cast<int>(gridDim.x) ? __ldcg(part + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float a = 0.f, b = 0.f, c = 0.f;
-    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 32) {  // fixed order per lane
-      a += part[i].x; b += part[i].y; c += part[i].z;
+#pragma unroll
+    for (int k = 0; k < kFinishMaxCtas / 32; ++k) {  // fixed order per lane
+      a += v[k].x; b += v[k].y; c += v[k].z;
     }
     a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
     if (threadIdx.x == 0) {

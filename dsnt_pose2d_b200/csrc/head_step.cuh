@@ -45,6 +45,10 @@ struct HeadStepParams {
   int nwarps;            // groups (of GROUP/32 warps) per CTA
   int nbufs;             // shared-memory buffers per CTA, >= nwarps: a ring shared by the groups
   int direct_store;      // 1: dz goes to global memory with 128-bit stores straight from registers; 0: in place + bulk store
+  int debug;             // head_step2 (DSNT_TUNE_STEP_DEBUG, measurements only): 1 = copy z -> dz with LDS + STG and no
+                         // arithmetic: the floor of the data-movement skeleton
+  int pace;              // head_step2: minimum SM clocks between two bulk loads issued by a CTA (0 = unpaced)
+  int stagger_ns;        // head_step2: warp w starts w * stagger_ns late, so the warps of a CTA are not all in the same sweep
 };
 
 // ---------------------------------------------------------------------------------- PTX: mbarrier + bulk copies

@@ -1,0 +1,624 @@
+// head_step2.cuh -- the one-pass training step (head_step.cuh) specialised at COMPILE TIME for one heatmap shape and
+// written on packed fp32 pairs.
+//
+// ncu on the generic step kernel with bf16 heatmaps (profiles/r01_v6_step_bf16_*): 70 % issue-active, XU 64 %, DRAM 39 %,
+// 28 instructions per pixel for JS -- 17.4 in the three sweeps, 4.9 per-heatmap scalar work, 3.0 in the per-pixel window
+// loop and 2.3 in the "heavy" rows of the backward (rcp + lg2 on every pixel of every row that touches the Gaussian
+// window, although only a third of their columns do).  The memory system idles because the SM cannot issue faster.
+// This kernel removes instructions instead of adding warps:
+//
+//  * H, W are template parameters: every sweep is fully unrolled, shared-memory and global addresses are the lane base
+//    plus an immediate, row coordinates fold into constants -- no loop counters, compares, branches, address arithmetic;
+//  * FADD2 / FMUL2 / FFMA2 (sm_100 packed fp32) process two neighbouring pixels per issue slot;
+//  * bf16: the maximum runs on packed bf16 pairs (HMNMX2.BF16_V2) without unpacking; the warp maximum is one
+//    CREDUX.MAX.F32;
+//  * the softmax sums are per-COLUMN accumulators (a lane always sees the same columns) + one row sum per sweep step, so
+//    S, S_x, S_y -- and the variance about the mean, without a second sweep -- come out of the same two adds per pixel;
+//  * the Gaussian window is processed as whole 128-bit vectors in a COMPACT lane mapping (vector k of the window -> lane
+//    k mod 32), forward and backward: log2 M per window pixel is computed once, kept in registers across the
+//    reduction, and reused by the backward (log2(1 + G/P) = log2 2M - log2 P), so the backward needs no rcp / lg2 at
+//    all and the main backward sweep has no window branch.
+//
+//  * e = 2^(z log2e - max) is computed ONCE: the sum sweep writes it back over z in the shared-memory buffer (fp32 heatmaps:
+//    exactly; bf16 heatmaps: as fp16 of e * 2^15, 11 significant bits for e >= 2e-9, against the 8 of the bf16 dz it
+//    produces) and the backward sweep is LDS, add, mul, store -- the profile of the first version of this kernel showed
+//    the XU pipe (MUFU.EX2) at 76 % with DRAM at 67 %, i.e. the second exponential per pixel was what bound it.  The
+//    window vectors are left alone (the window pass needs the logits themselves).
+//
+// Same mathematics and the same closed forms as head_step.cuh (src/dsnt/nn.py:25-116,168-298,
+// src/dsnt/model.py:24-63,145); the ring of shared-memory buffers, the bulk loads and the barrier protocol are shared
+// with it.  KL keeps the generic kernel (its window, 28x28 at sigma = 1 px, does not fit the register budget).
+#pragma once
+
+#include "f32x2.cuh"
+#include "head_step.cuh"
+
+namespace dsnt {
+
+template <typename T>
+__device__ __forceinline__ void unpack_pairs(const uint4& r, f2 (&v)[8 / sizeof(T)]) {
+  if constexpr (sizeof(T) == 4) {
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v[0].r) : "r"(r.x), "r"(r.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v[1].r) : "r"(r.z), "r"(r.w));
+  } else {
+    v[0] = bf16x2_to_f2(r.x); v[1] = bf16x2_to_f2(r.y); v[2] = bf16x2_to_f2(r.z); v[3] = bf16x2_to_f2(r.w);
+  }
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack_pairs(const f2 (&o)[8 / sizeof(T)]) {
+  uint4 r;
+  if constexpr (sizeof(T) == 4) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r.x), "=r"(r.y) : "l"(o[0].r));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r.z), "=r"(r.w) : "l"(o[1].r));
+  } else {
+    float lo, hi;
+    upk(o[0], lo, hi); r.x = pack_bf16(lo, hi);
+    upk(o[1], lo, hi); r.y = pack_bf16(lo, hi);
+    upk(o[2], lo, hi); r.z = pack_bf16(lo, hi);
+    upk(o[3], lo, hi); r.w = pack_bf16(lo, hi);
+  }
+  return r;
+}
+
+// e stash: what the sum sweep leaves in the buffer for the backward sweep (see the header)
+template <typename T>
+__device__ __forceinline__ uint4 stash_pack(const f2 (&e)[8 / sizeof(T)]) {
+  uint4 r;
+  if constexpr (sizeof(T) == 4) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r.x), "=r"(r.y) : "l"(e[0].r));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r.z), "=r"(r.w) : "l"(e[1].r));
+  } else {
+    float lo, hi;
+    upk(e[0], lo, hi); asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(hi), "f"(lo));
+    upk(e[1], lo, hi); asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(hi), "f"(lo));
+    upk(e[2], lo, hi); asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r.z) : "f"(hi), "f"(lo));
+    upk(e[3], lo, hi); asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r.w) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+__device__ __forceinline__ f2 f16x2_to_f2(uint32_t w) {
+  float lo, hi;
+  asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(lo), "=f"(hi) : "r"(w));
+  return pk(lo, hi);
+}
+template <typename T>
+__device__ __forceinline__ void stash_unpack(const uint4& r, f2 (&e)[8 / sizeof(T)]) {
+  if constexpr (sizeof(T) == 4) {
+    asm("mov.b64 %0, {%1, %2};" : "=l"(e[0].r) : "r"(r.x), "r"(r.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(e[1].r) : "r"(r.z), "r"(r.w));
+  } else {
+    e[0] = f16x2_to_f2(r.x); e[1] = f16x2_to_f2(r.y); e[2] = f16x2_to_f2(r.z); e[3] = f16x2_to_f2(r.w);
+  }
+}
+
+// The sweeps are fully unrolled (static register indices, immediate address offsets).  Left alone, ptxas hoists ALL of
+// a sweep's shared-memory loads to its top and spills (an empty asm fence disappears before ptxas schedules); a
+// __syncwarp() every kChunk steps is a real instruction with memory ordering that it will not move loads across, and
+// costs one issue slot per 4 * VEC pixels on a converged warp.
+// y0 is a per-lane constant, so "y0 + it * dyi" is invariant across heatmaps and would be hoisted out of the tile loop
+// for every sweep step (16-32 live registers); opaque() makes a copy the optimiser cannot see through.
+__device__ __forceinline__ float opaque(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+constexpr int kChunk = 4;
+__device__ __forceinline__ void sweep_fence(int it) {
+  if ((it % kChunk) == kChunk - 1) __syncwarp();
+}
+
+// axis_window (head_stream.cuh) with the approximate square root: a window one pixel larger or smaller than the exact
+// one is equally valid (it is padded by a pixel and any superset of it gives the same sums to the tolerance theta).
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void axis_window_fast(float t, int n, float half_n, float two_over_n, float bias_n, float r2,
+                                                 int& lo, int& hi) {
+  const float nm1 = static_cast<float>(n - 1);
+  const float js = fminf(fmaxf(rintf(fmaf(t + 1.0f, half_n, -0.5f)), 0.f), nm1);
+  const float ds = fmaf(js, two_over_n, bias_n) - t;
+  const float R = sqrt_approx(fmaf(ds, ds, r2)) * 1.000001f;
+  const float flo = fmaxf(ceilf(fmaf(t - R + 1.0f, half_n, -0.5f)) - 1.0f, 0.f);
+  const float fhi = fminf(floorf(fmaf(t + R + 1.0f, half_n, -0.5f)) + 1.0f, nm1);
+  lo = static_cast<int>(flo);
+  hi = static_cast<int>(fhi);
+}
+
+// Load pacing: every CTA reserves a time slot for each bulk load it issues, p.pace clocks after the previous one.  When
+// the warps are faster than memory they all wait for data, finish together when a burst of heatmaps arrives and
+// re-issue their loads (and their stores) together, which comes back as the next burst: measured on B200 a pure
+// copy through the ring runs at 0.91 of the HBM peak unpaced and at 1.0 paced (profiles/r01_v7_step2_sweeps.txt).
+// A load whose slot lies in the future is kept PENDING by lane 0 of the warp, which goes on with its next heatmap and
+// issues the load at one of its checkpoints -- or just before it would block on a barrier.
+struct PendingLoad {       // one per warp, in shared memory (only lane 0 touches it): tile < 0 means none
+  uint32_t when;           // low 32 bits of clock64 at which it may go (compared as a signed difference)
+  int tile;
+  uint32_t slot;           // buffer index | round << 8
+};
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Arms the barrier and starts the bulk load of one heatmap.  Deliberately NOT inlined: it is reached from several places
+// of a fully unrolled kernel whose size matters (the instruction stream is walked once per heatmap).
+__device__ __noinline__ void ring_issue(const char* src, uint32_t hm_bytes, uint32_t bar, uint32_t bufs, volatile int* flag, int value) {
+  mbar_expect_tx(bar, hm_bytes);
+  bulk_load(bufs, src, hm_bytes, bar);
+  __threadfence_block();
+  *flag = value;
+}
+// reserve the next slot; returns the clock at which the load may be issued (<= now: at once)
+__device__ __forceinline__ unsigned long long pace_reserve(unsigned long long* slot, int pace, unsigned long long now) {
+  unsigned long long mine = atomicAdd(slot, static_cast<unsigned long long>(pace));
+  if (mine < now) {                      // the schedule fell behind (start-up, compute-bound phases): restart it from now
+    atomicMax(slot, now + pace);
+    mine = now;
+  }
+  return mine;
+}
+
+// window slots per lane: the compact mapping covers 32 * slots vectors (host-checked bound, step2_window_fits)
+template <typename T>
+__host__ __device__ constexpr int step2_slots() { return sizeof(T) == 2 ? 3 : 4; }
+
+template <typename T, int REG, int H, int W, int NWMAX>
+__global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadStepParams p) {
+  constexpr bool kJS = REG == DSNT_REG_JS;
+  constexpr bool kVar = REG == DSNT_REG_VAR;
+  constexpr bool kMSE = REG == DSNT_REG_MSE;
+  constexpr bool kWin = kJS || kMSE;
+  static_assert(REG != DSNT_REG_KL, "KL takes the generic step kernel");
+  constexpr int VEC = 16 / sizeof(T);      // pixels per 128-bit vector
+  constexpr int NP = VEC / 2;              // packed pairs per vector
+  constexpr int WV = W / VEC;              // vectors per row
+  static_assert(W % VEC == 0 && 32 % WV == 0, "a warp must cover whole rows");
+  constexpr int RPI = 32 / WV;             // rows per sweep step
+  static_assert(H % RPI == 0, "whole sweep steps");
+  constexpr int ITERS = H / RPI;
+  constexpr int MAXS = step2_slots<T>();
+  constexpr uint32_t hm_bytes = static_cast<uint32_t>(H) * W * sizeof(T);
+  constexpr float tow = 2.0f / W, bw = 1.0f / W - 1.0f, toh = 2.0f / H, bh = 1.0f / H - 1.0f;
+  constexpr float dyi = RPI * toh;
+  // every e below is 2^(z log2e - m2 + kBias): bf16 heatmaps stash e as fp16, whose range [6e-8, 65504] is centred on
+  // the values by the bias; sums, 1/S and the probabilities P = e / S carry the factor consistently
+  constexpr float kBias = sizeof(T) == 2 ? 15.0f : 0.0f;
+  // MSE feeds e into its own gradient factor (2 rho (P - G) next to a x + b y - c): where the two nearly cancel, the 2^-12
+  // of an fp16 e would be amplified, so bf16 + MSE recomputes e from the logits in the backward sweep instead
+  constexpr bool kStash = !(kMSE && sizeof(T) == 2);
+
+  extern __shared__ __align__(128) unsigned char step_smem[];
+  __shared__ __align__(8) unsigned long long bars[kStepMaxBufs];
+  __shared__ volatile int issued[kStepMaxBufs];   // see head_step.cuh: loads issued into each buffer so far
+  __shared__ unsigned long long pace_next;        // clock at which the CTA may issue its next bulk load (p.pace)
+  __shared__ PendingLoad pend_all[NWMAX];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.nwarps) return;
+  const Geom& g = p.g;
+  const int NW = p.nwarps, NB = p.nbufs;
+  const uint32_t smem0_s = smem_u32(step_smem), bars0_s = smem_u32(&bars[0]);
+  const char* zsrc = static_cast<const char*>(p.z);
+  char* dzdst = static_cast<char*>(p.dz);
+  // tiles of this CTA, interleaved across the CTAs: heatmap = tile * gridDim.x + blockIdx.x (one contiguous range per CTA
+  // was measured slower, profiles/r01_v7_step2_sweeps.txt)
+  const long hm_mul = static_cast<long>(gridDim.x), hm_add = static_cast<long>(blockIdx.x);
+  const long ntiles = p.n > blockIdx.x ? (p.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (threadIdx.x == 0) pace_next = 0;
+  if (lane == 0) {
+    for (int t = warp; t < NB; t += NW) {
+      const uint32_t bar = bars0_s + 8 * t;
+      mbar_init(bar, 1);
+      if (t < ntiles) {
+        mbar_expect_tx(bar, hm_bytes);
+        bulk_load(smem0_s + static_cast<uint32_t>(t) * p.buf_bytes, zsrc + (t * hm_mul + hm_add) * hm_bytes,
+                  hm_bytes, bar);
+      }
+      issued[t] = 1;
+    }
+  }
+  __syncthreads();
+  if (p.stagger_ns > 0) __nanosleep(static_cast<unsigned>(warp * p.stagger_ns + (blockIdx.x & 3) * (p.stagger_ns >> 2)));
+  const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
+  const float inv_denom = 1.0f / __ldg(p.denom);
+  const float s2 = p.sigma * p.sigma;
+
+  // lane geometry: vector column cv (pixels cv*VEC ...), rows r0, r0 + RPI, ...
+  const int cv = lane & (WV - 1), r0 = lane / WV;
+  float xs[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) xs[c] = fmaf(static_cast<float>(cv * VEC + c), tow, bw);
+  const float y0 = fmaf(static_cast<float>(r0), toh, bh);
+  const f2 l2e2 = pk1(kLog2e);
+
+  volatile PendingLoad& pend = pend_all[warp];
+  if (lane == 0) pend.tile = -1;
+  __syncwarp();
+  auto issue_load = [&](long tile, uint32_t b, uint32_t rnd) {
+    ring_issue(zsrc + (tile * hm_mul + hm_add) * hm_bytes, hm_bytes, bars0_s + 8 * b, smem0_s + b * static_cast<uint32_t>(p.buf_bytes),
+               &issued[b], static_cast<int>(rnd) + 2);
+  };
+  // lane 0: the pending load goes if its time has come (force: wait for it)
+  auto flush_pending = [&](bool force) {
+    if (lane == 0 && pend.tile >= 0) {
+      if (force) { while (static_cast<int>(static_cast<uint32_t>(clock64()) - pend.when) < 0) { } }
+      if (force || static_cast<int>(static_cast<uint32_t>(clock64()) - pend.when) >= 0) {
+        issue_load(pend.tile, pend.slot & 0xffu, pend.slot >> 8);
+        pend.tile = -1;
+      }
+    }
+  };
+
+  // tile t lives in buffer bi = t mod NB on its round-th use (NW <= NB: bi wraps at most once per step)
+  uint32_t round = 0, bi = static_cast<uint32_t>(warp);
+  const int nt32 = static_cast<int>(ntiles);
+  // target and mask of the NEXT heatmap are fetched one heatmap ahead (the global-load latency was 12 % of the stall
+  // samples at the top of the loop, profiles/r01_v7_*)
+  float2 tgt_next = make_float2(0.f, 0.f);
+  float msk_next = 1.0f;
+  if (warp < nt32) {
+    const long hm0 = warp * hm_mul + hm_add;
+    if (p.target) tgt_next = __ldg(reinterpret_cast<const float2*>(p.target) + hm0);
+    if (p.mask) msk_next = __ldg(p.mask + hm0);
+  }
+  for (int t = warp; t < nt32; t += NW, bi += NW) {
+    if (bi >= static_cast<uint32_t>(NB)) { bi -= NB; ++round; }
+    const long hm = t * hm_mul + hm_add;
+    const uint32_t phase = round & 1u;
+    unsigned char* buf = step_smem + static_cast<size_t>(bi) * p.buf_bytes;
+    const uint32_t buf_s = smem0_s + bi * static_cast<uint32_t>(p.buf_bytes), bar_s = bars0_s + 8 * bi;
+    const uint4* bufv = reinterpret_cast<const uint4*>(buf);
+    const uint4* bv = bufv + lane;           // sweep step it reads bv[32 * it]
+    uint4* bst = reinterpret_cast<uint4*>(buf) + lane;   // the stash goes where the vector came from
+    uint4* dzv = reinterpret_cast<uint4*>(dzdst + hm * hm_bytes);
+
+    const float tx = tgt_next.x, ty = tgt_next.y;
+    const float wgt = msk_next * inv_denom;
+    if (t + NW < nt32) {
+      const long hmn = (t + NW) * hm_mul + hm_add;
+      if (p.target) tgt_next = __ldg(reinterpret_cast<const float2*>(p.target) + hmn);
+      if (p.mask) msk_next = __ldg(p.mask + hmn);
+    }
+    // the Gaussian window, widened to whole vectors along x
+    int i_lo = 0, jv_lo = 0, nvw = 0, nwv = 0, j_lo = 0, j_hi = -1, i_hi = -1;
+    if constexpr (kWin) {
+      Window win;
+      axis_window_fast(tx, W, 0.5f * W, tow, bw, g.r2_win, win.j_lo, win.j_hi);
+      axis_window_fast(ty, H, 0.5f * H, toh, bh, g.r2_win, win.i_lo, win.i_hi);
+      if (!win.empty()) {
+        j_lo = win.j_lo; j_hi = win.j_hi; i_lo = win.i_lo; i_hi = win.i_hi;
+        jv_lo = win.j_lo / VEC;
+        nvw = win.j_hi / VEC - jv_lo + 1;
+        nwv = (win.i_hi - win.i_lo + 1) * nvw;
+      }
+    }
+
+    // about to block on this heatmap's barrier?  then this warp's pending load must not wait for it
+    if (lane == 0 && pend.tile >= 0 && (issued[bi] < static_cast<int>(round) + 1 || !mbar_test(bar_s, phase))) flush_pending(true);
+    if (NB != NW) {
+      while (issued[bi] < static_cast<int>(round) + 1) { }
+    }
+    mbar_wait(bar_s, phase);
+
+    if (p.debug & 1) {   // measurement aid: the data movement of the step without its arithmetic (z copied to dz)
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) { dzv[lane + 32 * it] = bv[32 * it]; sweep_fence(it); }
+      __syncwarp();
+      if (lane == 0) {
+        const long nt = static_cast<long>(t) + NB;
+        if (nt < ntiles) {
+          if (p.pace > 0) {
+            const unsigned long long when = pace_reserve(&pace_next, p.pace, static_cast<unsigned long long>(clock64()));
+            while (static_cast<unsigned long long>(clock64()) < when) { }
+          }
+          issue_load(nt, bi, round);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+
+    // ---------------------------------------------------------------- forward: max
+    float mloc;
+    if constexpr (sizeof(T) == 2) {
+      uint32_t m0 = 0xff80ff80u, m1 = 0xff80ff80u;   // (-inf, -inf)
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const uint4 r = bv[32 * it];
+        m0 = max_bf16x2(m0, r.x); m1 = max_bf16x2(m1, r.y);
+        m0 = max_bf16x2(m0, r.z); m1 = max_bf16x2(m1, r.w);
+        sweep_fence(it);
+      }
+      m0 = max_bf16x2(m0, m1);
+      mloc = fmaxf(bf16lo(m0), bf16hi(m0));
+    } else {
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const uint4 r = bv[32 * it];
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(r.x), __uint_as_float(r.y)));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(r.z), __uint_as_float(r.w)));
+        sweep_fence(it);
+      }
+      mloc = fmaxf(m0, m1);
+    }
+    const float m2 = warp_max_redux(mloc) * kLog2e;
+    const f2 nm2 = pk1(kBias - m2);
+    // vectors of this lane inside the (vector-aligned) window: rows rlo..rhi relative to the lane's first row
+    const bool colin = kWin && nwv > 0 && cv >= jv_lo && cv < jv_lo + nvw;
+    const int rlo = i_lo - r0, rhi = i_hi - r0;
+
+    // ---------------------------------------------------------------- forward: column sums + row sums of e = 2^(z log2e - m2)
+    float S, Sx, Sy = 0.f, Tt = 0.f;
+    f2 colE[NP];
+    float rsk[kVar ? ITERS : 1];
+    {
+      f2 tt2 = pk1(0.f);
+      const float ya = opaque(y0);
+#pragma unroll
+      for (int c = 0; c < NP; ++c) colE[c] = pk1(0.f);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const uint4 raw = bv[32 * it];
+        f2 v[NP], e[NP];
+        unpack_pairs<T>(raw, v);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          e[c] = ex2_2(fma2(v[c], l2e2, nm2));
+          colE[c] = add2(colE[c], e[c]);
+          if (kMSE) tt2 = fma2(e[c], e[c], tt2);
+        }
+        f2 s = add2(e[0], e[1]);
+        if constexpr (NP == 4) s = add2(s, add2(e[2], e[3]));
+        const float rs = hsum(s);
+        Sy = fmaf(rs, ya + static_cast<float>(it) * dyi, Sy);
+        if constexpr (kVar) rsk[it] = rs;
+        const bool inwin = kWin && colin && (it * RPI >= rlo) && (it * RPI <= rhi);
+        if (kStash && !inwin) bst[32 * it] = stash_pack<T>(e);
+        sweep_fence(it);
+      }
+      S = 0.f; Sx = 0.f;
+#pragma unroll
+      for (int c = 0; c < NP; ++c) {
+        float lo, hi;
+        upk(colE[c], lo, hi);
+        S += lo + hi;
+        Sx = fmaf(lo, xs[2 * c], fmaf(hi, xs[2 * c + 1], Sx));
+      }
+      Tt = hsum(tt2);
+    }
+    {
+      const float k = warp_sum4_transposed(S, Sx, Sy, Tt, lane);
+      S = __shfl_sync(kFull, k, 0); Sx = __shfl_sync(kFull, k, 8); Sy = __shfl_sync(kFull, k, 16); Tt = __shfl_sync(kFull, k, 24);
+    }
+    flush_pending(false);
+    const float invS = rcp(S);             // S >= 1: one MUFU, 1 ulp
+    const float mux = Sx * invS, muy = Sy * invS;
+
+    float D = 0.f, creg = 0.f, ginv = 0.f, vx = 0.f, vy = 0.f;
+
+    // ---------------------------------------------------------------- forward: variance about the mean, from the sums
+    if constexpr (kVar) {
+      float ax = 0.f, ay = 0.f;
+      const float yv = opaque(y0) - muy;
+#pragma unroll
+      for (int c = 0; c < NP; ++c) {
+        float lo, hi;
+        upk(colE[c], lo, hi);
+        const float d0 = xs[2 * c] - mux, d1 = xs[2 * c + 1] - mux;
+        ax = fmaf(lo * d0, d0, fmaf(hi * d1, d1, ax));
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const float d = yv + static_cast<float>(it) * dyi;
+        ay = fmaf(rsk[it] * d, d, ay);
+      }
+      {
+        const float k = warp_sum2_transposed(ax, ay, lane);
+        ax = __shfl_sync(kFull, k, 0); ay = __shfl_sync(kFull, k, 16);
+      }
+      vx = ax * invS;
+      vy = ay * invS;
+      const float ex = vx - s2, ey = vy - s2;
+      D = ex * ex + ey * ey;
+      creg = 2.f * (ex * vx + ey * vy);
+    }
+
+    // ---------------------------------------------------------------- forward: divergence on the window (compact mapping)
+    f2 wd[kWin ? MAXS : 1][NP], wP[kWin ? MAXS : 1][NP];   // per window pixel: log2 P - 1 - log2 M (JS) or G (MSE); P
+    float inv_nvw = 0.f;
+    if constexpr (kWin) {
+      f2 qa = pk1(0.f), qb = pk1(0.f), qc = pk1(0.f);
+      if (nwv > 0) {
+        float sx = 0.f, sy = 0.f;
+        for (int j = j_lo + lane; j <= j_hi; j += 32) {
+          const float d = fmaf(static_cast<float>(j), tow, bw) - tx;
+          sx += ex2(g.k2 * d * d);
+        }
+        for (int i = i_lo + lane; i <= i_hi; i += 32) {
+          const float d = fmaf(static_cast<float>(i), toh, bh) - ty;
+          sy += ex2(g.k2 * d * d);
+        }
+        {
+          const float k = warp_sum2_transposed(sx, sy, lane);
+          sx = __shfl_sync(kFull, k, 0);
+          sy = __shfl_sync(kFull, k, 16);
+        }
+        ginv = rcp(sx * sy + kEps);
+        const float l2ginv = lg2(ginv);
+        const f2 tlm1 = pk1(-lg2(S) - 1.0f);         // log2 P - 1 = t + tlm1
+        const f2 hinvS = pk1(0.5f * invS), invS2 = pk1(invS), k2p = pk1(g.k2), half2 = pk1(0.5f), eps2 = pk1(kEps);
+        inv_nvw = rcp(static_cast<float>(nvw));
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+          const int k = lane + 32 * s;
+          if (k < nwv) {
+            const int r = static_cast<int>((static_cast<float>(k) + 0.5f) * inv_nvw);
+            const int i = i_lo + r, jv = jv_lo + (k - r * nvw);
+            const uint4 raw = bufv[i * WV + jv];
+            f2 v[NP];
+            unpack_pairs<T>(raw, v);
+            const float dy = fmaf(static_cast<float>(i), toh, bh) - ty;
+            const f2 rowt = pk1(fmaf(g.k2 * dy, dy, l2ginv));
+            const f2 dx0 = pk1(fmaf(static_cast<float>(jv * VEC), tow, bw) - tx);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) {
+              const f2 dx = add2(dx0, pk((2 * c) * tow, (2 * c + 1) * tow));
+              const f2 lgG = fma2(mul2(dx, k2p), dx, rowt);
+              const f2 G = ex2_2(lgG);
+              const f2 tt = fma2(v[c], l2e2, nm2);
+              const f2 e = ex2_2(tt);
+              const f2 P = mul2(e, invS2);
+              wP[s][c] = P;
+              if constexpr (kJS) {
+                const f2 L = lg2_2(fma2(e, hinvS, fma2(half2, G, eps2)));
+                const f2 d = sub2(add2(tt, tlm1), L);
+                qa = fma2(P, d, qa);
+                qb = fma2(G, sub2(lgG, L), qb);
+                wd[s][c] = d;
+              } else {
+                const f2 df = sub2(P, G);
+                qa = fma2(df, df, qa);
+                qb = fma2(P, P, qb);
+                qc = fma2(P, df, qc);
+                wd[s][c] = G;
+              }
+            }
+          }
+        }
+      }
+      float a0 = hsum(qa), a1 = hsum(qb), a2 = hsum(qc), a3 = 0.f;
+      {
+        const float k = warp_sum4_transposed(a0, a1, a2, a3, lane);
+        a0 = __shfl_sync(kFull, k, 0); a1 = __shfl_sync(kFull, k, 8); a2 = __shfl_sync(kFull, k, 16);
+      }
+      if (kMSE) {
+        const float outside = fmaxf(fmaf(Tt * invS, invS, -a1), 0.f);
+        D = outside + a0;
+        creg = 2.f * (outside + a2);
+      } else {
+        creg = 0.5f * kLn2 * (1.0f + a0);
+        D = fmaf(0.5f * kLn2, a1, creg);
+      }
+    }
+
+    // ---------------------------------------------------------------- outputs + the scalars of the backward
+    float dist = 0.f, a = 0.f, b = 0.f;
+    if (p.target) {
+      const float dx = mux - tx, dy = muy - ty;
+      const float d2 = dx * dx + dy * dy;
+      const float rs = rsqrtf(d2);
+      dist = d2 > 0.f ? d2 * rs : 0.f;
+      const float invd = d2 > 0.f ? rs : ((p.flags & DSNT_FLAG_STRICT_NAN) ? INFINITY : 0.f);
+      a = gl * wgt * (dx * invd);
+      b = gl * wgt * (dy * invd);
+    }
+    const float rho = gl * wgt * p.reg_coeff;
+    if (lane == 0) {
+      reinterpret_cast<float2*>(p.coords)[hm] = make_float2(mux, muy);
+      if (p.stats) {
+        float4* st = reinterpret_cast<float4*>(p.stats + hm * kStatsK);
+        st[0] = make_float4(m2, invS * exp2f(kBias), mux, muy);
+        st[1] = make_float4(vx, vy, creg, ginv);
+      }
+      if (p.terms) reinterpret_cast<float2*>(p.terms)[hm] = make_float2(dist, D);
+    }
+    const float cc = fmaf(a, mux, fmaf(b, muy, rho * creg));
+    float cbase = -cc;
+    if (kJS) cbase = fmaf(0.5f * kLn2, rho, cbase);
+
+    // ---------------------------------------------------------------- backward on the window vectors, from registers
+    if constexpr (kWin) {
+      if (nwv > 0) {
+        const f2 a2p = pk1(a), kw = pk1(kJS ? 0.5f * kLn2 * rho : 2.f * rho);
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+          const int k = lane + 32 * s;
+          if (k < nwv) {
+            const int r = static_cast<int>((static_cast<float>(k) + 0.5f) * inv_nvw);
+            const int i = i_lo + r, jv = jv_lo + (k - r * nvw);
+            const f2 rowc = pk1(fmaf(b, fmaf(static_cast<float>(i), toh, bh), cbase));
+            const f2 x0 = pk1(fmaf(static_cast<float>(jv * VEC), tow, bw));
+            f2 o[NP];
+#pragma unroll
+            for (int c = 0; c < NP; ++c) {
+              const f2 x = add2(x0, pk((2 * c) * tow, (2 * c + 1) * tow));
+              f2 gm = fma2(a2p, x, rowc);
+              if constexpr (kJS) gm = fma2(kw, wd[s][c], gm);                  // -(ln2/2) rho log2(1 + (G + 2 eps)/P)
+              else gm = fma2(kw, sub2(wP[s][c], wd[s][c]), gm);                // 2 rho (P - G)
+              o[c] = mul2(wP[s][c], gm);
+            }
+            dzv[i * WV + jv] = pack_pairs<T>(o);
+          }
+        }
+      }
+    }
+
+    // ---------------------------------------------------------------- backward: every other vector, dz = e * (A_col + R_row)
+    {
+      f2 acol[NP];
+#pragma unroll
+      for (int c = 0; c < NP; ++c) {
+        float v0 = a * xs[2 * c], v1 = a * xs[2 * c + 1];
+        if (kVar) {
+          const float kx = rho * 2.f * (vx - s2);
+          const float d0 = xs[2 * c] - mux, d1 = xs[2 * c + 1] - mux;
+          v0 = fmaf(kx * d0, d0, v0);
+          v1 = fmaf(kx * d1, d1, v1);
+        }
+        acol[c] = pk(v0 * invS, v1 * invS);
+      }
+      const float bS = b * invS, cbS = cbase * invS;
+      const float kyS = kVar ? rho * 2.f * (vy - s2) * invS : 0.f;
+      const f2 rpS = pk1(kMSE ? 2.f * rho * invS * invS : 0.f);
+      const float yb = opaque(y0);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const uint4 raw = bv[32 * it];
+        f2 e[NP], o[NP];
+        if constexpr (kStash) {
+          stash_unpack<T>(raw, e);
+        } else {
+          f2 v[NP];
+          unpack_pairs<T>(raw, v);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) e[c] = ex2_2(fma2(v[c], l2e2, nm2));
+        }
+        const float y = yb + static_cast<float>(it) * dyi;
+        float rc = fmaf(bS, y, cbS);
+        if (kVar) { const float d = y - muy; rc = fmaf(kyS * d, d, rc); }
+        const f2 rc2 = pk1(rc);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          f2 gm = add2(acol[c], rc2);
+          if (kMSE) gm = fma2(rpS, e[c], gm);
+          o[c] = mul2(e[c], gm);
+        }
+        const bool inwin = kWin && colin && (it * RPI >= rlo) && (it * RPI <= rhi);
+        if (!inwin) dzv[lane + 32 * it] = pack_pairs<T>(o);
+        sweep_fence(it);
+      }
+    }
+
+    // ---------------------------------------------------------------- hand the buffer to the next tile
+    if (kStash) fence_async_smem();   // this lane's writes of e (generic proxy) are ordered before the bulk load (async proxy)
+    __syncwarp();
+    flush_pending(true);     // at most one load is pending per warp
+    if (lane == 0) {
+      const long nt = static_cast<long>(t) + NB;
+      if (nt < ntiles) {
+        const unsigned long long now = static_cast<unsigned long long>(clock64());
+        const unsigned long long when = p.pace > 0 ? pace_reserve(&pace_next, p.pace, now) : now;
+        pend.when = static_cast<uint32_t>(when); pend.tile = static_cast<int>(nt); pend.slot = bi | (round << 8);
+      }
+    }
+    flush_pending(false);    // goes at once unless its slot lies in the future
+    __syncwarp();
+  }
+  flush_pending(true);
+}
+
+}  // namespace dsnt

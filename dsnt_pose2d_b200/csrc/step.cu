@@ -1,8 +1,11 @@
 // step.cu -- launcher and extern "C" entry point of the one-pass training step (head_step.cuh).
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "capi_util.cuh"
 #include "head_step.cuh"
+#include "head_step2.cuh"
 
 namespace dsnt {
 
@@ -25,6 +28,79 @@ static int env_int(const char* name, int dflt) {
 static int step_direct_store() { static const int v = env_int("DSNT_TUNE_STEP_STG", 1); return v; }
 static int step_group() { static const int v = env_int("DSNT_TUNE_STEP_GROUP", 32); return v; }
 static int step_warps() { static const int v = env_int("DSNT_TUNE_STEP_WARPS", 0); return v; }
+static int step_v2() { static const int v = env_int("DSNT_TUNE_STEP_V2", 1); return v; }
+static int step_spare() { static const int v = env_int("DSNT_TUNE_STEP_SPARE", -1); return v; }
+
+// ---------------------------------------------------------------------------------- shape-specialised kernel (head_step2.cuh)
+// The compact window mapping holds 32 * step2_slots() vectors in registers: the window of ANY target (upper bound as in
+// launch.cuh:stash_fits -- floor(n sqrt(r2 + 1/n^2)) + 4 pixels per axis, widened to whole vectors along x) must fit.
+template <typename T>
+static bool step2_window_fits(int H, int W, int vec, int reg, float r2_win) {
+  if (!reg_needs_gauss(reg)) return true;
+  const double r2 = r2_win;
+  const int mc = static_cast<int>(std::floor(W * std::sqrt(r2 + 1.0 / (static_cast<double>(W) * W)))) + 4;
+  const int mr = static_cast<int>(std::floor(H * std::sqrt(r2 + 1.0 / (static_cast<double>(H) * H)))) + 4;
+  const int vecs = std::min(W / vec, (mc + vec - 2) / vec + 1);
+  const int rows = std::min(H, mr);
+  return rows * vecs <= 32 * step2_slots<T>();
+}
+
+// Load pacing (head_step2.cuh:pace_wait): SM clocks between two bulk loads of a CTA = the time one heatmap (read + write)
+// takes at a whole-GPU bandwidth of DSNT_TUNE_STEP_PACE_GBS (0 = unpaced); DSNT_TUNE_STEP_PACE gives the clocks directly.
+static int step2_pace_cycles(long hm_bytes, int ctas) {
+  static const int fixed = env_int("DSNT_TUNE_STEP_PACE", -1);
+  if (fixed >= 0) return fixed;
+  static const int gbs = env_int("DSNT_TUNE_STEP_PACE_GBS", 6750);
+  if (gbs <= 0) return 0;
+  static double ghz = 0.0;
+  if (ghz == 0.0) {
+    int dev = 0, khz = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0)
+      khz = 1965000;
+    ghz = khz * 1e-6;
+  }
+  const double ns = 2.0 * hm_bytes * ctas / static_cast<double>(gbs);     // bytes / (GB/s) = ns
+  return static_cast<int>(ns * ghz + 0.5);
+}
+
+template <typename T, int REG, int H, int W, int NWMAX>
+static int launch_step2_nw(HeadStepParams p, cudaStream_t stream) {
+  auto kern = head_step2_kernel<T, REG, H, W, NWMAX>;
+  p.nbufs = kStepSmemBudget / p.buf_bytes;
+  if (p.nbufs > kStepMaxBufs) p.nbufs = kStepMaxBufs;
+  static const int nbuf_cap = env_int("DSNT_TUNE_STEP_NBUF2", 0);
+  if (nbuf_cap > 0 && p.nbufs > nbuf_cap) p.nbufs = nbuf_cap;
+  const int spare = step_spare() >= 0 ? step_spare() : 2;   // loads in flight while every warp computes
+  p.nwarps = step_warps() > 0 ? step_warps() : p.nbufs - spare;
+  if (p.nwarps > NWMAX) p.nwarps = NWMAX;
+  if (p.nwarps > p.nbufs) p.nwarps = p.nbufs;
+  if (p.nwarps < 1) p.nwarps = 1;
+  const size_t smem = static_cast<size_t>(p.nbufs) * p.buf_bytes;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return check_launch("head_step2_kernel (shared-memory opt-in)");
+    configured = smem;
+  }
+  long ctas = p.n < sm_count() ? p.n : sm_count();
+  p.pace = step2_pace_cycles(static_cast<long>(H) * W * sizeof(T), static_cast<int>(ctas));
+  kern<<<static_cast<unsigned>(ctas), p.nwarps * 32, smem, stream>>>(p);
+  return check_launch("head_step2_kernel");
+}
+
+// NWMAX only sets the register budget (__launch_bounds__): 65536 / (32 NWMAX) registers per thread.
+template <typename T, int REG, int H, int W>
+static int launch_step2(const HeadStepParams& p, cudaStream_t stream) {
+  static const int nwmax = env_int("DSNT_TUNE_STEP_NWMAX", 0);
+  if constexpr (sizeof(T) == 2) {
+    if (nwmax == 24) return launch_step2_nw<T, REG, H, W, 24>(p, stream);
+    if (nwmax == 20) return launch_step2_nw<T, REG, H, W, 20>(p, stream);
+    return launch_step2_nw<T, REG, H, W, 16>(p, stream);
+  } else {
+    if (nwmax == 16) return launch_step2_nw<T, REG, H, W, 16>(p, stream);
+    return launch_step2_nw<T, REG, H, W, 12>(p, stream);
+  }
+}
 
 // Measured on B200 at cfg 4 (profiles/r01_v4_step_sweep.txt, r01_v5_step_ring.txt): one warp per heatmap and direct
 // 128-bit stores; DSNT_TUNE_STEP_{WARPS,GROUP,STG} override for experiments.
@@ -53,6 +129,12 @@ static int launch_step_one(HeadStepParams p, cudaStream_t stream) {
 // one warp per heatmap by default (DSNT_TUNE_STEP_GROUP=64 selects two)
 template <typename T, int VEC, int REG>
 static int launch_step_fixc(HeadStepParams p, cudaStream_t stream) {
+  if constexpr (REG != DSNT_REG_KL) {
+    if (p.H == 64 && p.W == 64 && step_v2() && p.direct_store && step_group() != 64) {
+      p.g = make_geom(p.H, p.W, VEC, 32, p.sigma > 0.f ? p.sigma : 1.f, REG);
+      if (step2_window_fits<T>(p.H, p.W, VEC, REG, p.g.r2_win)) return launch_step2<T, REG, 64, 64>(p, stream);
+    }
+  }
   if (step_group() != 64) {
     p.g = make_geom(p.H, p.W, VEC, 32, p.sigma > 0.f ? p.sigma : 1.f, REG);
     return (32 % p.g.wv == 0) ? launch_step_one<T, VEC, REG, true, 32>(p, stream) : launch_step_one<T, VEC, REG, false, 32>(p, stream);
@@ -119,6 +201,11 @@ DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, cons
   p.buf_bytes = (H * W * es + 127) / 128 * 128;
   p.nwarps = 0; p.nbufs = 0;   // chosen at launch
   p.direct_store = step_direct_store();
+  static const int stagger = env_int("DSNT_TUNE_STEP_STAGGER", 0);
+  p.stagger_ns = stagger;
+  static const int debug = env_int("DSNT_TUNE_STEP_DEBUG", 0);
+  p.debug = debug;
+  p.pace = 0;   // set per kernel in launch_step2_nw
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dtype == DSNT_DTYPE_F32 ? launch_step_reg<float, 4>(p, reg, s) : launch_step_reg<__nv_bfloat16, 8>(p, reg, s);
 }

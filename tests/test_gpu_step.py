@@ -212,3 +212,75 @@ def test_step_in_cuda_graph_and_model_head(dp, tp):
     out = head.forward_part2(z2)
     head.forward_loss(out, target, mask).backward()
     assert rel_l2(z2.grad.cpu().double().numpy(), ref['dz'].numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The shape-specialised 64x64 kernel (csrc/head_step2.cuh): compact Gaussian-window mapping, e stashed in shared memory
+# (fp32 exactly, bf16 as scaled fp16), paced bulk loads.
+@pytest.mark.parametrize('reg', ['js', 'mse', 'var', 'none'])
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+def test_step64_window_clipping_and_targets_outside_the_image(dp, tp, reg, dtype):
+    """Targets on the border pixels, between pixels, and outside [-1, 1] (clipped / empty Gaussian window), every lane
+    position of the window's first vector, more heatmaps per CTA than ring buffers."""
+    gen = torch.Generator().manual_seed(61)
+    b, c, h, w = 40, 16, 64, 64
+    z = torch.randn(b, c, h, w, generator=gen) * 2.0
+    target = torch.rand(b, c, 2, generator=gen) * 2.8 - 1.4           # a third of them outside the image
+    edge = torch.tensor([-1.0, -63.0 / 64, -62.5 / 64, 0.0, 1.0 / 64, 63.0 / 64, 1.0, 1.3, -1.3, 3.0])
+    target[0, :10, 0] = edge
+    target[1, :10, 1] = edge
+    target[2, :10, 0] = edge
+    target[2, :10, 1] = edge.flip(0)
+    for k in range(16):                                               # window start at every column phase
+        target[3, k, 0] = (2 * (8 + k) + 1) / 64.0 - 1.0
+    mask = (torch.rand(b, c, generator=gen) > 0.1).float()
+    if dtype == 'bf16':
+        z = z.to(torch.bfloat16)
+    ref = tp.head_loss_and_grad(z.float()[:4], target[:4], mask[:4], reg, 1.0, 1.0, dtype=torch.float64)
+    got = run_step(dp, z, target, mask, reg)
+    # the oracle runs on the first four samples; its masked mean has its own denominator
+    scale = mask[:4].sum().clamp(min=1).item() / mask.sum().clamp(min=1).item()
+    e_coords = float(np.abs(got['coords'][:4] - ref['coords'].numpy()).max())
+    e_dz = rel_l2(got['dz'][:4], ref['dz'].numpy() * scale)
+    print('step64 %s %s coords %.2e dz %.2e' % (reg, dtype, e_coords, e_dz))
+    assert e_coords < TOL
+    assert e_dz < (4e-3 if dtype == 'bf16' else TOL)
+    two = run_step(dp, z, target, mask, reg, one_pass=False)
+    assert abs(got['loss'] - two['loss']) < 3e-6 * abs(two['loss'])
+    assert rel_l2(got['dz'], two['dz']) < (4e-3 if dtype == 'bf16' else 3e-6)
+
+
+@pytest.mark.parametrize('reg', ['js', 'mse', 'var'])
+def test_step64_bf16_gradient_is_within_one_bf16_ulp_per_element(dp, tp, reg):
+    """The backward sweep reads e back as fp16 (11 significant bits, scaled by 2^15).  Rounding dz to bf16 alone costs up
+    to 2^-8 relative (half a bf16 ulp just above a power of two); the stash adds at most 2^-11 (half an fp16 ulp), so
+    every element that is not vanishingly small next to the largest one must be within 2^-8 + 2^-10 of the fp64 oracle:
+    the correctly rounded bf16 value or, within an eighth of an ulp of a rounding boundary, its neighbour."""
+    gen = torch.Generator().manual_seed(62)
+    z = (torch.randn(8, 16, 64, 64, generator=gen) * 3.0).to(torch.bfloat16)
+    target = torch.rand(8, 16, 2, generator=gen) * 1.6 - 0.8
+    ref = tp.head_loss_and_grad(z.float(), target, None, reg, 1.0, 1.0, dtype=torch.float64)
+    got = run_step(dp, z, target, None, reg)
+    want = ref['dz'].numpy().reshape(128, -1)
+    have = got['dz'].reshape(128, -1)
+    big = np.abs(want) > 1e-6 * np.abs(want).max(-1, keepdims=True)
+    rel = np.abs(have - want)[big] / np.abs(want)[big]
+    print('bf16 %s: max per-element relative error %.3e over %d elements' % (reg, rel.max(), big.sum()))
+    assert rel.max() <= 2.0 ** -8 + 2.0 ** -10
+
+
+def test_step64_many_heatmaps_per_cta_and_peaked_logits(dp, tp):
+    """More than two rounds of the buffer ring on every CTA, logits with a large dynamic range (e underflows in places)."""
+    gen = torch.Generator().manual_seed(63)
+    n = 148 * 70
+    z = torch.randn(n, 1, 64, 64, generator=gen) * 12.0
+    target = torch.rand(n, 1, 2, generator=gen) * 1.6 - 0.8
+    got = run_step(dp, z, target, None, 'js')
+    two = run_step(dp, z, target, None, 'js', one_pass=False)
+    assert np.isfinite(got['dz']).all()
+    assert abs(got['loss'] - two['loss']) < 3e-6 * abs(two['loss'])
+    assert float(np.abs(got['coords'] - two['coords']).max()) < 2e-6
+    assert rel_l2(got['dz'], two['dz']) < 3e-6
+    idx = torch.randperm(n, generator=gen)[:24]
+    ref = tp.head_loss_and_grad(z[idx], target[idx], None, 'js', 1.0, 1.0, dtype=torch.float64)
+    assert rel_l2(got['dz'][idx.numpy()] * (n / 24.0), ref['dz'].numpy()) < TOL

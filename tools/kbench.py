@@ -57,6 +57,7 @@ def main():
     ap.add_argument('--dtypes', default='f32,bf16')
     ap.add_argument('--variants', default='0')
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--step-only', action='store_true', help='time only the one-pass step kernel')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     peak, how = peak_gbs()
@@ -96,10 +97,14 @@ def main():
                                   out8[3:4].data_ptr(), 1.0, rid, sigma, 0, dzs[i % len(dzs)].data_ptr(), variant,
                                   stream)
                     try:
+                        if args.step_only:
+                            raise StopIteration
                         tf, tf_min = time_calls(fwd, args.iters)
                         _lib.call('dsnt_finish_loss', terms.data_ptr(), mask.data_ptr(), n, 1.0, out8.data_ptr(),
                                   ws.data_ptr(), stream)
                         tb, tb_min = time_calls(bwd, args.iters)
+                    except StopIteration:
+                        tf = tb = None
                     except RuntimeError as e:
                         print('%-6s %-5s %-5s %3d | FAILED %s' % (cfg, dt, reg, variant, e))
                         continue
@@ -114,6 +119,10 @@ def main():
                                       coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), dzs[i % len(dzs)].data_ptr(),
                                       stream)
                         ts, _ = time_calls(step, args.iters)
+                    if tf is None:
+                        print('%-6s %-5s %-5s || one-pass step %7.1f us %6.0f GB/s %5.3f %8.2f Mhm/s' % (
+                            cfg, dt, reg, ts * 1e3, 2 * nbytes / ts / 1e6, 2 * nbytes / ts / 1e6 / peak, n / ts / 1e3))
+                        continue
                     gf = nbytes / tf / 1e6
                     gb = 2 * nbytes / tb / 1e6
                     tot = (3 * nbytes + 96 * n) / (tf + tb) / 1e6
