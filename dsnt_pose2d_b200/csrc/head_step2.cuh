@@ -165,7 +165,9 @@ __device__ __forceinline__ unsigned long long pace_reserve(unsigned long long* s
 template <typename T>
 __host__ __device__ constexpr int step2_slots() { return sizeof(T) == 2 ? 3 : 4; }
 
-template <typename T, int REG, int H, int W, int NWMAX>
+// PACED = false compiles the pacing out (loads are re-issued the moment a buffer is free): for the instantiations that
+// are bound by arithmetic anyway (bf16 with a Gaussian window), where the bookkeeping costs more than it brings.
+template <typename T, int REG, int H, int W, int NWMAX, bool PACED>
 __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadStepParams p) {
   constexpr bool kJS = REG == DSNT_REG_JS;
   constexpr bool kVar = REG == DSNT_REG_VAR;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   };
   // lane 0: the pending load goes if its time has come (force: wait for it)
   auto flush_pending = [&](bool force) {
+    if constexpr (!PACED) return;
     if (lane == 0 && pend.tile >= 0) {
       if (force) { while (static_cast<int>(static_cast<uint32_t>(clock64()) - pend.when) < 0) { } }
       if (force || static_cast<int>(static_cast<uint32_t>(clock64()) - pend.when) >= 0) {
@@ -297,7 +300,9 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     }
 
     // about to block on this heatmap's barrier?  then this warp's pending load must not wait for it
-    if (lane == 0 && pend.tile >= 0 && (issued[bi] < static_cast<int>(round) + 1 || !mbar_test(bar_s, phase))) flush_pending(true);
+    if constexpr (PACED) {
+      if (lane == 0 && pend.tile >= 0 && (issued[bi] < static_cast<int>(round) + 1 || !mbar_test(bar_s, phase))) flush_pending(true);
+    }
     if (NB != NW) {
       while (issued[bi] < static_cast<int>(round) + 1) { }
     }
@@ -610,9 +615,16 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     if (lane == 0) {
       const long nt = static_cast<long>(t) + NB;
       if (nt < ntiles) {
-        const unsigned long long now = static_cast<unsigned long long>(clock64());
-        const unsigned long long when = p.pace > 0 ? pace_reserve(&pace_next, p.pace, now) : now;
-        pend.when = static_cast<uint32_t>(when); pend.tile = static_cast<int>(nt); pend.slot = bi | (round << 8);
+        if constexpr (PACED) {
+          const unsigned long long now = static_cast<unsigned long long>(clock64());
+          const unsigned long long when = p.pace > 0 ? pace_reserve(&pace_next, p.pace, now) : now;
+          pend.when = static_cast<uint32_t>(when); pend.tile = static_cast<int>(nt); pend.slot = bi | (round << 8);
+        } else {
+          mbar_expect_tx(bar_s, hm_bytes);
+          bulk_load(buf_s, zsrc + (nt * hm_mul + hm_add) * hm_bytes, hm_bytes, bar_s);
+          __threadfence_block();
+          issued[bi] = static_cast<int>(round) + 2;
+        }
       }
     }
     flush_pending(false);    // goes at once unless its slot lies in the future

@@ -63,9 +63,9 @@ static int step2_pace_cycles(long hm_bytes, int ctas) {
   return static_cast<int>(ns * ghz + 0.5);
 }
 
-template <typename T, int REG, int H, int W, int NWMAX>
+template <typename T, int REG, int H, int W, int NWMAX, bool PACED>
 static int launch_step2_nw(HeadStepParams p, cudaStream_t stream) {
-  auto kern = head_step2_kernel<T, REG, H, W, NWMAX>;
+  auto kern = head_step2_kernel<T, REG, H, W, NWMAX, PACED>;
   p.nbufs = kStepSmemBudget / p.buf_bytes;
   if (p.nbufs > kStepMaxBufs) p.nbufs = kStepMaxBufs;
   static const int nbuf_cap = env_int("DSNT_TUNE_STEP_NBUF2", 0);
@@ -83,22 +83,27 @@ static int launch_step2_nw(HeadStepParams p, cudaStream_t stream) {
     configured = smem;
   }
   long ctas = p.n < sm_count() ? p.n : sm_count();
-  p.pace = step2_pace_cycles(static_cast<long>(H) * W * sizeof(T), static_cast<int>(ctas));
+  p.pace = PACED ? step2_pace_cycles(static_cast<long>(H) * W * sizeof(T), static_cast<int>(ctas)) : 0;
   kern<<<static_cast<unsigned>(ctas), p.nwarps * 32, smem, stream>>>(p);
   return check_launch("head_step2_kernel");
 }
 
-// NWMAX only sets the register budget (__launch_bounds__): 65536 / (32 NWMAX) registers per thread.
+// NWMAX only sets the register budget (__launch_bounds__): 65536 / (32 NWMAX) registers per thread.  bf16 heatmaps with a
+// Gaussian window are bound by arithmetic, not by HBM: they run unpaced (DSNT_TUNE_STEP_PACED=1 forces the paced build).
 template <typename T, int REG, int H, int W>
 static int launch_step2(const HeadStepParams& p, cudaStream_t stream) {
   static const int nwmax = env_int("DSNT_TUNE_STEP_NWMAX", 0);
+  static const int paced = env_int("DSNT_TUNE_STEP_PACED", -1);
   if constexpr (sizeof(T) == 2) {
-    if (nwmax == 24) return launch_step2_nw<T, REG, H, W, 24>(p, stream);
-    if (nwmax == 20) return launch_step2_nw<T, REG, H, W, 20>(p, stream);
-    return launch_step2_nw<T, REG, H, W, 16>(p, stream);
+    if (nwmax == 24) return launch_step2_nw<T, REG, H, W, 24, true>(p, stream);
+    if (nwmax == 20) return launch_step2_nw<T, REG, H, W, 20, true>(p, stream);
+    if constexpr (REG == DSNT_REG_JS || REG == DSNT_REG_MSE) {
+      if (paced != 1) return launch_step2_nw<T, REG, H, W, 16, false>(p, stream);
+    }
+    return launch_step2_nw<T, REG, H, W, 16, true>(p, stream);
   } else {
-    if (nwmax == 16) return launch_step2_nw<T, REG, H, W, 16>(p, stream);
-    return launch_step2_nw<T, REG, H, W, 12>(p, stream);
+    if (nwmax == 16) return launch_step2_nw<T, REG, H, W, 16, true>(p, stream);
+    return launch_step2_nw<T, REG, H, W, 12, true>(p, stream);
   }
 }
 

@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-timeout 800 python -m pytest tests -m gpu -q > gpurun_out/v7_pytest_gpu.log 2>&1; tail -4 gpurun_out/v7_pytest_gpu.log
-timeout 400 python bench.py > gpurun_out/v7_bench.json 2> gpurun_out/v7_bench.err; cat gpurun_out/v7_bench.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/v7_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/v7_ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:head_step2 -s 3 -c 1 -f -o gpurun_out/v7_step2_f32_js python tools/kbench.py --configs cfg4 --regs js --dtypes f32 --iters 3 --step-only > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:head_step2 -s 3 -c 1 -f -o gpurun_out/v7_step2_bf16_js python tools/kbench.py --configs cfg4 --regs js --dtypes bf16 --iters 3 --step-only > gpurun_out/ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:head_step2 -s 3 -c 1 -f -o gpurun_out/v7_step2_bf16_var python tools/kbench.py --configs cfg4 --regs var --dtypes bf16 --iters 3 --step-only > gpurun_out/ncu3.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_step.py tests/test_gpu_model.py tests/test_gpu_parity.py -q > gpurun_out/v8_pytest.log 2>&1; tail -3 gpurun_out/v8_pytest.log
+K="timeout 200 python tools/kbench.py --configs cfg4 --step-only"
+echo "== default"; $K --regs none,var,js,mse --dtypes f32,bf16 2>&1 | grep one-pass
+echo "== bf16 js/mse PACED=1"; DSNT_TUNE_STEP_PACED=1 $K --regs js,mse --dtypes bf16 2>&1 | grep one-pass
+timeout 400 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/v8_bench.json 2> gpurun_out/v8_bench.err; cat gpurun_out/v8_bench.json
