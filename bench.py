@@ -5,7 +5,8 @@
 
 Workload (BASELINE.json configs[3], the one the metric is quoted on): per GPU a batch of 4096 samples x 16
 MPII joints x 64x64 fp32 logits, Euclidean loss + JS regulariser (sigma = 1 px), joint mask; weak scaling
-(every rank owns a fixed 4096-sample shard of a 4096*N batch, three floats are all-reduced per step).
+(every rank owns a fixed 4096-sample shard of a 4096*N batch; the three partial sums of masked_average are
+exchanged between the ranks inside the finishing kernels over NVLink peer memory, or by NCCL where that is unavailable).
 
 A "step" is one pass of the hot path over one batch: fused forward (coords, loss) + backward (dL/dZ), through the
 public autograd API (`dsnt_head(...).loss.backward()`).  --path one-pass (default) lets the forward also write dL/dZ
@@ -279,7 +280,10 @@ def main_ours(args):
     mask = (torch.rand(bsz, joints, device=dev) > 0.1).float()
 
     from dsnt_pose2d_b200.head import step_supported
+    from dsnt_pose2d_b200.parallel import PeerExchange
     one_pass = args.path == 'one-pass' and step_supported(z)
+    exchange_note = ('inside the finishing kernels over NVLink peer memory (no collective launch)'
+                     if PeerExchange.get(group, dev) is not None else 'by a 3-float NCCL all-reduce')
 
     def step():
         z.grad = None
@@ -432,7 +436,8 @@ def main_ours(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
         'config': {'workload': args.workload, 'heatmaps_per_gpu': n_local, 'batch_per_gpu': bsz, 'joints': joints,
                    'heatmap': [h, w], 'reg': reg, 'hm_sigma_px': 1.0, 'mask': True,
-                   'parallelism': 'batch-sharded x%d, 3-float all-reduce per step' % world,
+                   'parallelism': ('batch-sharded x%d; the three partial sums of masked_average are exchanged %s' % (
+                       world, exchange_note)) if world > 1 else 'single GPU (batch shard = whole batch)',
                    'l2_policy': 'inputs larger than L2 (%.0f MiB of logits per step vs 126 MB L2)'
                                 % (n_local * hw * esize / 2 ** 20),
                    'path': ('one-pass: dsnt_mask_count + dsnt_head_step (forward and dL/dZ while the heatmap is in shared '

@@ -133,6 +133,13 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
                                g_reg, g_loss, denom, reg_coeff, reg, sigma, flags, variant, stream);
 }
 
+static PeerXchg no_peers() {
+  PeerXchg xc;
+  for (int r = 0; r < kMaxRanks; ++r) xc.peers[r] = nullptr;
+  xc.epoch = nullptr; xc.error = nullptr; xc.rank = 0; xc.world = 1;
+  return xc;
+}
+
 DSNT_API int dsnt_finish_workspace_bytes(void) { return static_cast<int>(sizeof(float) * kFinishWorkspaceFloats); }
 
 DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
@@ -145,8 +152,56 @@ DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, lon
   if (ctas < 1) ctas = 1;
   if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
   finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      terms, mask, n, n_per_stack > 0 ? n_per_stack : 1, reg_coeff, out, workspace);
+      terms, mask, n, n_per_stack > 0 ? n_per_stack : 1, reg_coeff, out, workspace, no_peers());
   return check_launch("finish_loss_kernel");
+}
+
+DSNT_API int dsnt_peer_exchange_bytes(void) { return static_cast<int>(sizeof(float4) * 2 * kMaxRanks); }
+
+static int make_peers(const void* const* peers, int rank, int world, unsigned* epoch, int* error, PeerXchg& xc) {
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !peers || !epoch || !error) {
+    set_error("peer exchange: bad arguments (world %d, rank %d, at most %d ranks)", world, rank, kMaxRanks);
+    return DSNT_ERR_BAD_ARG;
+  }
+  xc = no_peers();
+  for (int r = 0; r < world; ++r) {
+    if (!peers[r] || !aligned(peers[r], 16)) { set_error("peer exchange: buffer of rank %d is null or misaligned", r); return DSNT_ERR_BAD_ARG; }
+    xc.peers[r] = static_cast<float4*>(const_cast<void*>(peers[r]));
+  }
+  xc.epoch = epoch; xc.error = error; xc.rank = rank; xc.world = world;
+  return DSNT_OK;
+}
+
+DSNT_API int dsnt_finish_loss_peer(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
+                                   float* out, float* workspace, const void* const* peers, int rank, int world,
+                                   unsigned* epoch, int* error, void* stream) {
+  if (n_stacks < 1 || n_per_stack < 0) { set_error("dsnt_finish_loss_peer: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  const long n = n_per_stack * n_stacks;
+  if ((!terms && n > 0) || !out || !workspace) { set_error("dsnt_finish_loss_peer: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (!aligned(terms, 8) || !aligned(workspace, 16)) { set_error("dsnt_finish_loss_peer: misaligned buffers"); return DSNT_ERR_BAD_ARG; }
+  PeerXchg xc;
+  const int rc = make_peers(peers, rank, world, epoch, error, xc);
+  if (rc) return rc;
+  long ctas = (n + 1023) / 1024;
+  if (ctas < 1) ctas = 1;       // an empty shard still takes part in the exchange
+  if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
+  finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      terms, mask, n, n_per_stack > 0 ? n_per_stack : 1, reg_coeff, out, workspace, xc);
+  return check_launch("finish_loss_kernel<peer>");
+}
+
+DSNT_API int dsnt_mask_count_peer(const float* mask, long n, float* out, float* workspace, const void* const* peers,
+                                  int rank, int world, unsigned* epoch, int* error, void* stream) {
+  if (n < 0 || !out || !workspace || !aligned(workspace, 16)) { set_error("dsnt_mask_count_peer: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  PeerXchg xc;
+  const int rc = make_peers(peers, rank, world, epoch, error, xc);
+  if (rc) return rc;
+  long ctas = (n + 4095) / 4096;
+  if (ctas < 1) ctas = 1;
+  if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
+  finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      nullptr, mask, n, n > 0 ? n : 1, 0.f, out, workspace, xc);
+  return check_launch("finish_loss_kernel<count, peer>");
 }
 
 DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, float reg_coeff, float* out, float* workspace,
@@ -161,7 +216,7 @@ DSNT_API int dsnt_mask_count(const float* mask, long n, float* out, float* works
   if (ctas < 1) ctas = 1;
   if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
   finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, mask, n, n > 0 ? n : 1, 0.f, out, workspace);
+      nullptr, mask, n, n > 0 ? n : 1, 0.f, out, workspace, no_peers());
   return check_launch("finish_loss_kernel<count>");
 }
 

@@ -22,6 +22,7 @@ import collections
 import torch
 
 from . import _lib
+from .parallel import PeerExchange
 
 HeadOutput = collections.namedtuple('HeadOutput', ['coords', 'loss', 'euclid', 'reg'])
 
@@ -58,6 +59,31 @@ def all_reduce_sums(out8, group):
         dist.all_reduce(out8[0:3], op=dist.ReduceOp.SUM, group=group)
 
 
+def finish_loss(terms, mask, n_per_stack, n_stacks, reg_coeff, out8, ws, group, dev, stream):
+    """masked_average + loss composition over the per-heatmap terms; with a sharded batch the partial sums of the ranks
+    are exchanged inside the kernel over peer memory (one node) or all-reduced by NCCL.  terms=None: mask count only."""
+    peer = PeerExchange.get(group, dev)
+    if peer is not None:
+        if terms is None:
+            _lib.call('dsnt_mask_count_peer', _lib.ptr(mask), n_per_stack, out8.data_ptr(), ws.data_ptr(), *peer.args(),
+                      stream)
+        else:
+            _lib.call('dsnt_finish_loss_peer', terms.data_ptr(), _lib.ptr(mask), n_per_stack, n_stacks, reg_coeff,
+                      out8.data_ptr(), ws.data_ptr(), *peer.args(), stream)
+        return
+    if terms is None:
+        _lib.call('dsnt_mask_count', _lib.ptr(mask), n_per_stack, out8.data_ptr(), ws.data_ptr(), stream)
+    elif n_stacks == 1:
+        _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n_per_stack, reg_coeff, out8.data_ptr(),
+                  ws.data_ptr(), stream)
+    else:
+        _lib.call('dsnt_finish_loss_stacked', terms.data_ptr(), _lib.ptr(mask), n_per_stack, n_stacks, reg_coeff,
+                  out8.data_ptr(), ws.data_ptr(), stream)
+    if group is not None:
+        all_reduce_sums(out8, group)
+        _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+
+
 class _FusedHead(torch.autograd.Function):
     """forward: dsnt_head_fwd + dsnt_finish_loss;  backward: dsnt_head_bwd (include/dsnt_b200.h)."""
 
@@ -75,11 +101,7 @@ class _FusedHead(torch.autograd.Function):
                       _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(),
                       variant, stream)
             ws = _lib.finish_workspace(dev)
-            _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, reg_coeff, out8.data_ptr(),
-                      ws.data_ptr(), stream)
-            if group is not None:
-                all_reduce_sums(out8, group)
-                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+            finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(zc, target, mask, stats, out8)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, variant, input_is_logits, z.shape)
         ctx.set_materialize_grads(False)
@@ -125,11 +147,7 @@ class _FusedHeadPreact(torch.autograd.Function):
                       _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), variant,
                       stream)
             ws = _lib.finish_workspace(dev)
-            _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, reg_coeff, out8.data_ptr(),
-                      ws.data_ptr(), stream)
-            if group is not None:
-                all_reduce_sums(out8, group)
-                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+            finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(zc, target, mask, stats, out8)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, variant, z.shape)
         ctx.set_materialize_grads(False)
@@ -253,18 +271,11 @@ class _FusedHeadStep(torch.autograd.Function):
             dz = torch.empty_like(zc)
             ws = _lib.finish_workspace(dev)
             # the denominator of masked_average depends on the mask alone: known before the forward
-            _lib.call('dsnt_mask_count', _lib.ptr(mask), n, cnt8.data_ptr(), ws.data_ptr(), stream)
-            if group is not None:
-                all_reduce_sums(cnt8, group)
-                _lib.call('dsnt_combine_loss', cnt8.data_ptr(), reg_coeff, stream)
+            finish_loss(None, mask, n, 1, reg_coeff, cnt8, ws, group, dev, stream)
             _lib.call('dsnt_head_step', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
                       cnt8[3:4].data_ptr(), None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(),
                       terms.data_ptr(), dz.data_ptr(), stream)
-            _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, reg_coeff, out8.data_ptr(),
-                      ws.data_ptr(), stream)
-            if group is not None:
-                all_reduce_sums(out8, group)
-                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+            finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(zc, target, mask, stats, out8, dz)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, z.shape)
         ctx.set_materialize_grads(False)
@@ -317,11 +328,7 @@ class _FusedHeadStacked(torch.autograd.Function):
                       _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(),
                       variant, stream)
             ws = _lib.finish_workspace(dev)
-            _lib.call('dsnt_finish_loss_stacked', terms.data_ptr(), _lib.ptr(mask), n, s_count, reg_coeff,
-                      out8.data_ptr(), ws.data_ptr(), stream)
-            if group is not None:
-                all_reduce_sums(out8, group)
-                _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+            finish_loss(terms, mask, n, s_count, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(target, mask, stats, out8, *zcs)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, variant, [z.shape for z in zs])
         ctx.set_materialize_grads(False)

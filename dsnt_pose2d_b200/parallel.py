@@ -1,9 +1,12 @@
 """Batch sharding of the head across ranks.
 
 Every heatmap is independent; ranks own contiguous slices of the batch dimension and the only exchange
-is the 3-float all-reduce inside `dsnt_head(..., group=...)`.  One process per GPU, NCCL over NVLink.
+is that of three partial sums inside `dsnt_head(..., group=...)`.  One process per GPU.  On one node the sums
+travel through peer-mapped memory from inside the finishing kernel (`PeerExchange`, include/dsnt_b200.h:
+dsnt_finish_loss_peer); otherwise, or with DSNT_PEER_EXCHANGE=0, through a 3-float NCCL all-reduce.
 """
 
+import ctypes
 import os
 
 import torch
@@ -40,3 +43,66 @@ def init_from_env(backend=None):
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, local, world
+
+
+class PeerExchange:
+    """Exchange buffers of one process group on one node for the fused finishing reductions.
+
+    Every rank allocates a small symmetric-memory buffer that all ranks map (torch.distributed._symmetric_memory:
+    CUDA VMM handles shared between the processes, P2P over NVLink); the kernels then write their partial sums into
+    every rank's buffer and read the others' from their own -- no collective launch, CUDA-graph capturable.
+    `PeerExchange.get(group, device)` returns None where that is not possible (single rank, no symmetric memory,
+    DSNT_PEER_EXCHANGE=0); the caller then all-reduces with NCCL."""
+
+    _cache = {}
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 16:
+            raise RuntimeError('peer exchange serves at most 16 ranks')
+        nfloats = _lib.LIB.dsnt_peer_exchange_bytes() // 4
+        buf = symm.empty(nfloats, dtype=torch.float32, device=device)
+        buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(buf, group)
+        self.buf = buf
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+            raise RuntimeError('symmetric memory returned %r peer pointers for %d ranks' % (ptrs, self.world))
+        self.peers = (ctypes.c_void_p * self.world)(*ptrs)
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)     # [epoch, error]
+        torch.cuda.synchronize(device)
+        dist.barrier(group)            # every buffer is zero before anybody's first exchange can land in it
+
+    def args(self):
+        """(peers, rank, world, epoch*, error*) as the *_peer entry points take them."""
+        return (ctypes.cast(self.peers, ctypes.c_void_p), self.rank, self.world, self.state[0:1].data_ptr(),
+                self.state[1:2].data_ptr())
+
+    def check(self):
+        """Host read of the error flag (a peer that never arrived); not called on the hot path."""
+        if int(self.state[1].item()) != 0:
+            raise RuntimeError('peer exchange timed out: a rank of the group did not take part')
+
+    @classmethod
+    def get(cls, group, device):
+        import torch.distributed as dist
+        if group is None or not dist.is_available() or not dist.is_initialized():
+            return None
+        if os.environ.get('DSNT_PEER_EXCHANGE', '1') == '0' or dist.get_world_size(group) < 2:
+            return None
+        if dist.get_backend(group) != 'nccl' or torch.device(device).type != 'cuda':
+            return None
+        key = (id(group), torch.device(device).index)
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(group, torch.device(device))
+            except Exception as e:          # noqa: BLE001  (no symmetric memory on this system: NCCL all-reduce instead)
+                import warnings
+                warnings.warn('dsnt_pose2d_b200: peer exchange unavailable (%s); using NCCL all-reduce' % (e,))
+                cls._cache[key] = None
+        return cls._cache[key]

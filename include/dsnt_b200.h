@@ -53,6 +53,7 @@ extern "C" {
 
 /* per-heatmap statistics saved by the forward for the reduction-free backward */
 #define DSNT_MAX_STACKS 16 /* stacks (hourglass outputs) one *_stacked call can cover */
+#define DSNT_MAX_RANKS 16         /* ranks of one node that exchange partial sums through peer memory */
 
 #define DSNT_STATS_K 8
 /*   logits input : [0] m*log2(e)  [1] 1/S   [2] mu_x [3] mu_y [4] v_x [5] v_y [6] c_reg = sum P r [7] Gaussian normaliser 1/(sum G^ + 1e-24)
@@ -207,6 +208,25 @@ DSNT_API int dsnt_flip_tta_fwd(const void* z, int dtype, long batch, int C, int 
 DSNT_API int dsnt_finish_workspace_bytes(void);
 DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, float reg_coeff, float* out,
                      float* workspace, void* stream);
+
+/*
+ * Sharded batch (one process per GPU of a node): the same reductions with the exchange of the partial sums between
+ * the ranks fused into the kernel -- no NCCL launch, no separate combine.  The last CTA stores (out[0], out[1], out[2])
+ * into every rank's exchange buffer over NVLink peer mappings, waits for all ranks' slots in its own buffer and adds
+ * them in rank order, so every rank finishes with the same out[0..7] as one process on the whole batch would.
+ *   replaces: nothing in the reference (single GPU, src/dsnt/bin/train.py:220); it is what makes masked_average
+ *             (src/dsnt/nn.py:81-94) mean "over the global batch" when the batch dimension is sharded.
+ *   peers     HOST array of `world` DEVICE pointers; peers[r] is rank r's exchange buffer as mapped into this process
+ *             (dsnt_peer_exchange_bytes() bytes each, symmetric memory), zeroed once before first use
+ *   epoch     local DEVICE unsigned counter, zeroed once;  error: local DEVICE int, set if a peer never arrived (20 s)
+ *   All ranks must issue the same sequence of *_peer calls on the same group (as with any collective).
+ */
+DSNT_API int dsnt_peer_exchange_bytes(void);
+DSNT_API int dsnt_finish_loss_peer(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
+                                   float* out, float* workspace, const void* const* peers, int rank, int world,
+                                   unsigned* epoch, int* error, void* stream);
+DSNT_API int dsnt_mask_count_peer(const float* mask, long n, float* out, float* workspace, const void* const* peers,
+                                  int rank, int world, unsigned* epoch, int* error, void* stream);
 
 /* Recompute out[3..6] from (possibly all-reduced) out[0..2]; used after the NCCL all-reduce of the sums. */
 DSNT_API int dsnt_combine_loss(float* out, float reg_coeff, void* stream);

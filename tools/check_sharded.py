@@ -46,6 +46,14 @@ def main():
                 grads = [bufs[r][:shard(z, r, world).shape[0]] for r in range(world)]
             else:
                 grads = [zs.grad]
+            if world > 1:
+                # every rank must hold the SAME loss (the totals are added in rank order on every rank)
+                losses = [torch.empty_like(out.loss) for _ in range(world)]
+                dist.all_gather(losses, out.loss.detach())
+                same = all(torch.equal(losses[0], x) for x in losses)
+                ok &= same
+                if rank == 0 and not same:
+                    print('loss differs between ranks: %r' % ([x.item() for x in losses],), flush=True)
             if rank == 0:
                 zf = z.to(dev).requires_grad_(True)
                 full = dp.dsnt_head(zf, target.to(dev), mask.to(dev), reg=reg, one_pass=False)
@@ -58,6 +66,13 @@ def main():
                 print('world %d one_pass %-5s reg %-3s loss rel.err %.1e dz rel.L2 %.1e %s' % (
                     world, one_pass, reg, e_loss, e_dz, 'ok' if good else 'MISMATCH'), flush=True)
     if world > 1:
+        from dsnt_pose2d_b200.parallel import PeerExchange
+        peer = PeerExchange.get(dist.group.WORLD, dev)
+        if peer is not None:
+            peer.check()
+        if rank == 0:
+            print('exchange of the partial sums: %s' % ('peer memory, fused into the finishing kernels' if peer is not None
+                                                         else 'NCCL all-reduce'), flush=True)
         dist.barrier()
     if rank == 0:
         print('check_sharded: %s' % ('PASS' if ok else 'FAIL'), flush=True)
