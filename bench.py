@@ -345,8 +345,9 @@ def main_ours(args):
 
     # ---------------- pass 2 (same steps, still inside the clock-sampled window): CUDA events around every launch of
     # our kernels, on the stream they are enqueued on, for the per-kernel roofline
-    _lib.event_log = {'dsnt_head_fwd': [], 'dsnt_head_bwd': [], 'dsnt_head_step': [], 'dsnt_finish_loss': [],
-                      'dsnt_mask_count': [], 'dsnt_scale_unless_one': []}
+    _lib.event_log = {'dsnt_head_fwd': [], 'dsnt_head_bwd': [], 'dsnt_head_step': [], 'dsnt_head_step_fused': [],
+                      'dsnt_finish_loss': [], 'dsnt_mask_count': [], 'dsnt_scale_unless_one': [],
+                      'dsnt_finish_loss_peer': [], 'dsnt_mask_count_peer': []}
     for _ in range(args.steps):
         step()
     barrier()
@@ -407,17 +408,21 @@ def main_ours(args):
     hw = h * w
     alg = {'dsnt_head_fwd': n_local * (hw * esize + 56),        # read Z; target 8 r, coords 8 w, stats 32 w, terms 8 w
            'dsnt_head_bwd': n_local * (2 * hw * esize + 44),    # read Z, write dZ; stats 32 r, target 8 r, mask 4 r
-           'dsnt_head_step': n_local * (2 * hw * esize + 68)}   # read Z, write dZ; target 8 r, mask 4 r, coords/stats/terms 56 w
+           'dsnt_head_step': n_local * (2 * hw * esize + 68),   # read Z, write dZ; target 8 r, mask 4 r, coords/stats/terms 56 w
+           'dsnt_head_step_fused': n_local * (2 * hw * esize + 60)}   # the same without the terms (8 w); the mask again from L2
     ran = [k for k in alg if kernel_ms.get(k)]
     dominant = max(ran, key=lambda k: kernel_ms[k])
     per_kernel = {}
     for k in ran:
         ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
         per_kernel[k] = {'ms': kernel_ms[k], 'algorithmic_bytes': alg[k], 'achieved_gbs': ach, 'frac': ach / peak}
-    small = {k: kernel_ms[k] for k in ('dsnt_finish_loss', 'dsnt_mask_count', 'dsnt_scale_unless_one') if kernel_ms.get(k)}
+    small = {k: kernel_ms[k] for k in ('dsnt_finish_loss', 'dsnt_mask_count', 'dsnt_scale_unless_one',
+                                       'dsnt_finish_loss_peer', 'dsnt_mask_count_peer') if kernel_ms.get(k)}
     step_bytes = sum(alg[k] for k in ran)
     step_gbs = step_bytes * world / (elapsed_ms / args.steps * 1e-3) / 1e9
     traffic = committed_traffic(args.workload)
+    if isinstance(traffic, dict) and 'dsnt_head_step_fused' not in traffic and 'dsnt_head_step' in traffic:
+        traffic['dsnt_head_step_fused'] = traffic['dsnt_head_step']      # the same kernel (head_step2_kernel)
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': per_kernel[dominant]['achieved_gbs'], 'peak': peak,
                 'unit': 'GB/s', 'frac': per_kernel[dominant]['frac'],
                 'traffic': (traffic or {}).get(dominant) if isinstance(traffic, dict) else None,
@@ -440,9 +445,11 @@ def main_ours(args):
                        world, exchange_note)) if world > 1 else 'single GPU (batch shard = whole batch)',
                    'l2_policy': 'inputs larger than L2 (%.0f MiB of logits per step vs 126 MB L2)'
                                 % (n_local * hw * esize / 2 ** 20),
-                   'path': ('one-pass: dsnt_mask_count + dsnt_head_step (forward and dL/dZ while the heatmap is in shared '
-                            'memory, 2*H*W*sizeof algorithmic bytes) + dsnt_finish_loss; backward only scales in place '
-                            'when d(loss) != 1') if one_pass else
+                   'path': ('one-pass: %s (forward and dL/dZ while the heatmap is in shared memory, 2*H*W*sizeof '
+                            'algorithmic bytes); backward only scales in place when d(loss) != 1' % (
+                                'dsnt_head_step_fused, ONE launch: mask count, step and loss composition'
+                                if kernel_ms.get('dsnt_head_step_fused') else
+                                'dsnt_mask_count + dsnt_head_step + dsnt_finish_loss')) if one_pass else
                            'two-kernel: dsnt_head_fwd + dsnt_finish_loss + dsnt_head_bwd (3*H*W*sizeof algorithmic bytes)',
                    'launch': graph_note},
         'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks, 'e2e': e2e,

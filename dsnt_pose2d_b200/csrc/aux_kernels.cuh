@@ -5,6 +5,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "finish_common.cuh"
 
 namespace dsnt {
 
@@ -21,11 +22,8 @@ __device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& 
 // Two-level reduction in ONE launch: every CTA sums a contiguous slice of the per-heatmap terms in a fixed
 // order and parks its partial in the workspace; the CTA that draws the last ticket adds the partials in
 // index order.  No float atomics, fixed traversal => bit-reproducible for a given (N, grid).
-// workspace: kFinishMaxCtas*4 floats of partials followed by one unsigned ticket counter that must be zero
+// workspace: kFinishSlots*4 floats of partials followed by one unsigned ticket counter that must be zero
 // before the first launch and is reset by the kernel itself (stream-ordered use only).
-constexpr int kFinishBlock = 256;
-constexpr int kFinishMaxCtas = 128;
-constexpr int kFinishWorkspaceFloats = kFinishMaxCtas * 4 + 4;
 
 // ------------------------------------------------------------------------------------------------
 // Exchange of the three partial sums between the ranks of one node, INSIDE the finishing kernel (no NCCL launch):
@@ -85,12 +83,6 @@ __device__ __forceinline__ void peer_exchange_sum3(const PeerXchg& x, float& a, 
   if (lane == 0) *x.epoch = e;
 }
 
-__device__ __forceinline__ void write_loss_tail(float* out, float reg_coeff) {
-  const float cnt = out[2];
-  const float den = fmaxf(cnt, 1.0f);
-  const float eu = out[0] / den, rg = out[1] / den;
-  out[3] = den; out[4] = eu; out[5] = rg; out[6] = fmaf(reg_coeff, rg, eu); out[7] = 0.f;
-}
 
 // Stacked form: terms holds n = count*n_per rows (stack-major); the mask (one stack long) is shared, the mask
 // count -- the denominator of every per-stack average -- is taken over the first stack only, so
@@ -113,7 +105,7 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
     if (i < n_per) sm += w;
   }
   block_sum4<kFinishBlock>(sd, sr, sm, unused, red);
-  unsigned* ticket = reinterpret_cast<unsigned*>(workspace + kFinishMaxCtas * 4);
+  unsigned* ticket = reinterpret_cast<unsigned*>(workspace + kFinishSlots * 4);
   if (threadIdx.x == 0) {
     float4* part = reinterpret_cast<float4*>(workspace);
     part[blockIdx.x] = make_float4(sd, sr, sm, 0.f);

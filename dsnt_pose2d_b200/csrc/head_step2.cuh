@@ -30,6 +30,7 @@
 // with it.  KL keeps the generic kernel (its window, 28x28 at sigma = 1 px, does not fit the register budget).
 #pragma once
 
+#include "finish_common.cuh"
 #include "f32x2.cuh"
 #include "head_step.cuh"
 
@@ -151,6 +152,11 @@ __device__ __noinline__ void ring_issue(const char* src, uint32_t hm_bytes, uint
   __threadfence_block();
   *flag = value;
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 // reserve the next slot; returns the clock at which the load may be issued (<= now: at once)
 __device__ __forceinline__ unsigned long long pace_reserve(unsigned long long* slot, int pace, unsigned long long now) {
   unsigned long long mine = atomicAdd(slot, static_cast<unsigned long long>(pace));
@@ -197,6 +203,9 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   __shared__ volatile int issued[kStepMaxBufs];   // see head_step.cuh: loads issued into each buffer so far
   __shared__ unsigned long long pace_next;        // clock at which the CTA may issue its next bulk load (p.pace)
   __shared__ PendingLoad pend_all[NWMAX];
+  __shared__ float fin[NWMAX][2];                  // single-launch form: per-warp sums of mask * (distance, divergence)
+  __shared__ float mask_total;
+  __shared__ bool fin_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= p.nwarps) return;
@@ -222,10 +231,57 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
       issued[t] = 1;
     }
   }
+  // Single-launch form: no dsnt_mask_count before this kernel.  Every CTA adds up ITS slice of the mask, parks the partial in
+  // the workspace and meets the others at a grid barrier (the grid is one CTA per SM, all co-resident); then every CTA adds
+  // the partials in index order, so all hold the same denominator.  Three global round trips, hidden behind the first
+  // bulk loads, which are already in flight.  (All CTAs reading the whole mask instead -- 148 x 256 KiB out of the same
+  // L2 lines -- delayed the start of the kernel by ~20 us.)
+  float mask_count = 0.f;
+  if (!p.denom && p.mask) {
+    const long chunk = (p.n + gridDim.x - 1) / gridDim.x;
+    const long lo = blockIdx.x * chunk, hi = lo + chunk < p.n ? lo + chunk : p.n;
+    float sm = 0.f;
+    for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) sm += __ldg(p.mask + i);
+    sm = warp_sum(sm);
+    if (lane == 0) fin[warp][0] = sm;
+  }
   __syncthreads();
+  if (!p.denom) {
+    if (p.mask) {
+      unsigned* bar = reinterpret_cast<unsigned*>(p.ws + kFinishSlots * 4) + 1;
+      float* mpart = p.ws + kFinishSlots * 4 + 4;
+      if (warp == 0) {
+        if (lane == 0) {
+          float tot = 0.f;
+          for (int w2 = 0; w2 < p.nwarps; ++w2) tot += fin[w2][0];
+          mpart[blockIdx.x] = tot;
+          __threadfence();
+          atomicAdd(bar, 1u);
+          while (ld_acquire_gpu(bar) < gridDim.x) __nanosleep(64);
+        }
+        __syncwarp();
+        float v[kFinishSlots / 32];
+#pragma unroll
+        for (int k = 0; k < kFinishSlots / 32; ++k) {
+          const int i = lane + 32 * k;
+          v[k] = i < static_cast<int>(gridDim.x) ? __ldcg(mpart + i) : 0.f;
+        }
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < kFinishSlots / 32; ++k) tot += v[k];
+        tot = warp_sum(tot);
+        if (lane == 0) mask_total = tot;
+      }
+      __syncthreads();
+      mask_count = mask_total;
+    } else {
+      mask_count = static_cast<float>(p.n);
+    }
+  }
   if (p.stagger_ns > 0) __nanosleep(static_cast<unsigned>(warp * p.stagger_ns + (blockIdx.x & 3) * (p.stagger_ns >> 2)));
   const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
-  const float inv_denom = 1.0f / __ldg(p.denom);
+  const float inv_denom = 1.0f / (p.denom ? __ldg(p.denom) : fmaxf(mask_count, 1.0f));
+  float acc_d = 0.f, acc_r = 0.f;       // this warp's sums of mask * distance, mask * divergence (single-launch form)
   const float s2 = p.sigma * p.sigma;
 
   // lane geometry: vector column cv (pixels cv*VEC ...), rows r0, r0 + RPI, ...
@@ -279,7 +335,8 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     uint4* dzv = reinterpret_cast<uint4*>(dzdst + hm * hm_bytes);
 
     const float tx = tgt_next.x, ty = tgt_next.y;
-    const float wgt = msk_next * inv_denom;
+    const float mraw = msk_next;
+    const float wgt = mraw * inv_denom;
     if (t + NW < nt32) {
       const long hmn = (t + NW) * hm_mul + hm_add;
       if (p.target) tgt_next = __ldg(reinterpret_cast<const float2*>(p.target) + hmn);
@@ -531,6 +588,8 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
       }
       if (p.terms) reinterpret_cast<float2*>(p.terms)[hm] = make_float2(dist, D);
     }
+    acc_d = fmaf(mraw, dist, acc_d);
+    acc_r = fmaf(mraw, D, acc_r);
     const float cc = fmaf(a, mux, fmaf(b, muy, rho * creg));
     float cbase = -cc;
     if (kJS) cbase = fmaf(0.5f * kLn2, rho, cbase);
@@ -631,6 +690,44 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     __syncwarp();
   }
   flush_pending(true);
+
+  // ---------------------------------------------------------------- single-launch form: masked_average + loss composition
+  // (src/dsnt/nn.py:81-94, src/dsnt/model.py:145) as in finish_loss_kernel: warp order inside the CTA, the CTA with the last
+  // ticket adds the CTAs' partials in index order -- no float atomics, bit-reproducible for a given grid.
+  if (p.out8) {
+    if (lane == 0) { fin[warp][0] = acc_d; fin[warp][1] = acc_r; }
+    __syncthreads();
+    unsigned* ticket = reinterpret_cast<unsigned*>(p.ws + kFinishSlots * 4);
+    if (threadIdx.x == 0) {
+      float sd = 0.f, sr = 0.f;
+      for (int w2 = 0; w2 < p.nwarps; ++w2) { sd += fin[w2][0]; sr += fin[w2][1]; }
+      reinterpret_cast<float4*>(p.ws)[blockIdx.x] = make_float4(sd, sr, 0.f, 0.f);
+      __threadfence();
+      fin_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (fin_last && warp == 0) {
+      __threadfence();
+      const float4* part = reinterpret_cast<const float4*>(p.ws);
+      float4 v[kFinishSlots / 32];
+#pragma unroll
+      for (int k = 0; k < kFinishSlots / 32; ++k) {
+        const int i = lane + 32 * k;
+        v[k] = i < static_cast<int>(gridDim.x) ? __ldcg(part + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int k = 0; k < kFinishSlots / 32; ++k) { sa += v[k].x; sb += v[k].y; }
+      sa = warp_sum(sa); sb = warp_sum(sb);
+      if (lane == 0) {
+        p.out8[0] = sa; p.out8[1] = sb;
+        p.out8[2] = p.denom ? __ldg(p.denom) : mask_count;   // with an external denominator out8[2..3] repeat it
+        write_loss_tail(p.out8, p.reg_coeff);
+        ticket[0] = 0u;
+        ticket[1] = 0u;      // the mask barrier: every CTA passed it long ago
+      }
+    }
+  }
 }
 
 }  // namespace dsnt

@@ -131,15 +131,25 @@ static int launch_step_one(HeadStepParams p, cudaStream_t stream) {
   return check_launch("head_step_kernel");
 }
 
+// does this launch take the shape-specialised kernel (head_step2.cuh)?
+static bool step2_eligible(int dtype, int H, int W, int reg, float sigma) {
+  if (reg == DSNT_REG_KL || H != 64 || W != 64 || !step_v2() || !step_direct_store() || step_group() == 64) return false;
+  const int vec = dtype == DSNT_DTYPE_F32 ? 4 : 8;
+  const Geom g = make_geom(H, W, vec, 32, sigma > 0.f ? sigma : 1.f, reg);
+  return dtype == DSNT_DTYPE_F32 ? step2_window_fits<float>(H, W, vec, reg, g.r2_win)
+                                 : step2_window_fits<__nv_bfloat16>(H, W, vec, reg, g.r2_win);
+}
+
 // one warp per heatmap by default (DSNT_TUNE_STEP_GROUP=64 selects two)
 template <typename T, int VEC, int REG>
 static int launch_step_fixc(HeadStepParams p, cudaStream_t stream) {
   if constexpr (REG != DSNT_REG_KL) {
-    if (p.H == 64 && p.W == 64 && step_v2() && p.direct_store && step_group() != 64) {
+    if (step2_eligible(sizeof(T) == 4 ? DSNT_DTYPE_F32 : DSNT_DTYPE_BF16, p.H, p.W, REG, p.sigma)) {
       p.g = make_geom(p.H, p.W, VEC, 32, p.sigma > 0.f ? p.sigma : 1.f, REG);
-      if (step2_window_fits<T>(p.H, p.W, VEC, REG, p.g.r2_win)) return launch_step2<T, REG, 64, 64>(p, stream);
+      return launch_step2<T, REG, 64, 64>(p, stream);
     }
   }
+  if (p.out8 || !p.denom) { set_error("single-launch step: this shape / regulariser takes the generic kernel"); return DSNT_ERR_UNSUPPORTED; }
   if (step_group() != 64) {
     p.g = make_geom(p.H, p.W, VEC, 32, p.sigma > 0.f ? p.sigma : 1.f, REG);
     return (32 % p.g.wv == 0) ? launch_step_one<T, VEC, REG, true, 32>(p, stream) : launch_step_one<T, VEC, REG, false, 32>(p, stream);
@@ -177,13 +187,13 @@ DSNT_API int dsnt_head_step_supported(int dtype, int H, int W) {
   return kStepSmemBudget / buf >= 4 ? 1 : 0;
 }
 
-DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
-                            const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
-                            float* coords, float* stats, float* terms, void* dz, void* stream) {
+static int head_step_impl(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                          const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
+                          float* coords, float* stats, float* terms, void* dz, float* out8, float* ws, void* stream) {
   int rc = check_common(z, dtype, n, H, W, reg);
   if (rc) return rc;
   if (n == 0) return DSNT_OK;
-  if (!dz || !coords || !denom) { set_error("dsnt_head_step: z, dz, coords and denom are required"); return DSNT_ERR_BAD_ARG; }
+  if (!dz || !coords || (!denom && !out8)) { set_error("dsnt_head_step: z, dz, coords and denom are required"); return DSNT_ERR_BAD_ARG; }
   if (reg_needs_gauss(reg) && !target) { set_error("reg %d needs a target", reg); return DSNT_ERR_BAD_ARG; }
   if (reg != DSNT_REG_NONE && !(sigma > 0.f)) { set_error("sigma must be > 0"); return DSNT_ERR_BAD_ARG; }
   if (!aligned(coords, 8) || (stats && !aligned(stats, 16)) || (terms && !aligned(terms, 8)) || (target && !aligned(target, 8))) {
@@ -211,8 +221,37 @@ DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, cons
   static const int debug = env_int("DSNT_TUNE_STEP_DEBUG", 0);
   p.debug = debug;
   p.pace = 0;   // set per kernel in launch_step2_nw
+  p.out8 = out8; p.ws = ws;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dtype == DSNT_DTYPE_F32 ? launch_step_reg<float, 4>(p, reg, s) : launch_step_reg<__nv_bfloat16, 8>(p, reg, s);
+}
+
+DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                            const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
+                            float* coords, float* stats, float* terms, void* dz, void* stream) {
+  if (!denom && n != 0) { set_error("dsnt_head_step: denom is required (dsnt_mask_count)"); return DSNT_ERR_BAD_ARG; }
+  return head_step_impl(z, dtype, n, H, W, target, mask, denom, g_loss, reg_coeff, reg, sigma, flags, coords, stats, terms, dz,
+                        nullptr, nullptr, stream);
+}
+
+DSNT_API int dsnt_head_step_fused_supported(int dtype, int H, int W, int reg, float sigma) {
+  return dsnt_head_step_supported(dtype, H, W) && step2_eligible(dtype, H, W, reg, sigma) ? 1 : 0;
+}
+
+DSNT_API int dsnt_head_step_fused(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                                  const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords,
+                                  float* stats, void* dz, float* out, float* workspace, void* stream) {
+  if (!out || !workspace || !aligned(workspace, 16)) { set_error("dsnt_head_step_fused: out and a 16-byte aligned workspace are required"); return DSNT_ERR_BAD_ARG; }
+  if (n == 0) {     // empty batch: the loss block of an empty reduction
+    return dsnt_finish_loss(nullptr, mask, 0, reg_coeff, out, workspace, stream);
+  }
+  if (!dsnt_head_step_fused_supported(dtype, H, W, reg, sigma)) {
+    set_error("dsnt_head_step_fused: %dx%d, dtype %d, reg %d is not served by the single-launch kernel; use dsnt_mask_count + "
+              "dsnt_head_step + dsnt_finish_loss", H, W, dtype, reg);
+    return DSNT_ERR_UNSUPPORTED;
+  }
+  return head_step_impl(z, dtype, n, H, W, target, mask, nullptr, g_loss, reg_coeff, reg, sigma, flags, coords, stats, nullptr, dz,
+                        out, workspace, stream);
 }
 
 }  // extern "C"

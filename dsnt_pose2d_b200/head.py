@@ -270,12 +270,19 @@ class _FusedHeadStep(torch.autograd.Function):
             out8 = torch.empty(8, dtype=torch.float32, device=dev)
             dz = torch.empty_like(zc)
             ws = _lib.finish_workspace(dev)
-            # the denominator of masked_average depends on the mask alone: known before the forward
-            finish_loss(None, mask, n, 1, reg_coeff, cnt8, ws, group, dev, stream)
-            _lib.call('dsnt_head_step', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
-                      cnt8[3:4].data_ptr(), None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(),
-                      terms.data_ptr(), dz.data_ptr(), stream)
-            finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
+            sharded = group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+            if not sharded and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zc), h, w, reg_id, sigma):
+                # one launch: the kernel adds up the mask itself and its last CTA composes the loss
+                _lib.call('dsnt_head_step_fused', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
+                          None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(), dz.data_ptr(),
+                          out8.data_ptr(), ws.data_ptr(), stream)
+            else:
+                # the denominator of masked_average depends on the mask alone: known before the forward
+                finish_loss(None, mask, n, 1, reg_coeff, cnt8, ws, group, dev, stream)
+                _lib.call('dsnt_head_step', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
+                          cnt8[3:4].data_ptr(), None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(),
+                          terms.data_ptr(), dz.data_ptr(), stream)
+                finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(zc, target, mask, stats, out8, dz)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, z.shape)
         ctx.set_materialize_grads(False)

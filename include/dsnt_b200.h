@@ -129,6 +129,18 @@ DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, cons
                             const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
                             float* coords, float* stats, float* terms, void* dz, void* stream);
 DSNT_API int dsnt_mask_count(const float* mask, long n, float* out, float* workspace, void* stream);
+/*
+ * The same step in ONE launch (single process; csrc/head_step2.cuh): every CTA adds up the mask itself while its first
+ * bulk loads are in flight (no dsnt_mask_count), and the CTA that finishes last composes the loss (no dsnt_finish_loss):
+ * out[0..7] exactly as dsnt_finish_loss documents, workspace likewise.  Served for the shapes / regularisers of the
+ * shape-specialised kernel (dsnt_head_step_fused_supported: 64x64, not KL, Gaussian window within its register slots);
+ * otherwise DSNT_ERR_UNSUPPORTED and the caller uses the three-launch form.  A sharded batch uses the three-launch form
+ * with the *_peer reductions (the denominator then needs the other ranks' masks before the step can start).
+ */
+DSNT_API int dsnt_head_step_fused_supported(int dtype, int H, int W, int reg, float sigma);
+DSNT_API int dsnt_head_step_fused(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                                  const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords,
+                                  float* stats, void* dz, float* out, float* workspace, void* stream);
 /* x[0..numel) *= *g, skipped entirely (no traffic) when *g == 1: applies an upstream d(loss) != 1 to the gradient
  * dsnt_head_step already wrote, without a host read of *g. */
 DSNT_API int dsnt_scale_unless_one(void* x, int dtype, long numel, const float* g, void* stream);

@@ -284,3 +284,50 @@ def test_step64_many_heatmaps_per_cta_and_peaked_logits(dp, tp):
     idx = torch.randperm(n, generator=gen)[:24]
     ref = tp.head_loss_and_grad(z[idx], target[idx], None, 'js', 1.0, 1.0, dtype=torch.float64)
     assert rel_l2(got['dz'][idx.numpy()] * (n / 24.0), ref['dz'].numpy()) < TOL
+
+
+@pytest.mark.parametrize('reg', ['js', 'var', 'none', 'mse'])
+@pytest.mark.parametrize('with_mask', [True, False])
+def test_step64_single_launch_form_matches_the_three_launch_form(dp, reg, with_mask):
+    """dsnt_head_step_fused (mask count and loss composition inside the step kernel) against dsnt_mask_count +
+    dsnt_head_step + dsnt_finish_loss through the C ABI: identical coordinates and gradient, the same loss block up to
+    the order of the additions, bit-reproducible from call to call."""
+    from dsnt_pose2d_b200 import _lib
+    gen = torch.Generator().manual_seed(71)
+    n, h, w = 1000, 64, 64
+    z = torch.randn(n, h, w, generator=gen).to(DEV)
+    target = (torch.rand(n, 2, generator=gen) * 1.6 - 0.8).to(DEV)
+    mask = (torch.rand(n, generator=gen) > 0.2).float().to(DEV) if with_mask else None
+    rid, sigma = _lib.REG_IDS[reg], 2.0 / w
+    assert _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, rid, sigma) == 1
+    assert _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, _lib.REG_IDS['kl'], sigma) == 0
+    assert _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), 32, 32, rid, sigma) == 0
+    stream = torch.cuda.current_stream().cuda_stream
+    ws = _lib.finish_workspace(torch.device(DEV))
+
+    def three():
+        coords, stats, terms = (torch.empty(n, 2, device=DEV), torch.empty(n, 8, device=DEV), torch.empty(n, 2, device=DEV))
+        cnt8, out8, dz = torch.empty(8, device=DEV), torch.empty(8, device=DEV), torch.empty_like(z)
+        _lib.call('dsnt_mask_count', _lib.ptr(mask), n, cnt8.data_ptr(), ws.data_ptr(), stream)
+        _lib.call('dsnt_head_step', z.data_ptr(), 0, n, h, w, target.data_ptr(), _lib.ptr(mask), cnt8[3:4].data_ptr(), None,
+                  0.7, rid, sigma, 0, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), dz.data_ptr(), stream)
+        _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n, 0.7, out8.data_ptr(), ws.data_ptr(), stream)
+        return coords, stats, dz, out8
+
+    def fused():
+        coords, stats = torch.empty(n, 2, device=DEV), torch.empty(n, 8, device=DEV)
+        out8, dz = torch.empty(8, device=DEV), torch.empty_like(z)
+        _lib.call('dsnt_head_step_fused', z.data_ptr(), 0, n, h, w, target.data_ptr(), _lib.ptr(mask), None, 0.7, rid, sigma, 0,
+                  coords.data_ptr(), stats.data_ptr(), dz.data_ptr(), out8.data_ptr(), ws.data_ptr(), stream)
+        return coords, stats, dz, out8
+
+    a, b, c = three(), fused(), fused()
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.equal(b[3], c[3]) and torch.equal(b[2], c[2])
+    assert torch.equal(a[3][2:4], b[3][2:4])                                  # count and denominator: exact
+    assert torch.allclose(a[3], b[3], rtol=2e-6, atol=1e-7), (a[3], b[3])
+    with pytest.raises(RuntimeError):
+        _lib.call('dsnt_head_step_fused', z.data_ptr(), 0, n, h, w, target.data_ptr(), _lib.ptr(mask), None, 0.7,
+                  _lib.REG_IDS['kl'], sigma, 0, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
+                  ws.data_ptr(), stream)

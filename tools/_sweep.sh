@@ -1,6 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_step.py tests/test_gpu_model.py tests/test_gpu_parity.py -q > gpurun_out/v8_pytest.log 2>&1; tail -3 gpurun_out/v8_pytest.log
-K="timeout 200 python tools/kbench.py --configs cfg4 --step-only"
-echo "== default"; $K --regs none,var,js,mse --dtypes f32,bf16 2>&1 | grep one-pass
-echo "== bf16 js/mse PACED=1"; DSNT_TUNE_STEP_PACED=1 $K --regs js,mse --dtypes bf16 2>&1 | grep one-pass
-timeout 400 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/v8_bench.json 2> gpurun_out/v8_bench.err; cat gpurun_out/v8_bench.json
+timeout 600 python -m pytest tests/test_gpu_step.py tests/test_gpu_model.py -q > gpurun_out/v10_pytest_gpu.log 2>&1; tail -3 gpurun_out/v10_pytest_gpu.log
+timeout 400 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/v10_bench.json 2> gpurun_out/v10_bench.err; cut -c1-1900 gpurun_out/v10_bench.json; tail -3 gpurun_out/v10_bench.err
