@@ -49,6 +49,8 @@ SIGNATURES = {
     'dsnt_head_step': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int,
                                 _c_float, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_mask_count': (_c_int, [_c_ptr, _c_long, _c_ptr, _c_ptr, _c_ptr]),
+    'dsnt_head_step_fused_stacked': (_c_int, [_c_ptr, _c_ptr, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr,
+                                              _c_float, _c_int, _c_float, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_head_step_fused_supported': (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_float]),
     'dsnt_head_step_fused': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int,
                                       _c_float, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),

@@ -45,6 +45,8 @@ struct HeadStepParams {
   int nwarps;            // groups (of GROUP/32 warps) per CTA
   int nbufs;             // shared-memory buffers per CTA, >= nwarps: a ring shared by the groups
   int direct_store;      // 1: dz goes to global memory with 128-bit stores straight from registers; 0: in place + bulk store
+  Stacks st;             // head_step2: stacked hourglass (count > 1): n = count * n_per heatmaps, stack s at z + st.z_off[s];
+                         //   target / mask are one stack long (indexed inside the stack), coords / stats by heatmap
   float* out8;           // head_step2, single-launch form (dsnt_head_step_fused): the loss block of dsnt_finish_loss, or null
   float* ws;             //   its workspace (dsnt_finish_workspace_bytes); denom may then be null = computed from the mask here
   int debug;             // head_step2 (DSNT_TUNE_STEP_DEBUG, measurements only): 1 = copy z -> dz with LDS + STG and no

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
       mbar_init(bar, 1);
       if (t < ntiles) {
         mbar_expect_tx(bar, hm_bytes);
-        bulk_load(smem0_s + static_cast<uint32_t>(t) * p.buf_bytes, zsrc + (t * hm_mul + hm_add) * hm_bytes,
+        bulk_load(smem0_s + static_cast<uint32_t>(t) * p.buf_bytes, zsrc + locate(p.st, t * hm_mul + hm_add, hm_bytes).z_bytes,
                   hm_bytes, bar);
       }
       issued[t] = 1;
@@ -238,8 +238,9 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   // L2 lines -- delayed the start of the kernel by ~20 us.)
   float mask_count = 0.f;
   if (!p.denom && p.mask) {
-    const long chunk = (p.n + gridDim.x - 1) / gridDim.x;
-    const long lo = blockIdx.x * chunk, hi = lo + chunk < p.n ? lo + chunk : p.n;
+    const long nmask = p.st.count > 1 ? p.st.n_per : p.n;       // the stacks share one mask
+    const long chunk = (nmask + gridDim.x - 1) / gridDim.x;
+    const long lo = blockIdx.x * chunk, hi = lo + chunk < nmask ? lo + chunk : nmask;
     float sm = 0.f;
     for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) sm += __ldg(p.mask + i);
     sm = warp_sum(sm);
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
       __syncthreads();
       mask_count = mask_total;
     } else {
-      mask_count = static_cast<float>(p.n);
+      mask_count = static_cast<float>(p.st.count > 1 ? p.st.n_per : p.n);
     }
   }
   if (p.stagger_ns > 0) __nanosleep(static_cast<unsigned>(warp * p.stagger_ns + (blockIdx.x & 3) * (p.stagger_ns >> 2)));
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   if (lane == 0) pend.tile = -1;
   __syncwarp();
   auto issue_load = [&](long tile, uint32_t b, uint32_t rnd) {
-    ring_issue(zsrc + (tile * hm_mul + hm_add) * hm_bytes, hm_bytes, bars0_s + 8 * b, smem0_s + b * static_cast<uint32_t>(p.buf_bytes),
+    ring_issue(zsrc + locate(p.st, tile * hm_mul + hm_add, hm_bytes).z_bytes, hm_bytes, bars0_s + 8 * b, smem0_s + b * static_cast<uint32_t>(p.buf_bytes),
                &issued[b], static_cast<int>(rnd) + 2);
   };
   // lane 0: the pending load goes if its time has come (force: wait for it)
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   float2 tgt_next = make_float2(0.f, 0.f);
   float msk_next = 1.0f;
   if (warp < nt32) {
-    const long hm0 = warp * hm_mul + hm_add;
+    const long hm0 = locate(p.st, warp * hm_mul + hm_add, hm_bytes).nl;
     if (p.target) tgt_next = __ldg(reinterpret_cast<const float2*>(p.target) + hm0);
     if (p.mask) msk_next = __ldg(p.mask + hm0);
   }
@@ -332,13 +333,13 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     const uint4* bufv = reinterpret_cast<const uint4*>(buf);
     const uint4* bv = bufv + lane;           // sweep step it reads bv[32 * it]
     uint4* bst = reinterpret_cast<uint4*>(buf) + lane;   // the stash goes where the vector came from
-    uint4* dzv = reinterpret_cast<uint4*>(dzdst + hm * hm_bytes);
+    uint4* dzv = reinterpret_cast<uint4*>(dzdst + locate(p.st, hm, hm_bytes).dz_bytes);
 
     const float tx = tgt_next.x, ty = tgt_next.y;
     const float mraw = msk_next;
     const float wgt = mraw * inv_denom;
     if (t + NW < nt32) {
-      const long hmn = (t + NW) * hm_mul + hm_add;
+      const long hmn = locate(p.st, (t + NW) * hm_mul + hm_add, hm_bytes).nl;
       if (p.target) tgt_next = __ldg(reinterpret_cast<const float2*>(p.target) + hmn);
       if (p.mask) msk_next = __ldg(p.mask + hmn);
     }
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
           pend.when = static_cast<uint32_t>(when); pend.tile = static_cast<int>(nt); pend.slot = bi | (round << 8);
         } else {
           mbar_expect_tx(bar_s, hm_bytes);
-          bulk_load(buf_s, zsrc + (nt * hm_mul + hm_add) * hm_bytes, hm_bytes, bar_s);
+          bulk_load(buf_s, zsrc + locate(p.st, nt * hm_mul + hm_add, hm_bytes).z_bytes, hm_bytes, bar_s);
           __threadfence_block();
           issued[bi] = static_cast<int>(round) + 2;
         }

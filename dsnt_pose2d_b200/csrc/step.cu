@@ -189,7 +189,8 @@ DSNT_API int dsnt_head_step_supported(int dtype, int H, int W) {
 
 static int head_step_impl(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
                           const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
-                          float* coords, float* stats, float* terms, void* dz, float* out8, float* ws, void* stream) {
+                          float* coords, float* stats, float* terms, void* dz, float* out8, float* ws, void* stream,
+                          const Stacks* st = nullptr) {
   int rc = check_common(z, dtype, n, H, W, reg);
   if (rc) return rc;
   if (n == 0) return DSNT_OK;
@@ -222,6 +223,12 @@ static int head_step_impl(const void* z, int dtype, long n, int H, int W, const 
   p.debug = debug;
   p.pace = 0;   // set per kernel in launch_step2_nw
   p.out8 = out8; p.ws = ws;
+  if (st) {
+    p.st = *st;
+  } else {
+    p.st.count = 1; p.st.n_per = n;
+    for (int k = 0; k < kMaxStacks; ++k) { p.st.z_off[k] = 0; p.st.dz_off[k] = 0; }
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dtype == DSNT_DTYPE_F32 ? launch_step_reg<float, 4>(p, reg, s) : launch_step_reg<__nv_bfloat16, 8>(p, reg, s);
 }
@@ -252,6 +259,31 @@ DSNT_API int dsnt_head_step_fused(const void* z, int dtype, long n, int H, int W
   }
   return head_step_impl(z, dtype, n, H, W, target, mask, nullptr, g_loss, reg_coeff, reg, sigma, flags, coords, stats, nullptr, dz,
                         out, workspace, stream);
+}
+
+DSNT_API int dsnt_head_step_fused_stacked(const void* const* z, void* const* dz, int n_stacks, int dtype, long n_per_stack,
+                                          int H, int W, const float* target, const float* mask, const float* g_loss,
+                                          float reg_coeff, int reg, float sigma, int flags, float* coords, float* stats,
+                                          float* out, float* workspace, void* stream) {
+  if (!out || !workspace || !aligned(workspace, 16)) { set_error("dsnt_head_step_fused_stacked: out and a 16-byte aligned workspace are required"); return DSNT_ERR_BAD_ARG; }
+  if (n_stacks < 1 || n_stacks > kMaxStacks || n_per_stack < 0 || !z || !dz) { set_error("dsnt_head_step_fused_stacked: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (n_per_stack == 0) return dsnt_finish_loss(nullptr, mask, 0, reg_coeff, out, workspace, stream);
+  if (!dsnt_head_step_fused_supported(dtype, H, W, reg, sigma)) {
+    set_error("dsnt_head_step_fused_stacked: %dx%d, dtype %d, reg %d is not served by the single-launch kernel; use the "
+              "dsnt_head_fwd_stacked / dsnt_head_bwd_stacked form", H, W, dtype, reg);
+    return DSNT_ERR_UNSUPPORTED;
+  }
+  Stacks st;
+  st.count = n_stacks; st.n_per = n_per_stack;
+  for (int k = 0; k < kMaxStacks; ++k) { st.z_off[k] = 0; st.dz_off[k] = 0; }
+  for (int k = 0; k < n_stacks; ++k) {
+    if (!z[k] || !dz[k] || !aligned(z[k], 16) || !aligned(dz[k], 16)) { set_error("stack %d: null or misaligned heatmap pointer", k); return DSNT_ERR_BAD_ARG; }
+    st.z_off[k] = static_cast<const char*>(z[k]) - static_cast<const char*>(z[0]);
+    st.dz_off[k] = static_cast<char*>(dz[k]) - static_cast<char*>(dz[0]);
+  }
+  if (n_per_stack * n_stacks > 0x7fffffffL) { set_error("too many heatmaps for one stacked launch"); return DSNT_ERR_BAD_ARG; }
+  return head_step_impl(z[0], dtype, n_per_stack * n_stacks, H, W, target, mask, nullptr, g_loss, reg_coeff, reg, sigma, flags,
+                        coords, stats, nullptr, dz[0], out, workspace, stream, &st);
 }
 
 }  // extern "C"

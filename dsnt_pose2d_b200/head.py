@@ -50,6 +50,11 @@ def _as_f32(t, n, last, what):
     return t
 
 
+def _is_sharded(group):
+    import torch.distributed as dist
+    return group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
 def all_reduce_sums(out8, group):
     """Sum the three partial sums out8[0:3] over the ranks of `group` (no-op for a single rank)."""
     import torch.distributed as dist
@@ -226,7 +231,8 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     if preact not in _lib.PREACT_IDS:
         raise Exception('unrecognised heatmap preactivation function: {}'.format(preact))   # model.py:42-43
     if (one_pass and preact == 'softmax' and threshold is None and eps is None and input_is_logits
-            and z.requires_grad and torch.is_grad_enabled() and step_supported(z)):
+            and z.requires_grad and torch.is_grad_enabled() and step_supported(z)
+            and _step_pays(z, h, w, _lib.REG_IDS[reg], float(sigma), group)):
         coords, loss = _FusedHeadStep.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
                                             flags, group, aux)
     elif preact == 'softmax' and threshold is None and eps is None:
@@ -242,6 +248,15 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
                                               float(d_eps if eps is None else eps), int(variant), aux)
     out8 = aux['out8']
     return HeadOutput(coords, loss, out8[4], out8[5])
+
+
+def _step_pays(z, h, w, reg_id, sigma, group):
+    """The one-pass step saves a read of the logits.  Where the single-launch form serves the case it also saves launches;
+    where it does not (other shapes, KL, sharded batch) it takes one launch MORE than the two-kernel path, which only pays
+    once the logits no longer sit in L2 (small batches are bound by launches, tools/stepbench.py)."""
+    if not _is_sharded(group) and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, reg_id, sigma):
+        return True
+    return z.numel() * z.element_size() > (32 << 20)
 
 
 def step_supported(z):
@@ -270,7 +285,7 @@ class _FusedHeadStep(torch.autograd.Function):
             out8 = torch.empty(8, dtype=torch.float32, device=dev)
             dz = torch.empty_like(zc)
             ws = _lib.finish_workspace(dev)
-            sharded = group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+            sharded = _is_sharded(group)
             if not sharded and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zc), h, w, reg_id, sigma):
                 # one launch: the kernel adds up the mask itself and its last CTA composes the loss
                 _lib.call('dsnt_head_step_fused', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
@@ -370,11 +385,71 @@ class _FusedHeadStacked(torch.autograd.Function):
         return (None,) * 9 + tuple(dz.view(shape) for dz, shape in zip(dzs, shapes))
 
 
+class _FusedHeadStackedStep(torch.autograd.Function):
+    """All hourglass stacks in ONE launch that is forward and backward at once (dsnt_head_step_fused_stacked,
+    include/dsnt_b200.h): coordinates, the summed loss and dL/dz of every stack, each heatmap read once.  The backward hands
+    the stored gradients out (one contiguous buffer for all stacks, scaled in place when d(loss) != 1); gradients w.r.t.
+    the coordinates go through dsnt_head_bwd_stacked on the saved statistics."""
+
+    @staticmethod
+    def forward(ctx, target, mask, reg_id, sigma, reg_coeff, flags, aux, *zs):
+        flat = [_flat_heatmaps(z) for z in zs]
+        zcs = [f[0] for f in flat]
+        n, h, w = flat[0][1], flat[0][2], flat[0][3]
+        s_count = len(zcs)
+        dev = zcs[0].device
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zcs[0])
+            coords = torch.empty(s_count, n, 2, dtype=torch.float32, device=dev)
+            stats = torch.empty(s_count * n, _lib.STATS_K, dtype=torch.float32, device=dev)
+            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            dz = torch.empty((s_count,) + tuple(zcs[0].shape), dtype=zcs[0].dtype, device=dev)
+            ws = _lib.finish_workspace(dev)
+            _lib.call('dsnt_head_step_fused_stacked', _lib.ptr_array(zcs), _lib.ptr_array([dz[i] for i in range(s_count)]),
+                      s_count, _lib.dtype_id(zcs[0]), n, h, w, _lib.ptr(target), _lib.ptr(mask), None, reg_coeff, reg_id,
+                      sigma, flags, coords.data_ptr(), stats.data_ptr(), out8.data_ptr(), ws.data_ptr(), stream)
+        ctx.save_for_backward(target, mask, stats, out8, dz, *zcs)
+        ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, [z.shape for z in zs])
+        ctx.set_materialize_grads(False)
+        aux['out8'] = out8
+        lead = zs[0].shape[:-2]
+        return (out8[6],) + tuple(coords[i].view(*lead, 2) for i in range(s_count))
+
+    @staticmethod
+    def backward(ctx, g_loss, *g_coords):
+        target, mask, stats, out8, dz = ctx.saved_tensors[:5]
+        zcs = ctx.saved_tensors[5:]
+        n, h, w, reg_id, sigma, reg_coeff, flags, shapes = ctx.meta
+        s_count = len(zcs)
+        dev = zcs[0].device
+        if g_loss is None and all(g is None for g in g_coords):
+            return (None,) * (7 + s_count)
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(zcs[0])
+            if g_loss is not None:
+                g_loss = g_loss.to(torch.float32).contiguous()
+            if all(g is None for g in g_coords):
+                _lib.call('dsnt_scale_unless_one', dz.data_ptr(), _lib.dtype_id(dz), dz.numel(), g_loss.data_ptr(), stream)
+                return (None,) * 7 + tuple(dz[i].view(shape) for i, shape in enumerate(shapes))
+            gc = torch.zeros(s_count, n, 2, dtype=torch.float32, device=dev)
+            for i, g in enumerate(g_coords):
+                if g is not None:
+                    gc[i] = g.reshape(n, 2).to(torch.float32)
+            dzs = [torch.empty_like(z) for z in zcs]
+            _lib.call('dsnt_head_bwd_stacked', _lib.ptr_array(zcs), _lib.ptr_array(dzs), s_count,
+                      _lib.dtype_id(zcs[0]), 1, n, h, w, _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(),
+                      gc.data_ptr(), None, _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
+                      reg_coeff, reg_id, sigma, flags, 0, stream)
+        return (None,) * 7 + tuple(d.view(shape) for d, shape in zip(dzs, shapes))
+
+
 def dsnt_head_stacked(zs, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_sigma=None, group=None,
-                      variant=0):
+                      variant=0, one_pass=False):
     """Hourglass form (src/dsnt/model.py:233-246,286-292): every stack's head evaluated by one launch, losses summed.
 
     zs: list of logits tensors [..., H, W] of identical shape/dtype (one per stack, as hourglass.py:166-177 returns).
+    one_pass: a training step (only d(loss) flows back): one launch writes every stack's dL/dz while its heatmaps are on
+    chip (64x64 heatmaps, not KL, single process; other cases take the forward / backward launches as before).
     Returns (list of coords per stack, total loss = sum_s euclid_s + reg_coeff * reg_s)."""
     zs = list(zs)
     if not zs:
@@ -397,6 +472,11 @@ def dsnt_head_stacked(zs, target, mask=None, reg='none', sigma=None, reg_coeff=1
     mask = _as_f32(mask, n, 1, 'mask')
     flags = _lib.FLAG_STRICT_NAN if STRICT_NAN else 0
     aux = {}
-    out = _FusedHeadStacked.apply(target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff), flags, group,
-                                  int(variant), aux, *zs)
+    sharded = _is_sharded(group)
+    if (one_pass and not sharded and target is not None and n > 0
+            and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zs[0]), h, w, _lib.REG_IDS[reg], float(sigma))):
+        out = _FusedHeadStackedStep.apply(target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff), flags, aux, *zs)
+    else:
+        out = _FusedHeadStacked.apply(target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff), flags, group,
+                                      int(variant), aux, *zs)
     return list(out[1:]), out[0]

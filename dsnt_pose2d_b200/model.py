@@ -129,7 +129,7 @@ class DSNTHead(nn.Module):
                     and all(o is c for o, c in zip(out_var, self._coords))):
                 # one fused forward over all stacks, one finishing reduction; backward is one launch too
                 return dsnt_head_stacked(self._logits, target_var, mask_var, reg=self.reg, hm_sigma=self.hm_sigma,
-                                         reg_coeff=self.reg_coeff, group=self.group)[1]
+                                         reg_coeff=self.reg_coeff, group=self.group, one_pass=self.one_pass)[1]
             total = 0
             for i, out in enumerate(out_var):          # sum over stacks (model.py:238-246)
                 total = total + self._loss_one(i, out, target_var, mask_var)

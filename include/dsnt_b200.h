@@ -162,6 +162,12 @@ DSNT_API int dsnt_head_bwd_stacked(const void* const* z, void* const* dz, int n_
                                    const float* stats, const float* g_coords, const float* g_reg, const float* g_loss,
                                    const float* denom, float reg_coeff, int reg, float sigma, int flags, int variant,
                                    void* stream);
+/* The single-launch step (dsnt_head_step_fused) over all stacks: dz[s] receives d(sum_s euclid_s + reg_coeff*reg_s)/dz_s,
+ * out[] as dsnt_finish_loss_stacked.  Same support rule as dsnt_head_step_fused_supported. */
+DSNT_API int dsnt_head_step_fused_stacked(const void* const* z, void* const* dz, int n_stacks, int dtype, long n_per_stack,
+                                          int H, int W, const float* target, const float* mask, const float* g_loss,
+                                          float reg_coeff, int reg, float sigma, int flags, float* coords, float* stats,
+                                          float* out, float* workspace, void* stream);
 DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, long n_per_stack, int n_stacks,
                                       float reg_coeff, float* out, float* workspace, void* stream);
 

@@ -331,3 +331,40 @@ def test_step64_single_launch_form_matches_the_three_launch_form(dp, reg, with_m
         _lib.call('dsnt_head_step_fused', z.data_ptr(), 0, n, h, w, target.data_ptr(), _lib.ptr(mask), None, 0.7,
                   _lib.REG_IDS['kl'], sigma, 0, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
                   ws.data_ptr(), stream)
+
+
+@pytest.mark.parametrize('reg', ['js', 'var'])
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+def test_stacked_single_launch_step_matches_stacked_two_kernel_path_and_oracle(dp, tp, reg, dtype):
+    """Hourglass form (src/dsnt/model.py:233-246): dsnt_head_stacked(one_pass=True) -- ONE launch for all stacks, forward
+    and backward -- against the stacked forward/backward launches and the fp64 oracle."""
+    gen = torch.Generator().manual_seed(81)
+    stacks, b, c, h, w = 4, 6, 16, 64, 64
+    tdt = torch.float32 if dtype == 'f32' else torch.bfloat16
+    zs = [(torch.randn(b, c, h, w, generator=gen) * (1.0 + s)).to(tdt) for s in range(stacks)]
+    target = torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8
+    mask = (torch.rand(b, c, generator=gen) > 0.2).float()
+
+    def run(one_pass):
+        zz = [z.clone().to(DEV).requires_grad_(True) for z in zs]
+        coords, total = dp.dsnt_head_stacked(zz, target.to(DEV), mask.to(DEV), reg=reg, hm_sigma=1.0, reg_coeff=0.7,
+                                             one_pass=one_pass)
+        (total * 1.5).backward()
+        torch.cuda.synchronize()
+        return [cc.detach().cpu().double() for cc in coords], total.item(), [z.grad.cpu().double() for z in zz]
+
+    ca, la, ga = run(True)
+    cb, lb, gb = run(False)
+    dz_tol = 4e-3 if dtype == 'bf16' else 3e-6
+    assert abs(la - lb) < 3e-6 * abs(lb)
+    for s in range(stacks):
+        assert float((ca[s] - cb[s]).abs().max()) < 2e-6
+        assert rel_l2(ga[s].numpy(), gb[s].numpy()) < dz_tol
+    total, coords = tp.head_loss_stacked([z.double() for z in zs], target.double(), mask.double(), reg, 1.0, 0.7)
+    assert abs(la - total.item()) < TOL * abs(total.item())
+    z64 = [z.double().requires_grad_(True) for z in zs]
+    t64, _ = tp.head_loss_stacked(z64, target.double(), mask.double(), reg, 1.0, 0.7)
+    (t64 * 1.5).backward()
+    for s in range(stacks):
+        assert float((ca[s] - coords[s]).abs().max()) < TOL
+        assert rel_l2(ga[s].numpy(), z64[s].grad.numpy()) < (4e-3 if dtype == 'bf16' else TOL)

@@ -59,7 +59,7 @@ def main():
     torch.manual_seed(0)
     cases = [('cfg1 32x16x64x64', 1, 32, 16, 64, 64), ('cfg2 64x16x28x28', 1, 64, 16, 28, 28),
              ('cfg3 8 stacks 32x16x64x64', 8, 32, 16, 64, 64)]
-    print('%-28s %-22s %10s %10s %9s %12s' % ('config', 'path', 'eager us', 'graph us', 'launches', 'Mhm/s graph'))
+    print('%-28s %-30s %10s %10s %9s %12s' % ('config', 'path', 'eager us', 'graph us', 'launches', 'Mhm/s graph'))
     for name, stacks, b, c, h, w in cases:
         zs = [torch.randn(b, c, h, w, device=dev, requires_grad=True) for _ in range(stacks)]
         target = torch.rand(b, c, 2, device=dev) * 1.6 - 0.8
@@ -70,8 +70,23 @@ def main():
                 z.grad = None
             total = None
             for z in zs:
-                out = dp.dsnt_head(z, target, mask, reg=args.reg, hm_sigma=1.0)
+                out = dp.dsnt_head(z, target, mask, reg=args.reg, hm_sigma=1.0, one_pass=False)
                 total = out.loss if total is None else total + out.loss
+            total.backward()
+
+        def per_stack_step():
+            for z in zs:
+                z.grad = None
+            total = None
+            for z in zs:
+                out = dp.dsnt_head(z, target, mask, reg=args.reg, hm_sigma=1.0, one_pass=True)
+                total = out.loss if total is None else total + out.loss
+            total.backward()
+
+        def one_launch_step():
+            for z in zs:
+                z.grad = None
+            _, total = dp.dsnt_head_stacked(zs, target, mask, reg=args.reg, hm_sigma=1.0, one_pass=True)
             total.backward()
 
         def one_launch():
@@ -80,7 +95,9 @@ def main():
             _, total = dp.dsnt_head_stacked(zs, target, mask, reg=args.reg, hm_sigma=1.0)
             total.backward()
 
-        paths = [('per-stack calls', per_stack)] + ([('one stacked launch', one_launch)] if stacks > 1 else [])
+        paths = [('two-kernel, per stack', per_stack), ('single-launch step, per stack', per_stack_step)]
+        if stacks > 1:
+            paths += [('two-kernel, stacked launches', one_launch), ('single-launch step, stacked', one_launch_step)]
         for pname, fn in paths:
             before = _lib.launch_count
             fn()
@@ -88,7 +105,7 @@ def main():
             eager = timed(fn, args.iters)
             replay = graphed(fn)
             graph = timed(replay, args.iters)
-            print('%-28s %-22s %10.1f %10.1f %9d %12.1f' % (name, pname, eager, graph, launches,
+            print('%-28s %-30s %10.1f %10.1f %9d %12.1f' % (name, pname, eager, graph, launches,
                                                            stacks * b * c / graph))
 
 
