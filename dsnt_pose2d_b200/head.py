@@ -250,13 +250,16 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     return HeadOutput(coords, loss, out8[4], out8[5])
 
 
+STEP_MIN_BYTES = 32 << 20     # logits smaller than this take the one-pass step only in its single-launch form
+
+
 def _step_pays(z, h, w, reg_id, sigma, group):
     """The one-pass step saves a read of the logits.  Where the single-launch form serves the case it also saves launches;
     where it does not (other shapes, KL, sharded batch) it takes one launch MORE than the two-kernel path, which only pays
     once the logits no longer sit in L2 (small batches are bound by launches, tools/stepbench.py)."""
     if not _is_sharded(group) and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, reg_id, sigma):
         return True
-    return z.numel() * z.element_size() > (32 << 20)
+    return z.numel() * z.element_size() >= STEP_MIN_BYTES
 
 
 def step_supported(z):

@@ -27,6 +27,15 @@ def tp():
     return torch_port
 
 
+@pytest.fixture(autouse=True)
+def always_take_the_step_kernels(dp):
+    """These tests are about the step kernels: small logits must not be routed to the two-kernel path (head._step_pays)."""
+    from dsnt_pose2d_b200 import head
+    old, head.STEP_MIN_BYTES = head.STEP_MIN_BYTES, 0
+    yield
+    head.STEP_MIN_BYTES = old
+
+
 def run_step(dp, z, target, mask, reg, hm_sigma=1.0, coeff=1.0, g=None, one_pass=True):
     from dsnt_pose2d_b200 import _lib
     zz = z.detach().clone().to(DEV).requires_grad_(True)
