@@ -281,7 +281,7 @@ def main_ours(args):
 
     from dsnt_pose2d_b200.head import step_supported
     from dsnt_pose2d_b200.parallel import PeerExchange
-    one_pass = args.path == 'one-pass' and step_supported(z)
+    one_pass = args.path == 'one-pass' and step_supported(z, reg)
     exchange_note = ('inside the finishing kernels over NVLink peer memory (no collective launch)'
                      if PeerExchange.get(group, dev) is not None else 'by a 3-float NCCL all-reduce')
 

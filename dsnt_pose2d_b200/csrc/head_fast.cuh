@@ -138,8 +138,10 @@ __device__ __forceinline__ StashWin make_stash_window(const Window& w) {
 // (batch + b, perm[c]) of the same tensor; REG must be NONE then (no target at inference).
 // PA != SOFTMAX: P = f(z)/(sum f + eps) for the reference's other pre-activations.  P may be exactly 0 and sum P may
 // differ from 1 (eps), which the closed forms below carry as sumP / om; stats[7] holds om = 1 - sum P for `var`.
+// The body takes the index of the "block" of heatmaps it works on, so that a persistent kernel can call it in a loop
+// (head_step_l2.cuh); head_fwd_fast_kernel passes blockIdx.x.
 template <typename T, int VEC, int GROUP, int REG, bool FLIP = false, int PA = DSNT_PREACT_SOFTMAX>
-__global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_kernel(const HeadFwdFastParams ps) {
+__device__ __forceinline__ void head_fwd_fast_body(const HeadFwdFastParams& ps, long block_index) {
   static_assert(sizeof(T) * VEC == 16, "fast path = 16-byte vectors");
   static_assert(!FLIP || REG == DSNT_REG_NONE, "flip test-time augmentation is forward-only, no regulariser");
   constexpr bool kSM = preact_is_softmax(PA);       // needs the running maximum
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
   const FastGeom& fg = ps.f;
   const int tid = threadIdx.x;
   const int gid = tid / GROUP, lane_g = tid % GROUP, warp_g = lane_g >> 5, lane = tid & 31;
-  const long hm = static_cast<long>(blockIdx.x) * GPB + gid;
+  const long hm = block_index * GPB + gid;
   if (hm >= p.n) return;  // GROUP == 32 only; the grid is exact otherwise
 
   const int H = p.H, W = p.W;
@@ -464,6 +466,11 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_k
   if (lane_g == 0) write_outputs(p, hm, m2, invS, mux, muy, vx, vy, creg, ginv, tx, ty, D);
 }
 
+template <typename T, int VEC, int GROUP, int REG, bool FLIP = false, int PA = DSNT_PREACT_SOFTMAX>
+__global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_fwd_fast_kernel(const HeadFwdFastParams ps) {
+  head_fwd_fast_body<T, VEC, GROUP, REG, FLIP, PA>(ps, blockIdx.x);
+}
+
 // ================================================================================================ backward
 struct HeadBwdFastParams {
   HeadBwdParams base;
@@ -481,7 +488,7 @@ template <>
 __device__ __forceinline__ void st_scalar<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 template <typename T, int VEC, int GROUP, int REG>
-__global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_fast_kernel(const HeadBwdFastParams ps) {
+__device__ __forceinline__ void head_bwd_fast_body(const HeadBwdFastParams& ps, long block_index) {
   static_assert(sizeof(T) * VEC == 16, "fast path = 16-byte vectors");
   constexpr int BLOCK = stream_block_threads<GROUP>();
   constexpr int GPB = BLOCK / GROUP;
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_fast_k
   const FastGeom& fg = ps.f;
   const int tid = threadIdx.x;
   const int gid = tid / GROUP, lane_g = tid % GROUP, warp_g = lane_g >> 5, lane = tid & 31;
-  const long hm = static_cast<long>(blockIdx.x) * GPB + gid;
+  const long hm = block_index * GPB + gid;
   if (hm >= p.n) return;  // GROUP == 32 only
 
   const int H = p.H, W = p.W;
@@ -662,6 +669,11 @@ __global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_fast_k
       }
     }
   }
+}
+
+template <typename T, int VEC, int GROUP, int REG>
+__global__ void __launch_bounds__(stream_block_threads<GROUP>()) head_bwd_fast_kernel(const HeadBwdFastParams ps) {
+  head_bwd_fast_body<T, VEC, GROUP, REG>(ps, blockIdx.x);
 }
 
 }  // namespace dsnt

@@ -231,7 +231,7 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     if preact not in _lib.PREACT_IDS:
         raise Exception('unrecognised heatmap preactivation function: {}'.format(preact))   # model.py:42-43
     if (one_pass and preact == 'softmax' and threshold is None and eps is None and input_is_logits
-            and z.requires_grad and torch.is_grad_enabled() and step_supported(z)
+            and z.requires_grad and torch.is_grad_enabled() and step_supported(z, reg)
             and _step_pays(z, h, w, _lib.REG_IDS[reg], float(sigma), group)):
         coords, loss = _FusedHeadStep.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
                                             flags, group, aux)
@@ -250,6 +250,9 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     return HeadOutput(coords, loss, out8[4], out8[5])
 
 
+USE_L2_STEP = False           # heatmaps too large for shared memory: take the L2-staged one-pass step (csrc/step_l2.cu)?
+                              # Measured on B200 at BASELINE config 5 it does not beat the two-kernel path yet (996 vs 970 us:
+                              # two resident CTAs per SM keep the logits in L2 but too few bytes in flight), so it is off.
 STEP_MIN_BYTES = 32 << 20     # logits smaller than this take the one-pass step only in its single-launch form
 
 
@@ -262,11 +265,15 @@ def _step_pays(z, h, w, reg_id, sigma, group):
     return z.numel() * z.element_size() >= STEP_MIN_BYTES
 
 
-def step_supported(z):
-    """True when `dsnt_head_step` (one pass over the logits) can take heatmaps of this dtype and size."""
+def step_supported(z, reg=None):
+    """True when `dsnt_head_step` (one pass over the logits) can take heatmaps of this dtype and size: at least four of
+    them fit in shared memory, or -- for larger ones, given the regulariser -- the L2-staged form serves the case."""
     if z.dtype not in (torch.float32, torch.bfloat16) or z.dim() < 2 or z.numel() == 0:
         return False
-    return bool(_lib.LIB.dsnt_head_step_supported(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1])))
+    if reg is None or not USE_L2_STEP:
+        return bool(_lib.LIB.dsnt_head_step_supported(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1])))
+    return bool(_lib.LIB.dsnt_head_step_supported_reg(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1]),
+                                                      _lib.REG_IDS[reg]))
 
 
 class _FusedHeadStep(torch.autograd.Function):

@@ -32,8 +32,10 @@ def always_take_the_step_kernels(dp):
     """These tests are about the step kernels: small logits must not be routed to the two-kernel path (head._step_pays)."""
     from dsnt_pose2d_b200 import head
     old, head.STEP_MIN_BYTES = head.STEP_MIN_BYTES, 0
+    old_l2, head.USE_L2_STEP = head.USE_L2_STEP, True
     yield
     head.STEP_MIN_BYTES = old
+    head.USE_L2_STEP = old_l2
 
 
 def run_step(dp, z, target, mask, reg, hm_sigma=1.0, coeff=1.0, g=None, one_pass=True):
@@ -70,7 +72,10 @@ def test_step_is_taken_only_where_supported(dp):
     assert head.step_supported(torch.empty(1, 1, 64, 64, device=DEV))
     assert head.step_supported(torch.empty(1, 1, 28, 28, device=DEV))
     assert head.step_supported(torch.empty(1, 1, 128, 128, device=DEV, dtype=torch.bfloat16))
-    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV))     # 256 KiB: two-kernel path
+    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV))     # 256 KiB: not in shared memory ...
+    assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'var')  # ... but staged through L2 (step_l2.cu)
+    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'js')    # fp32 + Gaussian window: two-kernel
+    assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV, dtype=torch.bfloat16), 'js')
     assert not head.step_supported(torch.empty(1, 1, 7, 7, device=DEV))         # no 16-byte vectors
 
 
@@ -377,3 +382,31 @@ def test_stacked_single_launch_step_matches_stacked_two_kernel_path_and_oracle(d
     for s in range(stacks):
         assert float((ca[s] - coords[s]).abs().max()) < TOL
         assert rel_l2(ga[s].numpy(), z64[s].grad.numpy()) < (4e-3 if dtype == 'bf16' else TOL)
+
+
+@pytest.mark.parametrize('shape,dtype,reg', [((3, 16, 256, 256), 'f32', 'var'), ((3, 16, 256, 256), 'f32', 'none'),
+                                             ((2, 16, 256, 256), 'bf16', 'js'), ((2, 16, 256, 256), 'bf16', 'var'),
+                                             ((5, 16, 128, 128), 'f32', 'var'), ((40, 16, 256, 256), 'f32', 'var')])
+def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, dtype, reg):
+    """csrc/step_l2.cu: forward and backward of each heatmap back to back in one persistent kernel (BASELINE config 5:
+    256x256 with the variance regulariser).  Against the two-kernel path it must agree to rounding -- it runs the same
+    device code -- and against the fp64 oracle to the usual tolerance."""
+    from dsnt_pose2d_b200 import _lib
+    b, c, h, w = shape
+    gen = torch.Generator().manual_seed(91)
+    z = torch.randn(b, c, h, w, generator=gen) * 2.0
+    if dtype == 'bf16':
+        z = z.to(torch.bfloat16)
+    target = torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8
+    mask = (torch.rand(b, c, generator=gen) > 0.2).float()
+    before = _lib.launch_count
+    got = run_step(dp, z, target, mask, reg)
+    assert _lib.launch_count - before == 4          # mask count, step, finishing reduction, scale: not fwd + finish + bwd
+    two = run_step(dp, z, target, mask, reg, one_pass=False)
+    assert got['loss'] == two['loss'] and np.array_equal(got['coords'], two['coords'])
+    assert rel_l2(got['dz'], two['dz']) < (4e-3 if dtype == 'bf16' else 1e-6)
+    n_chk = min(b, 3)
+    ref = tp.head_loss_and_grad(z.float()[:n_chk], target[:n_chk], mask[:n_chk], reg, 1.0, 1.0, dtype=torch.float64)
+    scale = mask[:n_chk].sum().clamp(min=1).item() / mask.sum().clamp(min=1).item()
+    assert float(np.abs(got['coords'][:n_chk] - ref['coords'].numpy()).max()) < TOL
+    assert rel_l2(got['dz'][:n_chk], ref['dz'].numpy() * scale) < (4e-3 if dtype == 'bf16' else TOL)

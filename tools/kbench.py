@@ -109,7 +109,7 @@ def main():
                         print('%-6s %-5s %-5s %3d | FAILED %s' % (cfg, dt, reg, variant, e))
                         continue
                     ts = None
-                    if _lib.LIB.dsnt_head_step_supported(_lib.dtype_id(zs[0]), h, w):
+                    if _lib.LIB.dsnt_head_step_supported_reg(_lib.dtype_id(zs[0]), h, w, rid):
                         cnt8 = torch.empty(8, device=dev)
                         _lib.call('dsnt_mask_count', mask.data_ptr(), n, cnt8.data_ptr(), ws.data_ptr(), stream)
 
