@@ -57,7 +57,7 @@ static bool step2_window_fits(int H, int W, int vec, int reg, float r2_win) {
 static int step2_pace_cycles(long hm_bytes, int ctas) {
   static const int fixed = env_int("DSNT_TUNE_STEP_PACE", -1);
   if (fixed >= 0) return fixed;
-  static const int gbs = env_int("DSNT_TUNE_STEP_PACE_GBS", 6750);
+  static const int gbs = env_int("DSNT_TUNE_STEP_PACE_GBS", 6800);
   if (gbs <= 0) return 0;
   static double ghz = 0.0;
   if (ghz == 0.0) {

@@ -4,7 +4,7 @@
 # Knobs (read once per process by csrc/step.cu):
 #   DSNT_TUNE_STEP_V2=0          generic kernel instead of the 64x64 one
 #   DSNT_TUNE_STEP_WARPS=n       warps per CTA            DSNT_TUNE_STEP_NWMAX=12|16|20|24   register budget variant
-#   DSNT_TUNE_STEP_PACE_GBS=g    pacing target (0 = unpaced; default 6750)   DSNT_TUNE_STEP_PACE=c   pace in SM clocks
+#   DSNT_TUNE_STEP_PACE_GBS=g    pacing target (0 = unpaced; default 6800)   DSNT_TUNE_STEP_PACE=c   pace in SM clocks
 #   DSNT_TUNE_STEP_PACED=1       paced build for bf16 JS/MSE too             DSNT_TUNE_STEP_DEBUG=1  copy z -> dz, no arithmetic
 #   DSNT_TUNE_STEP_NBUF2=n       cap on the ring buffers  DSNT_TUNE_STEP_STAGGER=ns  staggered start of the warps
 K="timeout 200 python tools/kbench.py --configs cfg4 --step-only"
