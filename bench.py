@@ -282,7 +282,7 @@ def main_ours(args):
     from dsnt_pose2d_b200.head import step_supported
     from dsnt_pose2d_b200.parallel import PeerExchange
     one_pass = args.path == 'one-pass' and step_supported(z, reg)
-    exchange_note = ('inside the finishing kernels over NVLink peer memory (no collective launch)'
+    exchange_note = ('inside the kernels over NVLink peer memory (no collective launch)'
                      if PeerExchange.get(group, dev) is not None else 'by a 3-float NCCL all-reduce')
 
     def step():
@@ -346,6 +346,7 @@ def main_ours(args):
     # ---------------- pass 2 (same steps, still inside the clock-sampled window): CUDA events around every launch of
     # our kernels, on the stream they are enqueued on, for the per-kernel roofline
     _lib.event_log = {'dsnt_head_fwd': [], 'dsnt_head_bwd': [], 'dsnt_head_step': [], 'dsnt_head_step_fused': [],
+                      'dsnt_head_step_fused_peer': [],
                       'dsnt_finish_loss': [], 'dsnt_mask_count': [], 'dsnt_scale_unless_one': [],
                       'dsnt_finish_loss_peer': [], 'dsnt_mask_count_peer': []}
     for _ in range(args.steps):
@@ -410,7 +411,10 @@ def main_ours(args):
            'dsnt_head_bwd': n_local * (2 * hw * esize + 44),    # read Z, write dZ; stats 32 r, target 8 r, mask 4 r
            'dsnt_head_step': n_local * (2 * hw * esize + 68),   # read Z, write dZ; target 8 r, mask 4 r, coords/stats/terms 56 w
            'dsnt_head_step_fused': n_local * (2 * hw * esize + 60)}   # the same without the terms (8 w); the mask again from L2
+    alg['dsnt_head_step_fused_peer'] = alg['dsnt_head_step_fused']     # + 2 x 16 bytes to every peer
     ran = [k for k in alg if kernel_ms.get(k)]
+    if not ran:
+        raise RuntimeError('bench.py: none of the timed entry points ran (%r)' % (sorted(kernel_ms),))
     dominant = max(ran, key=lambda k: kernel_ms[k])
     per_kernel = {}
     for k in ran:
@@ -421,8 +425,9 @@ def main_ours(args):
     step_bytes = sum(alg[k] for k in ran)
     step_gbs = step_bytes * world / (elapsed_ms / args.steps * 1e-3) / 1e9
     traffic = committed_traffic(args.workload)
-    if isinstance(traffic, dict) and 'dsnt_head_step_fused' not in traffic and 'dsnt_head_step' in traffic:
-        traffic['dsnt_head_step_fused'] = traffic['dsnt_head_step']      # the same kernel (head_step2_kernel)
+    if isinstance(traffic, dict) and 'dsnt_head_step' in traffic:
+        for same in ('dsnt_head_step_fused', 'dsnt_head_step_fused_peer'):      # the same kernel (head_step2_kernel)
+            traffic.setdefault(same, traffic['dsnt_head_step'])
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': per_kernel[dominant]['achieved_gbs'], 'peak': peak,
                 'unit': 'GB/s', 'frac': per_kernel[dominant]['frac'],
                 'traffic': (traffic or {}).get(dominant) if isinstance(traffic, dict) else None,
@@ -447,6 +452,8 @@ def main_ours(args):
                                 % (n_local * hw * esize / 2 ** 20),
                    'path': ('one-pass: %s (forward and dL/dZ while the heatmap is in shared memory, 2*H*W*sizeof '
                             'algorithmic bytes); backward only scales in place when d(loss) != 1' % (
+                                'dsnt_head_step_fused_peer, ONE launch per rank: mask count, step, loss composition and '
+                                'both exchanges between the ranks' if kernel_ms.get('dsnt_head_step_fused_peer') else
                                 'dsnt_head_step_fused, ONE launch: mask count, step and loss composition'
                                 if kernel_ms.get('dsnt_head_step_fused') else
                                 'dsnt_mask_count + dsnt_head_step + dsnt_finish_loss')) if one_pass else

@@ -63,6 +63,9 @@ SIGNATURES = {
     'dsnt_peer_exchange_bytes': (_c_int, []),
     'dsnt_finish_loss_peer': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_float, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int,
                                        _c_ptr, _c_ptr, _c_ptr]),
+    'dsnt_head_step_fused_peer': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int,
+                                           _c_float, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int,
+                                           _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_mask_count_peer': (_c_int, [_c_ptr, _c_long, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_euclid_fwd': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_ptr, _c_ptr]),
     'dsnt_euclid_bwd': (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_long, _c_int, _c_int, _c_ptr,

@@ -25,65 +25,6 @@ __device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& 
 // workspace: kFinishSlots*4 floats of partials followed by one unsigned ticket counter that must be zero
 // before the first launch and is reset by the kernel itself (stream-ordered use only).
 
-// ------------------------------------------------------------------------------------------------
-// Exchange of the three partial sums between the ranks of one node, INSIDE the finishing kernel (no NCCL launch):
-// every rank owns an exchange buffer that all ranks of the group have mapped (torch symmetric memory: P2P over
-// NVLink); the CTA that holds the last ticket stores its sums into slot [rank] of EVERY rank's buffer, waits until
-// the slots of all ranks in its OWN buffer carry the current epoch, and adds them in rank order -- the same order on
-// every rank, so all ranks get bit-identical totals.  Two parities of slots: a rank can be at most one exchange ahead
-// of another (it cannot finish exchange e+1 without the other's contribution, sent only after that one finished e).
-constexpr int kMaxRanks = DSNT_MAX_RANKS;
-struct PeerXchg {
-  float4* peers[kMaxRanks];   // peers[r]: rank r's exchange buffer, 2 * kMaxRanks float4 slots, zero before first use
-  unsigned* epoch;            // local device counter of exchanges done so far (zero before first use)
-  int* error;                 // local device flag, set when a peer did not show up in time
-  int rank, world;
-};
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Called by the first warp of one CTA; (a, b, c) are valid on lane 0; returns the totals on every lane.
-__device__ __forceinline__ void peer_exchange_sum3(const PeerXchg& x, float& a, float& b, float& c) {
-  const int lane = threadIdx.x & 31;
-  a = __shfl_sync(kFull, a, 0); b = __shfl_sync(kFull, b, 0); c = __shfl_sync(kFull, c, 0);
-  const unsigned e = __shfl_sync(kFull, lane == 0 ? *x.epoch + 1u : 0u, 0);
-  const int par = static_cast<int>(e & 1u) * kMaxRanks;
-  if (lane < x.world) {            // lane r delivers to rank r
-    float4* dst = x.peers[lane] + par + x.rank;
-    float* d = reinterpret_cast<float*>(dst);
-    d[0] = a; d[1] = b; d[2] = c;
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned*>(d) + 3, e);
-  }
-  float va = 0.f, vb = 0.f, vc = 0.f;
-  if (lane < x.world) {            // lane r collects from rank r
-    const float4* src = x.peers[x.rank] + par + lane;
-    const unsigned* flag = reinterpret_cast<const unsigned*>(src) + 3;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    bool ok = true;
-    while (ld_acquire_sys(flag) != e) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { ok = false; break; }     // 20 s: a rank is gone; do not hang the GPU
-    }
-    const volatile float* sv = reinterpret_cast<const volatile float*>(src);
-    if (ok) { va = sv[0]; vb = sv[1]; vc = sv[2]; }
-    else { va = vb = vc = __int_as_float(0x7fc00000); *x.error = 1; }
-  }
-  a = 0.f; b = 0.f; c = 0.f;
-  for (int r = 0; r < x.world; ++r) {   // rank order: identical totals everywhere
-    a += __shfl_sync(kFull, va, r); b += __shfl_sync(kFull, vb, r); c += __shfl_sync(kFull, vc, r);
-  }
-  if (lane == 0) *x.epoch = e;
-}
-
-
 // Stacked form: terms holds n = count*n_per rows (stack-major); the mask (one stack long) is shared, the mask
 // count -- the denominator of every per-stack average -- is taken over the first stack only, so
 // out[6] = sum_s (euclid_s + reg_coeff*reg_s) as in src/dsnt/model.py:238-246.

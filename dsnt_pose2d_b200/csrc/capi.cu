@@ -133,13 +133,6 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
                                g_reg, g_loss, denom, reg_coeff, reg, sigma, flags, variant, stream);
 }
 
-static PeerXchg no_peers() {
-  PeerXchg xc;
-  for (int r = 0; r < kMaxRanks; ++r) xc.peers[r] = nullptr;
-  xc.epoch = nullptr; xc.error = nullptr; xc.rank = 0; xc.world = 1;
-  return xc;
-}
-
 DSNT_API int dsnt_finish_workspace_bytes(void) { return static_cast<int>(sizeof(float) * kFinishWorkspaceFloats); }
 
 DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
@@ -157,20 +150,6 @@ DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, lon
 }
 
 DSNT_API int dsnt_peer_exchange_bytes(void) { return static_cast<int>(sizeof(float4) * 2 * kMaxRanks); }
-
-static int make_peers(const void* const* peers, int rank, int world, unsigned* epoch, int* error, PeerXchg& xc) {
-  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !peers || !epoch || !error) {
-    set_error("peer exchange: bad arguments (world %d, rank %d, at most %d ranks)", world, rank, kMaxRanks);
-    return DSNT_ERR_BAD_ARG;
-  }
-  xc = no_peers();
-  for (int r = 0; r < world; ++r) {
-    if (!peers[r] || !aligned(peers[r], 16)) { set_error("peer exchange: buffer of rank %d is null or misaligned", r); return DSNT_ERR_BAD_ARG; }
-    xc.peers[r] = static_cast<float4*>(const_cast<void*>(peers[r]));
-  }
-  xc.epoch = epoch; xc.error = error; xc.rank = rank; xc.world = world;
-  return DSNT_OK;
-}
 
 DSNT_API int dsnt_finish_loss_peer(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
                                    float* out, float* workspace, const void* const* peers, int rank, int world,

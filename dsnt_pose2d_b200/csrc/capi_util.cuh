@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "finish_common.cuh"
 
 namespace dsnt {
 
@@ -31,6 +32,28 @@ inline int check_common(const void* z, int dtype, long n, int H, int W, int reg)
   if (static_cast<long>(H) * W > (1L << 28)) { set_error("heatmap %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
   if (n > 0x7fffffffL) { set_error("too many heatmaps: %ld", n); return DSNT_ERR_UNSUPPORTED; }
   if (reg < DSNT_REG_NONE || reg > DSNT_REG_MSE) { set_error("bad reg %d", reg); return DSNT_ERR_BAD_ARG; }
+  return DSNT_OK;
+}
+
+// ---- peer exchange block of the *_peer entry points (include/dsnt_b200.h)
+inline PeerXchg no_peers() {
+  PeerXchg xc;
+  for (int r = 0; r < kMaxRanks; ++r) xc.peers[r] = nullptr;
+  xc.epoch = nullptr; xc.error = nullptr; xc.rank = 0; xc.world = 1;
+  return xc;
+}
+
+inline int make_peers(const void* const* peers, int rank, int world, unsigned* epoch, int* error, PeerXchg& xc) {
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !peers || !epoch || !error) {
+    set_error("peer exchange: bad arguments (world %d, rank %d, at most %d ranks)", world, rank, kMaxRanks);
+    return DSNT_ERR_BAD_ARG;
+  }
+  xc = no_peers();
+  for (int r = 0; r < world; ++r) {
+    if (!peers[r] || !aligned(peers[r], 16)) { set_error("peer exchange: buffer of rank %d is null or misaligned", r); return DSNT_ERR_BAD_ARG; }
+    xc.peers[r] = static_cast<float4*>(const_cast<void*>(peers[r]));
+  }
+  xc.epoch = epoch; xc.error = error; xc.rank = rank; xc.world = world;
   return DSNT_OK;
 }
 

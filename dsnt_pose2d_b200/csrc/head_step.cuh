@@ -18,6 +18,7 @@
 // results agree with it to rounding; parity is checked against the same oracle.
 #pragma once
 
+#include "finish_common.cuh"
 #include "head_stream.cuh"
 
 namespace dsnt {
@@ -47,6 +48,8 @@ struct HeadStepParams {
   int direct_store;      // 1: dz goes to global memory with 128-bit stores straight from registers; 0: in place + bulk store
   Stacks st;             // head_step2: stacked hourglass (count > 1): n = count * n_per heatmaps, stack s at z + st.z_off[s];
                          //   target / mask are one stack long (indexed inside the stack), coords / stats by heatmap
+  PeerXchg xc;           // head_step2, single-launch form with a sharded batch (world > 1): the mask count and the loss sums
+                         //   cross the ranks from inside this kernel (finish_common.cuh: peer_exchange_sum3)
   float* out8;           // head_step2, single-launch form (dsnt_head_step_fused): the loss block of dsnt_finish_loss, or null
   float* ws;             //   its workspace (dsnt_finish_workspace_bytes); denom may then be null = computed from the mask here
   int debug;             // head_step2 (DSNT_TUNE_STEP_DEBUG, measurements only): 1 = copy z -> dz with LDS + STG and no

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   __shared__ unsigned long long pace_next;        // clock at which the CTA may issue its next bulk load (p.pace)
   __shared__ PendingLoad pend_all[NWMAX];
   __shared__ float fin[NWMAX][2];                  // single-launch form: per-warp sums of mask * (distance, divergence)
-  __shared__ float mask_total;
+  __shared__ float mask_total, mask_local;     // count over all ranks / over this rank's shard
   __shared__ bool fin_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   // bulk loads, which are already in flight.  (All CTAs reading the whole mask instead -- 148 x 256 KiB out of the same
   // L2 lines -- delayed the start of the kernel by ~20 us.)
   float mask_count = 0.f;
+  const bool sharded = p.xc.world > 1;
   if (!p.denom && p.mask) {
     const long nmask = p.st.count > 1 ? p.st.n_per : p.n;       // the stacks share one mask
     const long chunk = (nmask + gridDim.x - 1) / gridDim.x;
@@ -248,14 +249,17 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   }
   __syncthreads();
   if (!p.denom) {
-    if (p.mask) {
-      unsigned* bar = reinterpret_cast<unsigned*>(p.ws + kFinishSlots * 4) + 1;
-      float* mpart = p.ws + kFinishSlots * 4 + 4;
-      if (warp == 0) {
+    unsigned* bar = reinterpret_cast<unsigned*>(p.ws + kFinishSlots * 4) + 1;
+    unsigned* gflag = bar + 1;                                   // sharded: "the total over the ranks is in gtotal"
+    float* gtotal = reinterpret_cast<float*>(bar + 2);
+    float* mpart = p.ws + kFinishSlots * 4 + 4;
+    if (warp == 0) {
+      float tot = static_cast<float>(p.st.count > 1 ? p.st.n_per : p.n);       // no mask: every heatmap counts
+      if (p.mask) {
         if (lane == 0) {
-          float tot = 0.f;
-          for (int w2 = 0; w2 < p.nwarps; ++w2) tot += fin[w2][0];
-          mpart[blockIdx.x] = tot;
+          float t2 = 0.f;
+          for (int w2 = 0; w2 < p.nwarps; ++w2) t2 += fin[w2][0];
+          mpart[blockIdx.x] = t2;
           __threadfence();
           atomicAdd(bar, 1u);
           while (ld_acquire_gpu(bar) < gridDim.x) __nanosleep(64);
@@ -267,17 +271,36 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
           const int i = lane + 32 * k;
           v[k] = i < static_cast<int>(gridDim.x) ? __ldcg(mpart + i) : 0.f;
         }
-        float tot = 0.f;
+        tot = 0.f;
 #pragma unroll
         for (int k = 0; k < kFinishSlots / 32; ++k) tot += v[k];
         tot = warp_sum(tot);
-        if (lane == 0) mask_total = tot;
       }
-      __syncthreads();
-      mask_count = mask_total;
-    } else {
-      mask_count = static_cast<float>(p.st.count > 1 ? p.st.n_per : p.n);
+      if (lane == 0) mask_local = tot;
+      if (sharded) {
+        // the count over ALL ranks: CTA 0 exchanges this rank's total through peer memory and publishes the sum to the
+        // other CTAs of its grid.  Slot layout as in finish_loss_kernel (sum mask*dist, sum mask*D, sum mask), so that a
+        // rank on the three-launch form (an empty shard) meets the others in the same exchanges.
+        if (blockIdx.x == 0) {
+          float z0 = 0.f, z1 = 0.f;
+          peer_exchange_sum3(p.xc, z0, z1, tot);
+          if (lane == 0) {
+            __stcg(gtotal, tot);
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gflag), "r"(1u) : "memory");
+          }
+        } else {
+          if (lane == 0) {
+            while (ld_acquire_gpu(gflag) == 0u) __nanosleep(64);
+            tot = __ldcg(gtotal);
+          }
+          tot = __shfl_sync(kFull, tot, 0);
+        }
+      }
+      if (lane == 0) mask_total = tot;
     }
+    __syncthreads();
+    mask_count = mask_total;
   }
   if (p.stagger_ns > 0) __nanosleep(static_cast<unsigned>(warp * p.stagger_ns + (blockIdx.x & 3) * (p.stagger_ns >> 2)));
   const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
@@ -720,12 +743,14 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
 #pragma unroll
       for (int k = 0; k < kFinishSlots / 32; ++k) { sa += v[k].x; sb += v[k].y; }
       sa = warp_sum(sa); sb = warp_sum(sb);
+      if (sharded) { float cnt = mask_local; peer_exchange_sum3(p.xc, sa, sb, cnt); }   // totals over the ranks
       if (lane == 0) {
         p.out8[0] = sa; p.out8[1] = sb;
         p.out8[2] = p.denom ? __ldg(p.denom) : mask_count;   // with an external denominator out8[2..3] repeat it
         write_loss_tail(p.out8, p.reg_coeff);
         ticket[0] = 0u;
         ticket[1] = 0u;      // the mask barrier: every CTA passed it long ago
+        ticket[2] = 0u;      // and the flag of the count over the ranks
       }
     }
   }

@@ -197,7 +197,7 @@ DSNT_API int dsnt_head_step_supported(int dtype, int H, int W) {
 static int head_step_impl(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
                           const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
                           float* coords, float* stats, float* terms, void* dz, float* out8, float* ws, void* stream,
-                          const Stacks* st = nullptr) {
+                          const Stacks* st = nullptr, const PeerXchg* xc = nullptr) {
   int rc = check_common(z, dtype, n, H, W, reg);
   if (rc) return rc;
   if (n == 0) return DSNT_OK;
@@ -237,6 +237,7 @@ static int head_step_impl(const void* z, int dtype, long n, int H, int W, const 
   p.debug = debug;
   p.pace = 0;   // set per kernel in launch_step2_nw
   p.out8 = out8; p.ws = ws;
+  p.xc = xc ? *xc : no_peers();
   if (st) {
     p.st = *st;
   } else {
@@ -280,6 +281,23 @@ DSNT_API int dsnt_head_step_fused(const void* z, int dtype, long n, int H, int W
   }
   return head_step_impl(z, dtype, n, H, W, target, mask, nullptr, g_loss, reg_coeff, reg, sigma, flags, coords, stats, nullptr, dz,
                         out, workspace, stream);
+}
+
+DSNT_API int dsnt_head_step_fused_peer(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                                       const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords,
+                                       float* stats, void* dz, float* out, float* workspace, const void* const* peers,
+                                       int rank, int world, unsigned* epoch, int* error, void* stream) {
+  if (!out || !workspace || !aligned(workspace, 16)) { set_error("dsnt_head_step_fused_peer: out and a 16-byte aligned workspace are required"); return DSNT_ERR_BAD_ARG; }
+  PeerXchg xc;
+  const int rc = make_peers(peers, rank, world, epoch, error, xc);
+  if (rc) return rc;
+  if (n <= 0) { set_error("dsnt_head_step_fused_peer: an empty shard must take the three-launch form (every rank exchanges)"); return DSNT_ERR_UNSUPPORTED; }
+  if (!dsnt_head_step_fused_supported(dtype, H, W, reg, sigma)) {
+    set_error("dsnt_head_step_fused_peer: %dx%d, dtype %d, reg %d is not served by the single-launch kernel", H, W, dtype, reg);
+    return DSNT_ERR_UNSUPPORTED;
+  }
+  return head_step_impl(z, dtype, n, H, W, target, mask, nullptr, g_loss, reg_coeff, reg, sigma, flags, coords, stats, nullptr, dz,
+                        out, workspace, stream, nullptr, &xc);
 }
 
 DSNT_API int dsnt_head_step_fused_stacked(const void* const* z, void* const* dz, int n_stacks, int dtype, long n_per_stack,

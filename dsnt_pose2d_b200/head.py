@@ -18,6 +18,7 @@ single-process op on the concatenated batch.
 """
 
 import collections
+import os
 
 import torch
 
@@ -253,6 +254,10 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
 USE_L2_STEP = False           # heatmaps too large for shared memory: take the L2-staged one-pass step (csrc/step_l2.cu)?
                               # Measured on B200 at BASELINE config 5 it does not beat the two-kernel path yet (996 vs 970 us:
                               # two resident CTAs per SM keep the logits in L2 but too few bytes in flight), so it is off.
+# Sharded batch: take the single-launch step with both exchanges inside the kernel (dsnt_head_step_fused_peer)?  Parity-green
+# on 2 B200 (tools/check_sharded.py) but no faster than dsnt_mask_count_peer + dsnt_head_step + dsnt_finish_loss_peer there
+# (0.3687 vs 0.3687-0.3706 ms/step: what separates 2 GPUs from 1 is the slower of the two GPUs, not launches), so off.
+FUSED_PEER_STEP = os.environ.get('DSNT_FUSED_PEER_STEP', '0') != '0'
 STEP_MIN_BYTES = 32 << 20     # logits smaller than this take the one-pass step only in its single-launch form
 
 
@@ -260,7 +265,8 @@ def _step_pays(z, h, w, reg_id, sigma, group):
     """The one-pass step saves a read of the logits.  Where the single-launch form serves the case it also saves launches;
     where it does not (other shapes, KL, sharded batch) it takes one launch MORE than the two-kernel path, which only pays
     once the logits no longer sit in L2 (small batches are bound by launches, tools/stepbench.py)."""
-    if not _is_sharded(group) and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, reg_id, sigma):
+    if _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, reg_id, sigma) and (
+            not _is_sharded(group) or (FUSED_PEER_STEP and PeerExchange.get(group, z.device) is not None)):
         return True
     return z.numel() * z.element_size() >= STEP_MIN_BYTES
 
@@ -296,7 +302,14 @@ class _FusedHeadStep(torch.autograd.Function):
             dz = torch.empty_like(zc)
             ws = _lib.finish_workspace(dev)
             sharded = _is_sharded(group)
-            if not sharded and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zc), h, w, reg_id, sigma):
+            fused = bool(_lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zc), h, w, reg_id, sigma))
+            peer = PeerExchange.get(group, dev) if sharded and fused and n > 0 and FUSED_PEER_STEP else None
+            if peer is not None:
+                # one launch per rank: mask count and loss sums cross the ranks inside the kernel (peer memory)
+                _lib.call('dsnt_head_step_fused_peer', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target),
+                          _lib.ptr(mask), None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(),
+                          dz.data_ptr(), out8.data_ptr(), ws.data_ptr(), *peer.args(), stream)
+            elif not sharded and fused:
                 # one launch: the kernel adds up the mask itself and its last CTA composes the loss
                 _lib.call('dsnt_head_step_fused', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
                           None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(), dz.data_ptr(),

@@ -249,6 +249,13 @@ DSNT_API int dsnt_finish_loss_peer(const float* terms, const float* mask, long n
                                    unsigned* epoch, int* error, void* stream);
 DSNT_API int dsnt_mask_count_peer(const float* mask, long n, float* out, float* workspace, const void* const* peers,
                                   int rank, int world, unsigned* epoch, int* error, void* stream);
+/* The single-launch step (dsnt_head_step_fused) on a sharded batch: the mask count crosses the ranks at the start of the
+ * kernel (CTA 0 exchanges, the other CTAs of the grid wait for its result) and the loss sums at its end (the CTA with
+ * the last ticket) -- one launch per rank and step, no collective call.  n > 0 on every rank. */
+DSNT_API int dsnt_head_step_fused_peer(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                                       const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords,
+                                       float* stats, void* dz, float* out, float* workspace, const void* const* peers,
+                                       int rank, int world, unsigned* epoch, int* error, void* stream);
 
 /* Recompute out[3..6] from (possibly all-reduced) out[0..2]; used after the NCCL all-reduce of the sums. */
 DSNT_API int dsnt_combine_loss(float* out, float reg_coeff, void* stream);
