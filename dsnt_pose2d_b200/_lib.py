@@ -47,6 +47,7 @@ SIGNATURES = {
     'dsnt_decode_heatmaps': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_int, _c_ptr, _c_ptr]),
     'dsnt_head_step_supported': (_c_int, [_c_int, _c_int, _c_int]),
     'dsnt_head_step_supported_reg': (_c_int, [_c_int, _c_int, _c_int, _c_int]),
+    'dsnt_head_step_pair_supported': (_c_int, [_c_int, _c_int, _c_int, _c_int]),
     'dsnt_head_step': (_c_int, [_c_ptr, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float, _c_int,
                                 _c_float, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_mask_count': (_c_int, [_c_ptr, _c_long, _c_ptr, _c_ptr, _c_ptr]),

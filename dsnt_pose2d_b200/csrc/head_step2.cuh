@@ -146,7 +146,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 }
 // Arms the barrier and starts the bulk load of one heatmap.  Deliberately NOT inlined: it is reached from several places
 // of a fully unrolled kernel whose size matters (the instruction stream is walked once per heatmap).
-__device__ __noinline__ void ring_issue(const char* src, uint32_t hm_bytes, uint32_t bar, uint32_t bufs, volatile int* flag, int value) {
+static __device__ __noinline__ void ring_issue(const char* src, uint32_t hm_bytes, uint32_t bar, uint32_t bufs, volatile int* flag, int value) {
   mbar_expect_tx(bar, hm_bytes);
   bulk_load(bufs, src, hm_bytes, bar);
   __threadfence_block();

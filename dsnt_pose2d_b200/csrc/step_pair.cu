@@ -1,0 +1,363 @@
+// step_pair.cu -- the one-pass training step for 256x256 fp32 heatmaps (BASELINE config 5) on a PAIR of SMs.
+//
+// A 256x256 fp32 heatmap is 256 KiB: more than the 227 KiB of shared memory one CTA can have, which is why config 5 ran the
+// two-kernel path at 12 bytes per pixel.  A thread-block CLUSTER of two CTAs has 2 x 227 KiB: each CTA of the pair takes
+// one half of the heatmap (128 rows, 128 KiB, TMA bulk loads into its own shared memory), sweeps it for the maximum,
+// the sums and -- writing e = 2^(z log2e - max) back in place -- the gradient, and the pair exchanges its per-half partial
+// results through DISTRIBUTED SHARED MEMORY (each CTA reads the other's slot after a cluster barrier, both add in rank
+// order, so both hold bit-identical totals).  HBM sees every logit once: 8 bytes per pixel.
+//
+// The shared memory of a CTA is a ring of seven 32 KiB chunk buffers; a half heatmap takes four, so while heatmap k is
+// being processed three chunks of heatmap k+1 are already loading, and when k is done its four buffers take the last chunk
+// of k+1 and the first three of k+2: the loads of the next heatmap overlap the arithmetic of this one.
+//
+// Same mathematics as head_step2.cuh (src/dsnt/nn.py:25-116,274-298, src/dsnt/model.py:24-63,145):
+// column accumulators + one row sum per sweep step give S, S_x, S_y and the variance about the mean without a second look;
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2).  Regularisers: none and variance (what config 5 uses); the others keep the
+// two-kernel path.  The denominator of masked_average is an input, as for dsnt_head_step.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
+#include "capi_util.cuh"
+#include "f32x2.cuh"
+#include "head_step2.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dsnt {
+
+constexpr int kPairH = 256, kPairW = 256;
+constexpr int kPairThreads = 1024;
+constexpr int kPairHalfRows = kPairH / 2;                       // rows per CTA
+constexpr int kPairHalfBytes = kPairHalfRows * kPairW * 4;      // 128 KiB
+constexpr int kPairWV = kPairW / 4;                             // 64 vectors per row
+constexpr int kPairRowsPerStep = kPairThreads / kPairWV;        // 16 rows per sweep step
+constexpr int kPairIters = kPairHalfRows / kPairRowsPerStep;    // 8 sweep steps
+constexpr int kPairChunks = 4;                                  // a half heatmap = 4 chunks of 32 KiB
+constexpr int kPairChunkBytes = kPairHalfBytes / kPairChunks;   // 32 KiB = two sweep steps
+constexpr int kPairSlots = 7;                                   // ring of chunk buffers: 224 KiB of the 227 KiB a CTA may have
+constexpr int kPairSmemBytes = kPairSlots * kPairChunkBytes;
+
+struct PairParams {
+  const float* z;
+  float* dz;
+  const float* target;
+  const float* mask;
+  const float* denom;
+  const float* g_loss;
+  float* coords;
+  float* stats;
+  float* terms;
+  long n;
+  int flags;
+  float sigma, reg_coeff;
+};
+
+// sum over the 1024 threads of one CTA of up to four values, identical on every thread, fixed order
+__device__ __forceinline__ void pair_block_sum4(float& a, float& b, float& c, float& d, float (*red)[4], int warp, int lane) {
+  const float k = warp_sum4_transposed(a, b, c, d, lane);
+  if ((lane & 7) == 0) red[warp][lane >> 3] = k;
+  __syncthreads();
+  // 32 warps = 32 lanes: every warp adds the per-warp partials with the same butterfly
+  const float k2 = warp_sum4_transposed(red[lane][0], red[lane][1], red[lane][2], red[lane][3], lane);
+  a = __shfl_sync(kFull, k2, 0); b = __shfl_sync(kFull, k2, 8); c = __shfl_sync(kFull, k2, 16); d = __shfl_sync(kFull, k2, 24);
+  __syncthreads();      // red may be reused
+}
+
+template <int REG>
+__global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const PairParams p) {
+  constexpr bool kVar = REG == DSNT_REG_VAR;
+  constexpr float tow = 2.0f / kPairW, bw = 1.0f / kPairW - 1.0f, toh = 2.0f / kPairH, bh = 1.0f / kPairH - 1.0f;
+  extern __shared__ __align__(128) unsigned char pair_smem[];
+  __shared__ __align__(8) unsigned long long bars[kPairSlots];
+  __shared__ float red[32][4];
+  __shared__ __align__(16) float xin[2][4];               // the PEER's partial results, stored here by the peer (st.async over DSMEM)
+  __shared__ __align__(8) unsigned long long xbar[1];     // ... the two stores completing 32 bytes on this mbarrier
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();            // 0: rows 0..127, 1: rows 128..255
+  const unsigned peer = rank ^ 1u;
+  const long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // The exchange of a heatmap: thread 0 arms its own xbar for 32 bytes and stores its partial results into the peer's xin
+  // with st.async, which completes the bytes on the PEER's xbar; everybody then waits on the local barrier and reads the
+  // local xin.  No cluster-wide barrier (whose release fence makes all 1024 threads wait for their global stores: the
+  // first version of this kernel, 1053 us at config 5, against 878 us with three such exchanges and less with one).
+  const uint32_t xin_s = smem_u32(&xin[0][0]), xbar_s = smem_u32(&xbar[0]);
+  uint32_t peer_xin_s, peer_xbar_s;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xin_s) : "r"(xin_s), "r"(peer));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xbar_s) : "r"(xbar_s), "r"(peer));
+  auto send = [&](float a, float b, float c, float d, float e, float f) {      // thread 0
+    mbar_expect_tx(xbar_s, 32);
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(peer_xin_s),
+                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(peer_xbar_s)
+                 : "memory");
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(peer_xin_s + 16),
+                 "f"(e), "f"(f), "f"(0.f), "f"(0.f), "r"(peer_xbar_s)
+                 : "memory");
+  };
+  const uint32_t bars_s = smem_u32(&bars[0]), buf_s = smem_u32(pair_smem);
+  const long hm_floats = static_cast<long>(kPairH) * kPairW;
+  // heatmaps of this cluster: hm = cluster_id + k * n_clusters, k = 0 .. nk-1; chunk c of heatmap k is chunk number
+  // g = 4k + c of this CTA's stream and lives in ring slot g mod 7 on that slot's (g / 7)-th use
+  const long nk = p.n > cluster_id ? (p.n - cluster_id + n_clusters - 1) / n_clusters : 0;
+  auto issue = [&](long k, int c) {      // thread 0
+    if (k >= nk) return;
+    const long hm = cluster_id + k * n_clusters;
+    const unsigned g = static_cast<unsigned>(4 * k + c), slot = g % kPairSlots;
+    const char* src = reinterpret_cast<const char*>(p.z + hm * hm_floats) + static_cast<size_t>(rank) * kPairHalfBytes +
+                      static_cast<size_t>(c) * kPairChunkBytes;
+    mbar_expect_tx(bars_s + 8 * slot, kPairChunkBytes);
+    bulk_load(buf_s + slot * kPairChunkBytes, src, kPairChunkBytes, bars_s + 8 * slot);
+  };
+  if (tid == 0) {
+    for (int sl = 0; sl < kPairSlots; ++sl) mbar_init(bars_s + 8 * sl, 1);
+    mbar_init(xbar_s, 1);
+    for (int c = 0; c < 4; ++c) issue(0, c);
+    for (int c = 0; c < 3; ++c) issue(1, c);
+  }
+  cluster.sync();       // both CTAs' barriers exist before the first remote store
+  const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
+  const float inv_denom = 1.0f / __ldg(p.denom);
+  const float s2 = p.sigma * p.sigma;
+
+  // thread geometry: vector column cv (4 pixels), rows row_base + 16 * it inside this CTA's half
+  const int cv = tid & (kPairWV - 1), r0 = tid >> 6;
+  float xs[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xs[c] = fmaf(static_cast<float>(cv * 4 + c), tow, bw);
+  const float y0 = fmaf(static_cast<float>(rank * kPairHalfRows + r0), toh, bh);
+  constexpr float dyi = kPairRowsPerStep * toh;
+  const f2 l2e2 = pk1(kLog2e);
+
+  for (long k = 0; k < nk; ++k) {
+    const long hm = cluster_id + k * n_clusters;
+    // the four chunk buffers of this heatmap (byte offsets of this thread's vectors) -- sweep step it reads chunk it / 2
+    const unsigned g0 = static_cast<unsigned>(4 * k);
+    unsigned off[kPairIters];
+#pragma unroll
+    for (int it = 0; it < kPairIters; ++it)
+      off[it] = ((g0 + it / 2) % kPairSlots) * kPairChunkBytes + (it & 1) * (kPairChunkBytes / 2) + tid * 16;
+    float tx = 0.f, ty = 0.f;
+    if (p.target) {
+      const float2 tt = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
+      tx = tt.x; ty = tt.y;
+    }
+    const float wgt = (p.mask ? __ldg(p.mask + hm) : 1.0f) * inv_denom;
+
+    // ---------------------------------------------------------------- maximum (waits for each chunk on first touch)
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int it = 0; it < kPairIters; ++it) {
+      if ((it & 1) == 0) {
+        const unsigned g = g0 + it / 2;
+        mbar_wait(bars_s + 8 * (g % kPairSlots), (g / kPairSlots) & 1u);
+      }
+      const uint4 r = *reinterpret_cast<const uint4*>(pair_smem + off[it]);
+      m0 = fmaxf(m0, fmaxf(__uint_as_float(r.x), __uint_as_float(r.y)));
+      m1 = fmaxf(m1, fmaxf(__uint_as_float(r.z), __uint_as_float(r.w)));
+    }
+    float mloc = warp_max_redux(fmaxf(m0, m1));
+    if (lane == 0) red[warp][0] = mloc;
+    __syncthreads();
+    mloc = warp_max_redux(red[lane][0]);
+    __syncthreads();                                  // red is free again
+    // Each half is summed relative to ITS OWN maximum; the halves are merged afterwards like two blocks of an online
+    // softmax (S = S_0 2^(m_0 - m) + S_1 2^(m_1 - m)), so ONE exchange per heatmap carries everything.
+    const float m2h = mloc * kLog2e;
+    const f2 nm2 = pk1(-m2h);
+
+    // ---------------------------------------------------------------- sums; e goes back into the buffer
+    f2 colE[2] = {pk1(0.f), pk1(0.f)};
+    float rsk[kVar ? kPairIters : 1];
+    float Sy = 0.f;
+#pragma unroll
+    for (int it = 0; it < kPairIters; ++it) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(pair_smem + off[it]);
+      f2 v[2], e[2];
+      unpack_pairs<float>(raw, v);
+      e[0] = ex2_2(fma2(v[0], l2e2, nm2));
+      e[1] = ex2_2(fma2(v[1], l2e2, nm2));
+      colE[0] = add2(colE[0], e[0]);
+      colE[1] = add2(colE[1], e[1]);
+      const float rs = hsum(add2(e[0], e[1]));
+      Sy = fmaf(rs, y0 + static_cast<float>(it) * dyi, Sy);
+      if constexpr (kVar) rsk[it] = rs;
+      *reinterpret_cast<uint4*>(pair_smem + off[it]) = pack_pairs<float>(e);
+    }
+    float c0, c1, c2, c3;
+    upk(colE[0], c0, c1);
+    upk(colE[1], c2, c3);
+    float Sh = (c0 + c1) + (c2 + c3);
+    float Sxh = fmaf(c0, xs[0], fmaf(c1, xs[1], fmaf(c2, xs[2], c3 * xs[3])));
+    float Syh = Sy, zero = 0.f;
+    pair_block_sum4(Sh, Sxh, Syh, zero, red, warp, lane);
+    // variance: second moments of this half about ITS OWN mean, merged with the other half's by the parallel-variance
+    // formula (Chan et al.): no E[x^2] - mu^2 anywhere
+    float axh = 0.f, ayh = 0.f;
+    if constexpr (kVar) {
+      const float ih = rcp(Sh);
+      const float mxh = Sxh * ih, myh = Syh * ih;
+      {
+        const float d0 = xs[0] - mxh, d1 = xs[1] - mxh, d2 = xs[2] - mxh, d3 = xs[3] - mxh;
+        axh = fmaf(c0 * d0, d0, fmaf(c1 * d1, d1, fmaf(c2 * d2, d2, c3 * d3 * d3)));
+      }
+#pragma unroll
+      for (int it = 0; it < kPairIters; ++it) {
+        const float d = (y0 + static_cast<float>(it) * dyi) - myh;
+        ayh = fmaf(rsk[it] * d, d, ayh);
+      }
+      float z0 = 0.f, z1 = 0.f;
+      pair_block_sum4(axh, ayh, z0, z1, red, warp, lane);
+    }
+    const uint32_t xphase = static_cast<uint32_t>(k) & 1u;
+    if (tid == 0) send(m2h, Sh, Sxh, Syh, axh, ayh);
+    mbar_wait(xbar_s, xphase);
+    // merge in rank order on both CTAs: bit-identical totals
+    const bool first = rank == 0;
+    const float p_m = xin[0][0], p_S = xin[0][1], p_Sx = xin[0][2], p_Sy = xin[0][3], p_ax = xin[1][0], p_ay = xin[1][1];
+    const float h_m[2] = {first ? m2h : p_m, first ? p_m : m2h};
+    const float h_S[2] = {first ? Sh : p_S, first ? p_S : Sh};
+    const float h_Sx[2] = {first ? Sxh : p_Sx, first ? p_Sx : Sxh};
+    const float h_Sy[2] = {first ? Syh : p_Sy, first ? p_Sy : Syh};
+    const float h_ax[2] = {first ? axh : p_ax, first ? p_ax : axh};
+    const float h_ay[2] = {first ? ayh : p_ay, first ? p_ay : ayh};
+    const float m2 = fmaxf(h_m[0], h_m[1]);
+    const float sc0 = ex2(h_m[0] - m2), sc1 = ex2(h_m[1] - m2);
+    const float S0 = h_S[0] * sc0, S1 = h_S[1] * sc1;
+    const float S = S0 + S1;
+    const float Sx = fmaf(h_Sx[0], sc0, h_Sx[1] * sc1), Sys = fmaf(h_Sy[0], sc0, h_Sy[1] * sc1);
+    const float invS = rcp(S);
+    const float mux = Sx * invS, muy = Sys * invS;
+    const float invSh = (first ? sc0 : sc1) * invS;       // this half's e (relative to its own maximum) -> probability
+
+    float D = 0.f, creg = 0.f, vx = 0.f, vy = 0.f;
+    if constexpr (kVar) {
+      const float i0 = rcp(h_S[0]), i1 = rcp(h_S[1]);
+      const float dmx = h_Sx[0] * i0 - h_Sx[1] * i1, dmy = h_Sy[0] * i0 - h_Sy[1] * i1;
+      const float cross = S0 * S1 * invS;
+      vx = (fmaf(h_ax[0], sc0, h_ax[1] * sc1) + dmx * dmx * cross) * invS;
+      vy = (fmaf(h_ay[0], sc0, h_ay[1] * sc1) + dmy * dmy * cross) * invS;
+      const float ex = vx - s2, ey = vy - s2;
+      D = ex * ex + ey * ey;
+      creg = 2.f * (ex * vx + ey * vy);
+    }
+
+    // ---------------------------------------------------------------- outputs + the scalars of the backward
+    float dist = 0.f, a = 0.f, b = 0.f;
+    if (p.target) {
+      const float dx = mux - tx, dy = muy - ty;
+      const float d2 = dx * dx + dy * dy;
+      const float rs = rsqrtf(d2);
+      dist = d2 > 0.f ? d2 * rs : 0.f;
+      const float invd = d2 > 0.f ? rs : ((p.flags & DSNT_FLAG_STRICT_NAN) ? INFINITY : 0.f);
+      a = gl * wgt * (dx * invd);
+      b = gl * wgt * (dy * invd);
+    }
+    const float rho = gl * wgt * p.reg_coeff;
+    if (rank == 0 && tid == 0) {
+      reinterpret_cast<float2*>(p.coords)[hm] = make_float2(mux, muy);
+      if (p.stats) {
+        float4* st = reinterpret_cast<float4*>(p.stats + hm * kStatsK);
+        st[0] = make_float4(m2, invS, mux, muy);
+        st[1] = make_float4(vx, vy, creg, 0.f);
+      }
+      if (p.terms) reinterpret_cast<float2*>(p.terms)[hm] = make_float2(dist, D);
+    }
+    const float cbase = -fmaf(a, mux, fmaf(b, muy, rho * creg));
+
+    // ---------------------------------------------------------------- backward: dz = e * (A_col + R_row) / S
+    {
+      f2 acol[2];
+      const float kx = kVar ? rho * 2.f * (vx - s2) : 0.f;
+      float av[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v0 = a * xs[c];
+        if (kVar) { const float d = xs[c] - mux; v0 = fmaf(kx * d, d, v0); }
+        av[c] = v0 * invSh;
+      }
+      acol[0] = pk(av[0], av[1]);
+      acol[1] = pk(av[2], av[3]);
+      const float bS = b * invSh, cbS = cbase * invSh;
+      const float kyS = kVar ? rho * 2.f * (vy - s2) * invSh : 0.f;
+      uint4* dzv = reinterpret_cast<uint4*>(p.dz + hm * hm_floats) + static_cast<size_t>(rank) * (kPairHalfBytes / 16);
+#pragma unroll
+      for (int it = 0; it < kPairIters; ++it) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(pair_smem + off[it]);
+        f2 e[2], o[2];
+        unpack_pairs<float>(raw, e);
+        const float y = y0 + static_cast<float>(it) * dyi;
+        float rc = fmaf(bS, y, cbS);
+        if (kVar) { const float d = y - muy; rc = fmaf(kyS * d, d, rc); }
+        const f2 rc2 = pk1(rc);
+        o[0] = mul2(e[0], add2(acol[0], rc2));
+        o[1] = mul2(e[1], add2(acol[1], rc2));
+        dzv[it * kPairThreads + tid] = pack_pairs<float>(o);
+      }
+    }
+
+    // ---------------------------------------------------------------- this heatmap's four buffers are free: they take the
+    // last chunk of the next heatmap and the first three of the one after it
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      issue(k + 1, 3);
+      for (int c = 0; c < 3; ++c) issue(k + 2, c);
+    }
+  }
+  cluster.sync();      // neither CTA leaves while the other may still store into its shared memory
+}
+
+static int pair_enabled() {
+  static const int v = [] { const char* e = std::getenv("DSNT_TUNE_STEP_PAIR"); return e ? std::atoi(e) : 1; }();
+  return v;
+}
+
+bool step_pair_supported(int dtype, int H, int W, int reg) {
+  return pair_enabled() && dtype == DSNT_DTYPE_F32 && H == kPairH && W == kPairW && (reg == DSNT_REG_NONE || reg == DSNT_REG_VAR);
+}
+
+template <int REG>
+static int launch_pair(const PairParams& p, cudaStream_t stream) {
+  auto kern = head_step_pair_kernel<REG>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes) != cudaSuccess)
+      return check_launch("head_step_pair_kernel (shared-memory opt-in)");
+    cudaLaunchConfig_t probe = {};
+    probe.gridDim = dim3(2 * 148); probe.blockDim = dim3(kPairThreads); probe.dynamicSmemBytes = kPairSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    probe.attrs = at; probe.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &probe) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = 64; }
+    max_clusters = nc;
+  }
+  long clusters = p.n < max_clusters ? p.n : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters)); cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = kPairSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return check_launch("head_step_pair_kernel");
+  return check_launch("head_step_pair_kernel");
+}
+
+// returns 1 when the case is not served
+int launch_step_pair(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
+                     const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
+                     float* coords, float* stats, float* terms, void* dz, cudaStream_t stream) {
+  if (!step_pair_supported(dtype, H, W, reg) || !denom) return 1;
+  PairParams p;
+  p.z = static_cast<const float*>(z); p.dz = static_cast<float*>(dz); p.target = target; p.mask = mask; p.denom = denom;
+  p.g_loss = g_loss; p.coords = coords; p.stats = stats; p.terms = terms; p.n = n; p.flags = flags; p.sigma = sigma;
+  p.reg_coeff = reg_coeff;
+  return reg == DSNT_REG_VAR ? launch_pair<DSNT_REG_VAR>(p, stream) : launch_pair<DSNT_REG_NONE>(p, stream);
+}
+
+}  // namespace dsnt

@@ -251,6 +251,8 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     return HeadOutput(coords, loss, out8[4], out8[5])
 
 
+USE_PAIR_STEP = True          # 256x256 fp32, no / variance regulariser: the cluster-of-two-CTAs one-pass step (csrc/step_pair.cu),
+                              # 800 us against 970 us of forward + backward at BASELINE config 5
 USE_L2_STEP = False           # heatmaps too large for shared memory: take the L2-staged one-pass step (csrc/step_l2.cu)?
                               # Measured on B200 at BASELINE config 5 it does not beat the two-kernel path yet (996 vs 970 us:
                               # two resident CTAs per SM keep the logits in L2 but too few bytes in flight), so it is off.
@@ -276,6 +278,9 @@ def step_supported(z, reg=None):
     them fit in shared memory, or -- for larger ones, given the regulariser -- the L2-staged form serves the case."""
     if z.dtype not in (torch.float32, torch.bfloat16) or z.dim() < 2 or z.numel() == 0:
         return False
+    if reg is not None and USE_PAIR_STEP and _lib.LIB.dsnt_head_step_pair_supported(
+            _lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1]), _lib.REG_IDS[reg]):
+        return True
     if reg is None or not USE_L2_STEP:
         return bool(_lib.LIB.dsnt_head_step_supported(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1])))
     return bool(_lib.LIB.dsnt_head_step_supported_reg(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1]),

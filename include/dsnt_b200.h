@@ -129,6 +129,9 @@ DSNT_API int dsnt_head_step_supported(int dtype, int H, int W);
  * backward of each heatmap back to back in one persistent kernel, so the second read of the logits hits L2 and HBM
  * still sees 2*H*W*sizeof bytes per heatmap.  Serves every regulariser for bf16, none / var for fp32; needs stats. */
 DSNT_API int dsnt_head_step_supported_reg(int dtype, int H, int W, int reg);
+/* 256x256 fp32 with no or the variance regulariser (BASELINE config 5) is served by a cluster of two CTAs, each holding
+ * half the heatmap in shared memory, partial results exchanged through distributed shared memory (csrc/step_pair.cu). */
+DSNT_API int dsnt_head_step_pair_supported(int dtype, int H, int W, int reg);
 DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
                             const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
                             float* coords, float* stats, float* terms, void* dz, void* stream);

@@ -33,9 +33,11 @@ def always_take_the_step_kernels(dp):
     from dsnt_pose2d_b200 import head
     old, head.STEP_MIN_BYTES = head.STEP_MIN_BYTES, 0
     old_l2, head.USE_L2_STEP = head.USE_L2_STEP, True
+    old_pair, head.USE_PAIR_STEP = head.USE_PAIR_STEP, True
     yield
     head.STEP_MIN_BYTES = old
     head.USE_L2_STEP = old_l2
+    head.USE_PAIR_STEP = old_pair
 
 
 def run_step(dp, z, target, mask, reg, hm_sigma=1.0, coeff=1.0, g=None, one_pass=True):
@@ -49,6 +51,11 @@ def run_step(dp, z, target, mask, reg, hm_sigma=1.0, coeff=1.0, g=None, one_pass
     torch.cuda.synchronize()
     return {'loss': out.loss.item(), 'euclid': out.euclid.item(), 'reg': out.reg.item(),
             'coords': out.coords.detach().cpu().double().numpy(), 'dz': zz.grad.detach().cpu().double().numpy()}
+
+
+def _lib_pair(h, w, reg):
+    from dsnt_pose2d_b200 import _lib
+    return bool(_lib.LIB.dsnt_head_step_pair_supported(0, h, w, _lib.REG_IDS[reg]))
 
 
 def _lib_counts(_lib):
@@ -75,6 +82,7 @@ def test_step_is_taken_only_where_supported(dp):
     assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV))     # 256 KiB: not in shared memory ...
     assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'var')  # ... but staged through L2 (step_l2.cu)
     assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'js')    # fp32 + Gaussian window: two-kernel
+    assert _lib_pair(256, 256, 'var') and _lib_pair(256, 256, 'none') and not _lib_pair(256, 256, 'js') and not _lib_pair(128, 128, 'var')
     assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV, dtype=torch.bfloat16), 'js')
     assert not head.step_supported(torch.empty(1, 1, 7, 7, device=DEV))         # no 16-byte vectors
 
@@ -388,9 +396,11 @@ def test_stacked_single_launch_step_matches_stacked_two_kernel_path_and_oracle(d
                                              ((2, 16, 256, 256), 'bf16', 'js'), ((2, 16, 256, 256), 'bf16', 'var'),
                                              ((5, 16, 128, 128), 'f32', 'var'), ((40, 16, 256, 256), 'f32', 'var')])
 def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, dtype, reg):
-    """csrc/step_l2.cu: forward and backward of each heatmap back to back in one persistent kernel (BASELINE config 5:
-    256x256 with the variance regulariser).  Against the two-kernel path it must agree to rounding -- it runs the same
-    device code -- and against the fp64 oracle to the usual tolerance."""
+    """Heatmaps of which fewer than four fit in one CTA's shared memory (BASELINE config 5: 256x256 with the variance
+    regulariser).  256x256 fp32 with no / the variance regulariser: csrc/step_pair.cu, a cluster of two CTAs holding half a
+    heatmap each, partial results exchanged through distributed shared memory.  The rest: csrc/step_l2.cu, forward and
+    backward of each heatmap back to back in one persistent kernel -- the same device code as the two-kernel path, so the
+    results agree bit for bit.  Both against the fp64 oracle to the usual tolerance."""
     from dsnt_pose2d_b200 import _lib
     b, c, h, w = shape
     gen = torch.Generator().manual_seed(91)
@@ -403,8 +413,14 @@ def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, 
     got = run_step(dp, z, target, mask, reg)
     assert _lib.launch_count - before == 4          # mask count, step, finishing reduction, scale: not fwd + finish + bwd
     two = run_step(dp, z, target, mask, reg, one_pass=False)
-    assert got['loss'] == two['loss'] and np.array_equal(got['coords'], two['coords'])
-    assert rel_l2(got['dz'], two['dz']) < (4e-3 if dtype == 'bf16' else 1e-6)
+    pair = bool(_lib.LIB.dsnt_head_step_pair_supported(0 if dtype == 'f32' else 1, h, w, _lib.REG_IDS[reg]))
+    assert pair == (dtype == 'f32' and (h, w) == (256, 256))
+    if pair:
+        assert abs(got['loss'] - two['loss']) < 3e-6 * abs(two['loss'])
+        assert float(np.abs(got['coords'] - two['coords']).max()) < 2e-6
+    else:
+        assert got['loss'] == two['loss'] and np.array_equal(got['coords'], two['coords'])
+    assert rel_l2(got['dz'], two['dz']) < (4e-3 if dtype == 'bf16' else 3e-6)
     n_chk = min(b, 3)
     ref = tp.head_loss_and_grad(z.float()[:n_chk], target[:n_chk], mask[:n_chk], reg, 1.0, 1.0, dtype=torch.float64)
     scale = mask[:n_chk].sum().clamp(min=1).item() / mask.sum().clamp(min=1).item()
