@@ -333,9 +333,10 @@ static int launch_pair(const PairParams& p, cudaStream_t stream) {
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     probe.attrs = at; probe.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, kern, &probe) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = 64; }
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &probe) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = -1; }
     max_clusters = nc;
   }
+  if (max_clusters < 0) return 1;      // clusters of this size cannot run here
   long clusters = p.n < max_clusters ? p.n : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters)); cfg.blockDim = dim3(kPairThreads);
@@ -344,7 +345,11 @@ static int launch_pair(const PairParams& p, cudaStream_t stream) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return check_launch("head_step_pair_kernel");
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) {
+    // no room for a cluster of two 224 KiB CTAs on this device / partition: not an error, the caller takes another kernel
+    cudaGetLastError();
+    return 1;
+  }
   return check_launch("head_step_pair_kernel");
 }
 
