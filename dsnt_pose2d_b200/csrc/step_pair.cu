@@ -2,14 +2,15 @@
 //
 // A 256x256 fp32 heatmap is 256 KiB: more than the 227 KiB of shared memory one CTA can have, which is why config 5 ran the
 // two-kernel path at 12 bytes per pixel.  A thread-block CLUSTER of two CTAs has 2 x 227 KiB: each CTA of the pair takes
-// one half of the heatmap (128 rows, 128 KiB, TMA bulk loads into its own shared memory), sweeps it for the maximum,
-// the sums and -- writing e = 2^(z log2e - max) back in place -- the gradient, and the pair exchanges its per-half partial
-// results through DISTRIBUTED SHARED MEMORY (each CTA reads the other's slot after a cluster barrier, both add in rank
-// order, so both hold bit-identical totals).  HBM sees every logit once: 8 bytes per pixel.
+// one half of the heatmap (128 rows, 128 KiB, TMA bulk loads into its own shared memory), reads it ONCE into the registers
+// of its 1024 threads (32 per thread) taking the maximum on the way, turns it into e = 2^(z log2e - max) there, and writes
+// the gradient from there; the pair exchanges its per-half partial results through DISTRIBUTED SHARED MEMORY (each CTA
+// stores into the other's shared memory, both merge in rank order, so both hold bit-identical totals).  HBM sees every
+// logit once: 8 bytes per pixel; shared memory is written once (by the TMA) and read once per heatmap.
 //
 // The shared memory of a CTA is a ring of seven 32 KiB chunk buffers; a half heatmap takes four, so while heatmap k is
-// being processed three chunks of heatmap k+1 are already loading, and when k is done its four buffers take the last chunk
-// of k+1 and the first three of k+2: the loads of the next heatmap overlap the arithmetic of this one.
+// being processed three chunks of heatmap k+1 are already loading, and as soon as k has been read into registers its four
+// buffers take the last chunk of k+1 and the first three of k+2: the loads of the next heatmaps overlap all the arithmetic.
 //
 // Same mathematics as head_step2.cuh (src/dsnt/nn.py:25-116,274-298, src/dsnt/model.py:24-63,145):
 // column accumulators + one row sum per sweep step give S, S_x, S_y and the variance about the mean without a second look;
@@ -133,12 +134,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
 
   for (long k = 0; k < nk; ++k) {
     const long hm = cluster_id + k * n_clusters;
-    // the four chunk buffers of this heatmap (byte offsets of this thread's vectors) -- sweep step it reads chunk it / 2
-    const unsigned g0 = static_cast<unsigned>(4 * k);
-    unsigned off[kPairIters];
-#pragma unroll
-    for (int it = 0; it < kPairIters; ++it)
-      off[it] = ((g0 + it / 2) % kPairSlots) * kPairChunkBytes + (it & 1) * (kPairChunkBytes / 2) + tid * 16;
+    const unsigned g0 = static_cast<unsigned>(4 * k);       // chunk number of this heatmap's first chunk
     float tx = 0.f, ty = 0.f;
     if (p.target) {
       const float2 tt = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
@@ -146,21 +142,29 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     }
     const float wgt = (p.mask ? __ldg(p.mask + hm) : 1.0f) * inv_denom;
 
-    // ---------------------------------------------------------------- maximum (waits for each chunk on first touch)
+    // ---------------------------------------------------------------- the half heatmap comes into REGISTERS (32 per thread)
+    // and its maximum is taken on the way; shared memory is read exactly once, so its buffers are free for the next loads
+    // as soon as this sweep is over
+    f2 ev[kPairIters][2];
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int it = 0; it < kPairIters; ++it) {
-      if ((it & 1) == 0) {
-        const unsigned g = g0 + it / 2;
-        mbar_wait(bars_s + 8 * (g % kPairSlots), (g / kPairSlots) & 1u);
-      }
-      const uint4 r = *reinterpret_cast<const uint4*>(pair_smem + off[it]);
+      const unsigned g = g0 + it / 2, slot = g % kPairSlots;
+      if ((it & 1) == 0) mbar_wait(bars_s + 8 * slot, (g / kPairSlots) & 1u);
+      const uint4 r = *reinterpret_cast<const uint4*>(pair_smem + slot * kPairChunkBytes + (it & 1) * (kPairChunkBytes / 2) + tid * 16);
+      unpack_pairs<float>(r, ev[it]);
       m0 = fmaxf(m0, fmaxf(__uint_as_float(r.x), __uint_as_float(r.y)));
       m1 = fmaxf(m1, fmaxf(__uint_as_float(r.z), __uint_as_float(r.w)));
     }
     float mloc = warp_max_redux(fmaxf(m0, m1));
     if (lane == 0) red[warp][0] = mloc;
     __syncthreads();
+    // every thread has its data: this heatmap's four buffers take the last chunk of the next heatmap and the first three of
+    // the one after it (nothing was written to them by the generic proxy, so no proxy fence)
+    if (tid == 0) {
+      issue(k + 1, 3);
+      for (int c = 0; c < 3; ++c) issue(k + 2, c);
+    }
     mloc = warp_max_redux(red[lane][0]);
     __syncthreads();                                  // red is free again
     // Each half is summed relative to ITS OWN maximum; the halves are merged afterwards like two blocks of an online
@@ -168,23 +172,17 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     const float m2h = mloc * kLog2e;
     const f2 nm2 = pk1(-m2h);
 
-    // ---------------------------------------------------------------- sums; e goes back into the buffer
+    // ---------------------------------------------------------------- sums; e replaces z in the registers
     f2 colE[2] = {pk1(0.f), pk1(0.f)};
-    float rsk[kVar ? kPairIters : 1];
     float Sy = 0.f;
 #pragma unroll
     for (int it = 0; it < kPairIters; ++it) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(pair_smem + off[it]);
-      f2 v[2], e[2];
-      unpack_pairs<float>(raw, v);
-      e[0] = ex2_2(fma2(v[0], l2e2, nm2));
-      e[1] = ex2_2(fma2(v[1], l2e2, nm2));
-      colE[0] = add2(colE[0], e[0]);
-      colE[1] = add2(colE[1], e[1]);
-      const float rs = hsum(add2(e[0], e[1]));
+      ev[it][0] = ex2_2(fma2(ev[it][0], l2e2, nm2));
+      ev[it][1] = ex2_2(fma2(ev[it][1], l2e2, nm2));
+      colE[0] = add2(colE[0], ev[it][0]);
+      colE[1] = add2(colE[1], ev[it][1]);
+      const float rs = hsum(add2(ev[it][0], ev[it][1]));
       Sy = fmaf(rs, y0 + static_cast<float>(it) * dyi, Sy);
-      if constexpr (kVar) rsk[it] = rs;
-      *reinterpret_cast<uint4*>(pair_smem + off[it]) = pack_pairs<float>(e);
     }
     float c0, c1, c2, c3;
     upk(colE[0], c0, c1);
@@ -206,7 +204,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
 #pragma unroll
       for (int it = 0; it < kPairIters; ++it) {
         const float d = (y0 + static_cast<float>(it) * dyi) - myh;
-        ayh = fmaf(rsk[it] * d, d, ayh);
+        ayh = fmaf(hsum(add2(ev[it][0], ev[it][1])) * d, d, ayh);      // the row sum again, from registers
       }
       float z0 = 0.f, z1 = 0.f;
       pair_block_sum4(axh, ayh, z0, z1, red, warp, lane);
@@ -285,27 +283,17 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       uint4* dzv = reinterpret_cast<uint4*>(p.dz + hm * hm_floats) + static_cast<size_t>(rank) * (kPairHalfBytes / 16);
 #pragma unroll
       for (int it = 0; it < kPairIters; ++it) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(pair_smem + off[it]);
-        f2 e[2], o[2];
-        unpack_pairs<float>(raw, e);
+        f2 o[2];
         const float y = y0 + static_cast<float>(it) * dyi;
         float rc = fmaf(bS, y, cbS);
         if (kVar) { const float d = y - muy; rc = fmaf(kyS * d, d, rc); }
         const f2 rc2 = pk1(rc);
-        o[0] = mul2(e[0], add2(acol[0], rc2));
-        o[1] = mul2(e[1], add2(acol[1], rc2));
+        o[0] = mul2(ev[it][0], add2(acol[0], rc2));
+        o[1] = mul2(ev[it][1], add2(acol[1], rc2));
         dzv[it * kPairThreads + tid] = pack_pairs<float>(o);
       }
     }
 
-    // ---------------------------------------------------------------- this heatmap's four buffers are free: they take the
-    // last chunk of the next heatmap and the first three of the one after it
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      issue(k + 1, 3);
-      for (int c = 0; c < 3; ++c) issue(k + 2, c);
-    }
   }
   cluster.sync();      // neither CTA leaves while the other may still store into its shared memory
 }
