@@ -426,3 +426,30 @@ def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, 
     scale = mask[:n_chk].sum().clamp(min=1).item() / mask.sum().clamp(min=1).item()
     assert float(np.abs(got['coords'][:n_chk] - ref['coords'].numpy()).max()) < TOL
     assert rel_l2(got['dz'][:n_chk], ref['dz'].numpy() * scale) < (4e-3 if dtype == 'bf16' else TOL)
+
+
+@pytest.mark.parametrize('n,reg,with_mask', [(1, 'var', True), (3, 'none', False), (75, 'var', False), (149, 'none', True)])
+def test_pair_step_edge_counts(dp, tp, n, reg, with_mask):
+    """csrc/step_pair.cu with fewer heatmaps than clusters, one more than the clusters (74 on a B200), and an odd count;
+    without a mask; peaked logits in one half only (the halves are merged like blocks of an online softmax)."""
+    gen = torch.Generator().manual_seed(95)
+    z = torch.randn(n, 1, 256, 256, generator=gen)
+    z[:, :, 200:210, 30:40] += 8.0                     # most of the mass in the lower half: the upper half's scale is ~2^-11
+    if n > 1:
+        z[1, :, 200:210, 30:40] -= 8.0
+        z[1, :, 2:6, 248:252] += 10.0                  # ... and one heatmap with it in the upper half
+    target = torch.rand(n, 1, 2, generator=gen) * 1.6 - 0.8
+    mask = (torch.rand(n, 1, generator=gen) > 0.3).float() if with_mask else None
+    if with_mask:
+        mask[0] = 1.0
+    got = run_step(dp, z, target, mask, reg)
+    two = run_step(dp, z, target, mask, reg, one_pass=False)
+    assert abs(got['loss'] - two['loss']) < 3e-6 * abs(two['loss'])
+    assert float(np.abs(got['coords'] - two['coords']).max()) < 2e-6
+    assert rel_l2(got['dz'], two['dz']) < TOL          # two fp32 evaluations of very peaked maps; the oracle below is the arbiter
+    k = min(n, 2)
+    ref = tp.head_loss_and_grad(z[:k], target[:k], None if mask is None else mask[:k], reg, 1.0, 1.0, dtype=torch.float64)
+    denom_all = float(n) if mask is None else max(mask.sum().item(), 1.0)
+    denom_k = float(k) if mask is None else max(mask[:k].sum().item(), 1.0)
+    assert float(np.abs(got['coords'][:k] - ref['coords'].numpy()).max()) < TOL
+    assert rel_l2(got['dz'][:k], ref['dz'].numpy() * (denom_k / denom_all)) < TOL
