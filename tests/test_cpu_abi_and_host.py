@@ -116,3 +116,81 @@ def test_shard_range_partitions_the_batch():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(8, 2, 2)
+
+
+def test_step_support_queries_are_host_logic(libpath):
+    """Which kernel serves which case is decided on the host (no GPU needed): the shared-memory ring, the 64x64
+    single-launch kernel with its Gaussian-window register slots, the cluster-of-two-CTAs kernel for 256x256 fp32."""
+    from dsnt_pose2d_b200 import _lib
+    lib, reg = _lib.LIB, _lib.REG_IDS
+    f32, bf16 = _lib.DTYPE_F32, _lib.DTYPE_BF16
+    # at least four heatmaps in 224 KiB of shared memory, 16-byte vectors
+    assert lib.dsnt_head_step_supported(f32, 64, 64) == 1 and lib.dsnt_head_step_supported(bf16, 128, 128) == 1
+    assert lib.dsnt_head_step_supported(f32, 128, 128) == 0 and lib.dsnt_head_step_supported(f32, 256, 256) == 0
+    assert lib.dsnt_head_step_supported(f32, 7, 7) == 0 and lib.dsnt_head_step_supported(5, 64, 64) == 0
+    # single-launch form: 64x64, not KL, and the widest possible Gaussian window must fit the register slots
+    sigma_1px = 2.0 / 64
+    for r in ('none', 'var', 'js', 'mse'):
+        assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg[r], sigma_1px) == 1
+        assert lib.dsnt_head_step_fused_supported(bf16, 64, 64, reg[r], sigma_1px) == 1
+        assert lib.dsnt_head_step_fused_supported(f32, 32, 32, reg[r], 2.0 / 32) == 0
+    assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg['kl'], sigma_1px) == 0
+    assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg['js'], 20 * sigma_1px) == 0      # window = whole image
+    assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg['var'], 20 * sigma_1px) == 1     # no window to fit
+    # 256x256 fp32: a pair of CTAs, without a Gaussian window
+    assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['var']) == 1
+    assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['none']) == 1
+    assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['js']) == 0
+    assert lib.dsnt_head_step_pair_supported(bf16, 256, 256, reg['var']) == 0
+    assert lib.dsnt_head_step_pair_supported(f32, 128, 128, reg['var']) == 0
+    assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['var']) == 1
+    assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['js']) == 0
+    assert lib.dsnt_head_step_supported_reg(bf16, 256, 256, reg['js']) == 1                      # L2-staged form
+    # exchange buffer of the peer reductions: two parities x 16 ranks x float4
+    assert lib.dsnt_peer_exchange_bytes() == 2 * 16 * 16
+    assert lib.dsnt_finish_workspace_bytes() >= (256 * 4 + 4 + 256) * 4
+
+
+def test_peer_entry_points_validate_their_arguments(libpath):
+    from dsnt_pose2d_b200 import _lib
+    lib = _lib.LIB
+    buf = (ctypes.c_float * 2048)()
+    addr = ctypes.addressof(buf)
+    peers = (ctypes.c_void_p * 2)(addr, addr + 1024)
+    pp = ctypes.cast(peers, ctypes.c_void_p)
+    assert lib.dsnt_mask_count_peer(None, 4, addr, addr, pp, 0, 17, addr, addr, None) == -1      # too many ranks
+    assert 'at most 16' in _lib.last_error()
+    assert lib.dsnt_mask_count_peer(None, 4, addr, addr, pp, 2, 2, addr, addr, None) == -1       # rank out of range
+    assert lib.dsnt_mask_count_peer(None, 4, addr, addr, None, 0, 2, addr, addr, None) == -1     # no peer table
+    bad = (ctypes.c_void_p * 2)(addr, None)
+    assert lib.dsnt_finish_loss_peer(addr, None, 4, 1, 1.0, addr, addr, ctypes.cast(bad, ctypes.c_void_p), 0, 2, addr, addr,
+                                     None) == -1
+    assert 'rank 1' in _lib.last_error()
+    assert lib.dsnt_head_step_fused(addr, 0, 4, 64, 64, addr, None, None, 1.0, _lib.REG_IDS['kl'], 2.0 / 64, 0, addr, addr,
+                                    addr, addr, addr, None) == -2                               # KL: three-launch form
+    assert lib.dsnt_head_step_fused(addr, 0, 4, 64, 64, addr, None, None, 1.0, 0, 1.0, 0, addr, addr, addr, None, addr,
+                                    None) == -1                                                 # no loss block
+
+
+def test_one_pass_dispatch_rule_without_gpu():
+    """head._step_pays: the one-pass step is taken where it saves launches or where the logits no longer sit in L2."""
+    from dsnt_pose2d_b200 import head, _lib
+
+    class FakeZ:                        # only what the rule looks at
+        def __init__(self, n, h, w, dtype):
+            self.shape, self.dtype, self._n = (n, h, w), dtype, n * h * w
+            self.device = torch.device('cpu')
+
+        def numel(self):
+            return self._n
+
+        def element_size(self):
+            return 4 if self.dtype == torch.float32 else 2
+
+    js, kl = _lib.REG_IDS['js'], _lib.REG_IDS['kl']
+    small, big = FakeZ(512, 64, 64, torch.float32), FakeZ(65536, 64, 64, torch.float32)
+    assert head._step_pays(small, 64, 64, js, 2.0 / 64, None)            # single-launch form: always
+    assert not head._step_pays(small, 64, 64, kl, 2.0 / 64, None)        # KL, 8 MiB: two kernels are one launch fewer
+    assert head._step_pays(big, 64, 64, kl, 2.0 / 64, None)              # KL, 1 GiB: the saved read pays
+    odd = FakeZ(1024, 28, 28, torch.float32)
+    assert not head._step_pays(odd, 28, 28, js, 2.0 / 28, None)
