@@ -23,7 +23,13 @@
 //    exactly; bf16 heatmaps: as fp16 of e * 2^15, 11 significant bits for e >= 2e-9, against the 8 of the bf16 dz it
 //    produces) and the backward sweep is LDS, add, mul, store -- the profile of the first version of this kernel showed
 //    the XU pipe (MUFU.EX2) at 76 % with DRAM at 67 %, i.e. the second exponential per pixel was what bound it.  The
-//    window vectors are left alone (the window pass needs the logits themselves).
+//    window vectors are left alone (the window pass needs the logits themselves);
+//  * bulk loads are PACED (pace_reserve / PendingLoad below): a slot schedule per CTA breaks the convoy in which all warps
+//    wait for data, finish together and re-issue loads and stores together (copy through the ring: 0.91 -> 1.01 of the
+//    measured HBM peak; fp32 JS step 357 -> 334 us);
+//  * single-launch form (p.out8): the mask count (CTA slices + grid barrier) and masked_average + loss composition (last
+//    ticket) run inside this kernel; with p.xc.world > 1 both cross the ranks of a sharded batch through peer memory;
+//    p.st.count > 1 walks the stacks of a stacked hourglass.
 //
 // Same mathematics and the same closed forms as head_step.cuh (src/dsnt/nn.py:25-116,168-298,
 // src/dsnt/model.py:24-63,145); the ring of shared-memory buffers, the bulk loads and the barrier protocol are shared
