@@ -56,7 +56,7 @@ struct PairParams {
 };
 
 // sum over the 1024 threads of one CTA of up to four values, identical on every thread, fixed order
-__device__ __forceinline__ void pair_block_sum4(float& a, float& b, float& c, float& d, float (*red)[4], int warp, int lane) {
+__device__ __forceinline__ void pair_block_sum4(float& a, float& b, float& c, float& d, float (*red)[8], int warp, int lane) {
   const float k = warp_sum4_transposed(a, b, c, d, lane);
   if ((lane & 7) == 0) red[warp][lane >> 3] = k;
   __syncthreads();
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
   constexpr float tow = 2.0f / kPairW, bw = 1.0f / kPairW - 1.0f, toh = 2.0f / kPairH, bh = 1.0f / kPairH - 1.0f;
   extern __shared__ __align__(128) unsigned char pair_smem[];
   __shared__ __align__(8) unsigned long long bars[kPairSlots];
-  __shared__ float red[32][4];
+  __shared__ float red[32][8];
   __shared__ __align__(16) float xin[2][4];               // the PEER's partial results, stored here by the peer (st.async over DSMEM)
   __shared__ __align__(8) unsigned long long xbar[1];     // ... the two stores completing 32 bytes on this mbarrier
 
@@ -189,25 +189,45 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     upk(colE[1], c2, c3);
     float Sh = (c0 + c1) + (c2 + c3);
     float Sxh = fmaf(c0, xs[0], fmaf(c1, xs[1], fmaf(c2, xs[2], c3 * xs[3])));
-    float Syh = Sy, zero = 0.f;
-    pair_block_sum4(Sh, Sxh, Syh, zero, red, warp, lane);
-    // variance: second moments of this half about ITS OWN mean, merged with the other half's by the parallel-variance
-    // formula (Chan et al.): no E[x^2] - mu^2 anywhere
+    float Syh = Sy;
     float axh = 0.f, ayh = 0.f;
-    if constexpr (kVar) {
-      const float ih = rcp(Sh);
-      const float mxh = Sxh * ih, myh = Syh * ih;
+    if constexpr (!kVar) {
+      float zero = 0.f;
+      pair_block_sum4(Sh, Sxh, Syh, zero, red, warp, lane);
+    } else {
+      // Variance: second moments about the WARP's own mean first, then ONE block-wide reduction that merges the 32 warps
+      // by the parallel-variance formula (Chan et al.): M2 = sum_w [M2_w + S_w (mu_w - mu)^2] -- no E[x^2] - mu^2 anywhere,
+      // and no second pair of block barriers for the moments.
+      const float kw = warp_sum4_transposed(Sh, Sxh, Syh, 0.f, lane);
+      const float Sw = __shfl_sync(kFull, kw, 0), Sxw = __shfl_sync(kFull, kw, 8), Syw = __shfl_sync(kFull, kw, 16);
+      const float iw = Sw > 0.f ? rcp(Sw) : 0.f;
+      const float mxw = Sxw * iw, myw = Syw * iw;
+      float axt, ayt = 0.f;
       {
-        const float d0 = xs[0] - mxh, d1 = xs[1] - mxh, d2 = xs[2] - mxh, d3 = xs[3] - mxh;
-        axh = fmaf(c0 * d0, d0, fmaf(c1 * d1, d1, fmaf(c2 * d2, d2, c3 * d3 * d3)));
+        const float d0 = xs[0] - mxw, d1 = xs[1] - mxw, d2 = xs[2] - mxw, d3 = xs[3] - mxw;
+        axt = fmaf(c0 * d0, d0, fmaf(c1 * d1, d1, fmaf(c2 * d2, d2, c3 * d3 * d3)));
       }
 #pragma unroll
       for (int it = 0; it < kPairIters; ++it) {
-        const float d = (y0 + static_cast<float>(it) * dyi) - myh;
-        ayh = fmaf(hsum(add2(ev[it][0], ev[it][1])) * d, d, ayh);      // the row sum again, from registers
+        const float d = (y0 + static_cast<float>(it) * dyi) - myw;
+        ayt = fmaf(hsum(add2(ev[it][0], ev[it][1])) * d, d, ayt);      // the row sum again, from registers
       }
-      float z0 = 0.f, z1 = 0.f;
-      pair_block_sum4(axh, ayh, z0, z1, red, warp, lane);
+      const float km = warp_sum2_transposed(axt, ayt, lane);
+      const float axw = __shfl_sync(kFull, km, 0), ayw = __shfl_sync(kFull, km, 16);
+      if (lane == 0) {
+        red[warp][0] = Sw; red[warp][1] = Sxw; red[warp][2] = Syw; red[warp][3] = axw; red[warp][4] = ayw;
+      }
+      __syncthreads();
+      // every warp merges the 32 per-warp results (lane l holds warp l's) with the same butterflies
+      const float Sl = red[lane][0], Sxl = red[lane][1], Syl = red[lane][2], axl = red[lane][3], ayl = red[lane][4];
+      const float kb = warp_sum4_transposed(Sl, Sxl, Syl, 0.f, lane);
+      Sh = __shfl_sync(kFull, kb, 0); Sxh = __shfl_sync(kFull, kb, 8); Syh = __shfl_sync(kFull, kb, 16);
+      const float ih = rcp(Sh);                       // > 0: the half's maximum contributes 1
+      const float il = Sl > 0.f ? rcp(Sl) : 0.f;
+      const float dxl = Sxl * il - Sxh * ih, dyl = Syl * il - Syh * ih;
+      const float kc = warp_sum2_transposed(fmaf(Sl * dxl, dxl, axl), fmaf(Sl * dyl, dyl, ayl), lane);
+      axh = __shfl_sync(kFull, kc, 0); ayh = __shfl_sync(kFull, kc, 16);
+      __syncthreads();                                // red may be reused
     }
     const uint32_t xphase = static_cast<uint32_t>(k) & 1u;
     if (tid == 0) send(m2h, Sh, Sxh, Syh, axh, ayh);
