@@ -1,31 +1,40 @@
 #!/usr/bin/env python
 """bench.py -- DSNT head throughput (heatmaps/s, fwd+bwd+regulariser) and fraction of the HBM roofline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
 
-Workload (BASELINE.json configs[3], the one the metric is quoted on): per GPU a batch of 4096 samples x 16
-MPII joints x 64x64 fp32 logits, Euclidean loss + JS regulariser (sigma = 1 px), joint mask; weak scaling
-(every rank owns a fixed 4096-sample shard of a 4096*N batch; the three partial sums of masked_average are
-exchanged between the ranks inside the finishing kernels over NVLink peer memory, or by NCCL where that is unavailable).
+Workload (BASELINE.json configs[3], the one the metric is quoted on): a batch of 4096 samples x 16 MPII joints x 64x64
+fp32 logits, Euclidean loss + JS regulariser (sigma = 1 px), joint mask.
 
-A "step" is one pass of the hot path over one batch: fused forward (coords, loss) + backward (dL/dZ), through the
-public autograd API (`dsnt_head(...).loss.backward()`).  --path one-pass (default) lets the forward also write dL/dZ
-while the heatmap is on chip (dsnt_head_step: 2*H*W*sizeof algorithmic bytes per heatmap); --path two-kernel is the
-forward kernel + the streaming backward kernel (3*H*W*sizeof).  Heatmaps too large for the one-pass kernel
-(256x256) take the two-kernel path either way; config.path says which ran.
-  value  whole-job heatmaps/s with Z already resident in HBM (CUDA events, barrier + sync both sides, max
-         over ranks).  Z is 1 GiB per step, far larger than the 126 MB L2, so no flush is needed.
-  e2e    the same step through the public API with HOST buffers: pinned Z/target/mask -> device copies
-         in, loss + coords device -> host out, all inside the timed region.
-  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+  --scaling weak   (default; the line of record) every rank owns a fixed 4096-sample shard of a 4096*N batch;
+  --scaling strong the batch of 4096 is sliced over the N ranks (`parallel.shard`, BASELINE configs[3] as written).
+  The default run measures BOTH: the JSON line is the weak one and carries the strong measurement under "strong".
+  The three partial sums of masked_average (src/dsnt/nn.py:81-94) are exchanged between the ranks inside the kernels over
+  NVLink peer memory (NCCL all-reduce where that is unavailable); every rank must end with the bit-identical loss, which the
+  bench asserts ("loss_identical_on_all_ranks").
 
---impl reference times the reference's CPU implementation of the same path on this box's host cores.
-The reference is pure Python on torch; its tree is not on the GPU box, so this arm executes the committed
-restatement oracle/torch_port.py (the only place besides the cpu_baseline leg where bench.py executes oracle/).
+A "step" is one pass of the hot path over one batch: fused forward (coords, loss) + backward (dL/dZ), through the public
+autograd API (`dsnt_head(...).loss.backward()`).  --path one-pass (default) lets the forward also write dL/dZ while the
+heatmap is on chip (2*H*W*sizeof algorithmic bytes per heatmap); --path two-kernel is the forward kernel + the streaming
+backward kernel (3*H*W*sizeof).  config.path says which ran.
+  value     whole-job heatmaps/s with Z already resident in HBM (CUDA events, barrier + sync both sides, max over ranks).
+  e2e       the same step through the public API with HOST buffers: pinned Z/target/mask -> device copies in, loss +
+            coords device -> host out, all inside the timed region.
+  roofline / cpu_baseline / clocks: DESIGN.md "Measurement".
+  extra_workloads (N = 1): the other BASELINE workloads through the same public API, each with its own roofline --
+            cfg4 bf16 JS, cfg4 fp32 variance, cfg5 256x256 fp32 variance, and the launch-bound head steps of cfg1 / cfg2 / cfg3.
+  gpu_eager_baseline (N = 1): the reference's own op chain (src/dsnt/nn.py on CUDA tensors, eager torch) on this GPU:
+            "what a user gets today" (BASELINE.md section 3); a labelled baseline, not the CPU baseline.
+  self_check: this run's loss / coords / dL/dZ against the two-kernel path and against the CPU reference on a sample.
+
+--impl reference times the reference's CPU implementation of the same path on this box's host cores: the UNMODIFIED
+reference installed under baseline/_ref (tools/install_ref.sh; `kind: "reference"`), else the committed restatement
+oracle/torch_port.py (`kind: "port"`).
 """
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -38,17 +47,26 @@ sys.path.insert(0, ROOT)
 RESULT_OUT = sys.stdout
 METRIC = 'dsnt_head_heatmaps_per_sec'
 UNIT = 'heatmaps/s'
+L2_BYTES = 126e6
 WORKLOADS = {
-    # name: (batch per GPU, joints, H, W, reg, dtype)
-    'cfg4_64x64_f32_js': (4096, 16, 64, 64, 'js', 'f32'),
-    'cfg4_64x64_bf16_js': (4096, 16, 64, 64, 'js', 'bf16'),
-    'cfg4_64x64_f32_var': (4096, 16, 64, 64, 'var', 'f32'),
-    'cfg5_256x256_f32_var': (512, 16, 256, 256, 'var', 'f32'),
-    'cfg1_64x64_f32_js': (32, 16, 64, 64, 'js', 'f32'),
-    'cfg2_28x28_f32_js': (64, 16, 28, 28, 'js', 'f32'),
+    # name: (batch, joints, H, W, reg, dtype, stacks)
+    'cfg4_64x64_f32_js': (4096, 16, 64, 64, 'js', 'f32', 1),
+    'cfg4_64x64_bf16_js': (4096, 16, 64, 64, 'js', 'bf16', 1),
+    'cfg4_64x64_f32_var': (4096, 16, 64, 64, 'var', 'f32', 1),
+    'cfg4_64x64_f32_kl': (4096, 16, 64, 64, 'kl', 'f32', 1),
+    'cfg4_64x64_f32_mse': (4096, 16, 64, 64, 'mse', 'f32', 1),
+    'cfg4_64x64_bf16_var': (4096, 16, 64, 64, 'var', 'bf16', 1),
+    'cfg5_256x256_f32_var': (512, 16, 256, 256, 'var', 'f32', 1),
+    'cfg5_256x256_f32_js': (512, 16, 256, 256, 'js', 'f32', 1),
+    'cfg1_64x64_f32_js': (32, 16, 64, 64, 'js', 'f32', 1),
+    'cfg2_28x28_f32_js': (64, 16, 28, 28, 'js', 'f32', 1),
+    'cfg3_8x64x64_f32_js': (32, 16, 64, 64, 'js', 'f32', 8),
 }
 DEFAULT_WORKLOAD = 'cfg4_64x64_f32_js'
-CPU_SAMPLE = (32, 16, 64, 64)          # BASELINE cfg 1 shape: what the reference's CPU path is timed on
+EXTRA_WORKLOADS = ['cfg4_64x64_bf16_js', 'cfg4_64x64_f32_var', 'cfg5_256x256_f32_var', 'cfg1_64x64_f32_js',
+                   'cfg2_28x28_f32_js', 'cfg3_8x64x64_f32_js']
+CPU_SAMPLE = (32, 16, 64, 64)          # BASELINE cfg 1 shape: what the reference's CPU path is timed on in the `ours` run
+REG_FN = {'js': 'js_reg_loss', 'kl': 'kl_reg_loss', 'mse': 'mse_reg_loss', 'var': 'variance_reg_loss'}
 
 
 def parse_args():
@@ -58,8 +76,10 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip extra_workloads, gpu_eager_baseline and the strong leg')
     ap.add_argument('--path', default='one-pass', choices=['one-pass', 'two-kernel'])
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='time eager autograd calls instead of replaying the captured step (CUDA graph)')
@@ -84,6 +104,30 @@ def committed_traffic(workload):
         return None
 
 
+def rotation(n_local, h, w, esize):
+    """How many input sets a workload rotates among so that a step never finds its logits in the 126 MB L2."""
+    step_bytes = 2 * n_local * h * w * esize
+    return 1 if step_bytes >= 2 * L2_BYTES else int(min(24, math.ceil(2.5 * L2_BYTES / max(step_bytes, 1))))
+
+
+def workload_config(name, world, scaling):
+    """The description of the workload -- identical for our arm and the reference arm (the reference arm is timed 'on your
+    arm's config'); everything specific to how an arm ran goes under other keys of the line."""
+    bsz, joints, h, w, reg, dtype, stacks = WORKLOADS[name]
+    esize = 4 if dtype == 'f32' else 2
+    per_gpu = bsz if scaling == 'weak' else int(math.ceil(bsz / world))
+    n_rot = rotation(per_gpu * joints * stacks, h, w, esize)
+    cfg = {'workload': name, 'global_batch': bsz * world if scaling == 'weak' else bsz, 'batch_per_gpu': per_gpu,
+           'heatmaps_per_gpu': per_gpu * joints * stacks, 'joints': joints, 'heatmap': [h, w], 'reg': reg,
+           'hm_sigma_px': 1.0, 'mask': True, 'stacks': stacks,
+           'parallelism': 'batch-sharded x%d (%s scaling)' % (world, scaling) if world > 1 else 'single GPU',
+           'l2_policy': ('inputs larger than L2 (%.0f MiB of logits + as much dL/dZ per GPU and step vs 126 MB L2)'
+                         % (per_gpu * joints * stacks * h * w * esize / 2 ** 20)) if n_rot == 1 else
+                        ('rotating among %d input sets (%.0f MiB touched between two uses of a set vs 126 MB L2)'
+                         % (n_rot, n_rot * 2 * per_gpu * joints * stacks * h * w * esize / 2 ** 20))}
+    return cfg
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
 
@@ -101,7 +145,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
@@ -168,45 +212,76 @@ def start_watchdog(seconds):
     timer.start()
 
 
-def launches_per_step(step, lib):
-    """Kernels of ours enqueued by one step (counted on an eager call; a graph replay launches the same set)."""
-    before = lib.launch_count
-    step()
-    return lib.launch_count - before
+# ----------------------------------------------------------------------------------------------- the reference's own code
+def load_reference():
+    """(module with the reference's dsnt.nn API, kind).  baseline/_ref is the pip-installed UNMODIFIED reference
+    (tools/install_ref.sh; git-ignored, travels to the GPU box); without it the committed restatement is used."""
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if os.path.exists(os.path.join(ref_dir, 'dsnt', 'nn.py')):
+        import warnings
+        warnings.filterwarnings('ignore')
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+        import dsnt.nn as ref_nn               # the reference's own module: pure torch
+        return ref_nn, 'reference'
+    from oracle import torch_port
+    return torch_port, 'port'
 
 
-def cpu_reference_step(tp, torch, z, target, mask, reg):
-    """One fwd+bwd of the reference's head on CPU tensors (oracle/torch_port.py restates it op for op)."""
+def reference_step(mod, kind, torch, z, target, mask, reg, hm_sigma=1.0, reg_coeff=1.0):
+    """One fwd+bwd of the reference's head on the tensors' own device; returns (loss, coords, dL/dz).
+    kind == 'reference': the reference's operators (dsnt.nn) composed exactly as its model does --
+    src/dsnt/model.py:24-30,44-45 (softmax branch of _hm_preact), :176-183 (forward_part2), :138-145 (forward_loss),
+    :47-63 (_calculate_reg_loss).  kind == 'port': oracle/torch_port.py."""
     zz = z.detach().requires_grad_(True)
-    loss, _, _, _ = tp.head_loss(zz, target, mask, reg, 1.0, 1.0)
+    if kind == 'port':
+        loss, coords, _, _ = mod.head_loss(zz, target, mask, reg, hm_sigma, reg_coeff)
+    else:
+        n_chans, h, w = zz.size(-3), zz.size(-2), zz.size(-1)
+        flat = torch.nn.functional.softmax(zz.contiguous().view(-1, h * w), dim=-1)
+        hm = flat.view(-1, n_chans, h, w)
+        coords = mod.dsnt(hm)
+        loss = mod.euclidean_loss(coords, target, mask)
+        if reg in REG_FN:
+            loss = loss + reg_coeff * getattr(mod, REG_FN[reg])(hm, target, 2.0 * hm_sigma / w, mask)
     loss.backward()
-    return loss.item()
+    return loss.detach(), coords.detach(), zz.grad
+
+
+def synth(torch, b, c, h, w, seed, device='cpu', dtype=None):
+    g = torch.Generator(device=device).manual_seed(seed)
+    z = torch.randn(b, c, h, w, generator=g, device=device)
+    if dtype is not None:
+        z = z.to(dtype)
+    target = torch.rand(b, c, 2, generator=g, device=device) * 1.6 - 0.8
+    mask = (torch.rand(b, c, generator=g, device=device) > 0.1).float()
+    return z, target, mask
 
 
 def run_cpu_baseline(reg, budget_s=12.0, max_iters=10):
     import torch
-    from oracle import torch_port as tp
+    mod, kind = load_reference()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     b, c, h, w = CPU_SAMPLE
-    g = torch.Generator().manual_seed(0)
-    z = torch.randn(b, c, h, w, generator=g)
-    target = torch.rand(b, c, 2, generator=g) * 1.6 - 0.8
-    mask = (torch.rand(b, c, generator=g) > 0.1).float()
+    z, target, mask = synth(torch, b, c, h, w, 0)
     for _ in range(2):
-        cpu_reference_step(tp, torch, z, target, mask, reg)
+        reference_step(mod, kind, torch, z, target, mask, reg)
     times = []
     t_start = time.perf_counter()
+    res = None
     while len(times) < max_iters and (time.perf_counter() - t_start < budget_s or len(times) < 3):
         t0 = time.perf_counter()
-        cpu_reference_step(tp, torch, z, target, mask, reg)
+        res = reference_step(mod, kind, torch, z, target, mask, reg)
         times.append(time.perf_counter() - t0)
     times.sort()
     med = times[len(times) // 2]
-    return {'value': b * c / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+    what = ('the unmodified reference (baseline/_ref: dsnt.nn composed as src/dsnt/model.py does)' if kind == 'reference'
+            else 'oracle/torch_port.py')
+    return {'value': b * c / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind,
             'sample': '%d iterations of fwd+bwd on %dx%dx%dx%d fp32 (BASELINE cfg 1 shape), euclid + %s + mask, '
-                      'oracle/torch_port.py on torch CPU, median %.1f ms/iter' % (len(times), b, c, h, w, reg,
-                                                                                  med * 1e3)}
+                      '%s on torch CPU, median %.1f ms/iter' % (len(times), b, c, h, w, reg, what, med * 1e3)}, \
+        (z, target, mask, res)
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -215,34 +290,49 @@ def main_reference(args):
     if rank != 0:
         return 0
     import torch
-    from oracle import torch_port as tp
-    bsz, joints, h, w, reg, dtype = WORKLOADS[args.workload]
+    mod, kind = load_reference()
+    world = max(1, int(os.environ.get('WORLD_SIZE', str(args.gpus))))
+    bsz, joints, h, w, reg, dtype, stacks = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    b, c = CPU_SAMPLE[0], CPU_SAMPLE[1]
-    if h * w > 64 * 64:
-        b = max(1, b * 64 * 64 // (h * w))
-    g = torch.Generator().manual_seed(0)
-    z = torch.randn(b, c, h, w, generator=g)
-    target = torch.rand(b, c, 2, generator=g) * 1.6 - 0.8
-    mask = (torch.rand(b, c, generator=g) > 0.1).float()
+    # How much of the workload one step can carry: time a 512-heatmap probe, then take the largest sample (up to the
+    # whole per-GPU batch) that lets warmup + steps end within ~150 s and whose temporaries fit in host memory
+    # (the JS chain keeps ~50 heatmap-sized fp32 tensors alive for autograd).
+    full_b = bsz if args.scaling == 'weak' else int(math.ceil(bsz / world))
+    pb = max(1, min(full_b, 32 * 64 * 64 // (h * w)))
+    z, target, mask = synth(torch, pb, joints, h, w, 0)
+    reference_step(mod, kind, torch, z, target, mask, reg)
+    t0 = time.perf_counter()
+    reference_step(mod, kind, torch, z, target, mask, reg)
+    per_hm = (time.perf_counter() - t0) / (pb * joints)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:          # noqa: BLE001
+        avail = 32 << 30
+    by_mem = int(0.5 * avail / (60 * h * w * 4 * joints))
+    b = max(1, min(full_b, int(budget / (1.3 * per_hm * joints)), by_mem))
+    z, target, mask = synth(torch, b, joints, h, w, 0)
     for _ in range(args.warmup):
-        cpu_reference_step(tp, torch, z, target, mask, reg)
+        reference_step(mod, kind, torch, z, target, mask, reg)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(tp, torch, z, target, mask, reg)
+        reference_step(mod, kind, torch, z, target, mask, reg)
     dt = time.perf_counter() - t0
-    value = b * c * args.steps / dt
-    sample = ('each step = fwd+bwd on a %dx%dx%dx%d fp32 sample of the workload (bounded so the run ends within '
-              'minutes), oracle/torch_port.py restating src/dsnt/nn.py + model.py on torch CPU' % (b, c, h, w))
+    value = b * joints * args.steps / dt
+    what = ('the UNMODIFIED reference installed under baseline/_ref (dsnt.nn, composed as src/dsnt/model.py:24-63,138-145 does)'
+            if kind == 'reference' else 'oracle/torch_port.py restating src/dsnt/nn.py + model.py')
+    sample = ('each step = fwd+bwd on %dx%dx%dx%d fp32 (%s of the per-GPU batch of %d; bounded by the time budget of the run '
+              'and host memory), %s, torch CPU, %d threads' % (b, joints, h, w, 'ALL' if b == full_b else '%.1f %%' % (100.0 * b / full_b),
+                                                               full_b, what, torch.get_num_threads()))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'heatmap': [h, w], 'joints': joints, 'reg': reg,
-                   'sample_heatmaps_per_step': b * c, 'device': 'host CPU'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': sample},
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, world, args.scaling),
+        'sample_heatmaps_per_step': b * joints, 'whole_per_gpu_batch': b == full_b, 'device': 'host CPU',
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -252,215 +342,520 @@ def main_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
-def main_ours(args):
-    import torch
-    import torch.distributed as dist
-    import dsnt_pose2d_b200 as dp
-    from dsnt_pose2d_b200 import _lib
-    from dsnt_pose2d_b200.parallel import init_from_env
+class Ctx:
+    """What every measurement of our arm needs."""
 
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import dsnt_pose2d_b200 as dp
+        from dsnt_pose2d_b200 import _lib
+        from dsnt_pose2d_b200.parallel import init_from_env
+        self.torch, self.dist, self.dp, self.lib, self.args = torch, dist, dp, _lib, args
+        self.rank, self.local, self.world = init_from_env('nccl')
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        self.group = dist.group.WORLD if self.world > 1 else None
+        self.peak, self.peak_how = measured_peak()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+
+class Head:
+    """One workload through the public API: `n_rot` rotating input sets (so that consecutive steps of a workload smaller
+    than the L2 never find their logits there), step(i) = forward + backward on set i."""
+
+    def __init__(self, cx, name, scaling='weak', path='one-pass', group='default'):
+        torch, dp = cx.torch, cx.dp
+        self.cx, self.name, self.scaling = cx, name, scaling
+        bsz, joints, h, w, reg, dtype, stacks = WORKLOADS[name]
+        self.joints, self.h, self.w, self.reg, self.dtype, self.stacks = joints, h, w, reg, dtype, stacks
+        self.tdt = torch.float32 if dtype == 'f32' else torch.bfloat16
+        self.esize = 4 if dtype == 'f32' else 2
+        self.group = cx.group if group == 'default' else group
+        world, rank = (cx.world, cx.rank) if self.group is not None else (1, 0)
+        from dsnt_pose2d_b200.parallel import shard_range
+        if scaling == 'weak':
+            lo, hi, gb, seed = 0, bsz, bsz, 1234 + rank          # every rank its own 4096 samples
+        else:
+            lo, hi = shard_range(bsz, rank, world)               # the SAME global tensors sliced on dim 0 (SURVEY 8d)
+            gb, seed = bsz, 1234
+        self.b_local = hi - lo
+        self.n_local = self.b_local * joints * stacks
+        self.n_rot = rotation(self.n_local, h, w, self.esize)
+        self.sets = []
+        for r in range(self.n_rot):
+            g = torch.Generator(device=cx.dev).manual_seed(seed + 7919 * r)
+            target = torch.rand(gb, joints, 2, generator=g, device=cx.dev) * 1.6 - 0.8
+            mask = (torch.rand(gb, joints, generator=g, device=cx.dev) > 0.1).float()
+            zs = []
+            for _ in range(stacks):
+                if scaling == 'weak' or world == 1:
+                    zf = torch.randn(gb, joints, h, w, generator=g, device=cx.dev)
+                else:                                            # global tensor generated in slabs, only the own slice kept
+                    zf = torch.empty(hi - lo, joints, h, w, device=cx.dev)
+                    slab = 512
+                    for s0 in range(0, gb, slab):
+                        s1 = min(gb, s0 + slab)
+                        part = torch.randn(s1 - s0, joints, h, w, generator=g, device=cx.dev)
+                        a, bnd = max(lo, s0), min(hi, s1)
+                        if a < bnd:
+                            zf[a - lo:bnd - lo] = part[a - s0:bnd - s0]
+                        del part
+                zs.append(zf.to(self.tdt).requires_grad_(True))
+                del zf
+            self.sets.append((zs, target[lo:hi].contiguous(), mask[lo:hi].contiguous()))
+        from dsnt_pose2d_b200.head import step_supported
+        self.one_pass = path == 'one-pass' and step_supported(self.sets[0][0][0], reg)
+        self.last = None
+
+    def step(self, i=0):
+        zs, target, mask = self.sets[i % self.n_rot]
+        dp = self.cx.dp
+        for z in zs:
+            z.grad = None
+        if self.stacks == 1:
+            out = dp.dsnt_head(zs[0], target, mask, reg=self.reg, hm_sigma=1.0, reg_coeff=1.0, group=self.group,
+                               one_pass=self.one_pass)
+            out.loss.backward()
+            self.last = (out.loss, out.coords)
+        else:
+            coords, loss = dp.dsnt_head_stacked(zs, target, mask, reg=self.reg, hm_sigma=1.0, reg_coeff=1.0,
+                                                group=self.group, one_pass=self.one_pass)
+            loss.backward()
+            self.last = (loss, coords[-1])
+        return self.last
+
+    def free(self):
+        self.sets = []
+        self.last = None
+
+
+def capture(cx, head):
+    """One CUDA graph per rotating input set (the step has no host synchronisation); None if capture is refused."""
+    torch = cx.torch
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(max(3, head.n_rot)):
+                head.step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        graphs = []
+        for i in range(head.n_rot):
+            for z in head.sets[i][0]:
+                z.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                head.step(i)
+            graphs.append(g)
+        return graphs, 'cuda-graph replay of the public-API step'
+    except Exception as e:          # noqa: BLE001
+        torch.cuda.synchronize()
+        return None, 'eager autograd (graph capture failed: %s)' % (str(e).splitlines()[0][:120],)
+
+
+def time_steps(cx, run, steps, warmup):
+    """warm-up, barrier + sync, EXACTLY `steps` steps between two CUDA events, barrier + sync, max over ranks -> ms."""
+    torch = cx.torch
+    for i in range(warmup):
+        run(i)
+    cx.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    for i in range(steps):
+        run(i)
+    ev1.record()
+    cx.barrier()
+    return cx.max_over_ranks(ev0.elapsed_time(ev1)), t0, time.time()
+
+
+def measure(cx, head, steps, warmup, graph=True):
+    graphs, note = capture(cx, head) if graph else (None, 'eager autograd')
+    if graphs is not None:
+        run = lambda i: graphs[i % len(graphs)].replay()          # noqa: E731
+    else:
+        run = head.step
+    ms, t0, t1 = time_steps(cx, run, steps, max(warmup, 3))
+    return ms, note, graphs, (t0, t1)
+
+
+ENTRY_POINTS = ['dsnt_head_fwd', 'dsnt_head_bwd', 'dsnt_head_step', 'dsnt_head_step_fused', 'dsnt_head_step_fused_peer',
+                'dsnt_head_fwd_stacked', 'dsnt_head_bwd_stacked', 'dsnt_head_step_fused_stacked',
+                'dsnt_finish_loss', 'dsnt_finish_loss_stacked', 'dsnt_mask_count', 'dsnt_scale_unless_one',
+                'dsnt_finish_loss_peer', 'dsnt_mask_count_peer', 'dsnt_combine_loss']
+
+
+def kernel_pass(cx, head, steps):
+    """CUDA events around every launch of our kernels (on the stream they are enqueued on), eager steps; also counts them."""
+    lib = cx.lib
+    lib.event_log = {k: [] for k in ENTRY_POINTS}
+    before = lib.launch_count
+    for i in range(steps):
+        head.step(i)
+    cx.barrier()
+    launches = (lib.launch_count - before) / float(steps)
+    logs, lib.event_log = lib.event_log, None
+    return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in logs.items() if v}, launches
+
+
+def roofline_of(cx, head, kernel_ms, traffic=None):
+    """Algorithmic bytes per launch / live CUDA-event duration, for the kernels that move heatmaps."""
+    n, hw, es = head.n_local, head.h * head.w, head.esize
+    alg = {'dsnt_head_fwd': n * (hw * es + 56),          # read Z; target 8 r, coords 8 w, stats 32 w, terms 8 w
+           'dsnt_head_bwd': n * (2 * hw * es + 44),      # read Z, write dZ; stats 32 r, target 8 r, mask 4 r
+           'dsnt_head_step': n * (2 * hw * es + 68),     # read Z, write dZ; target 8 r, mask 4 r, coords/stats/terms 56 w
+           'dsnt_head_step_fused': n * (2 * hw * es + 60)}    # the same without the terms (8 w); the mask again from L2
+    alg['dsnt_head_step_fused_peer'] = alg['dsnt_head_step_fused']       # + 2 x 24 bytes to every peer
+    alg['dsnt_head_step_fused_stacked'] = alg['dsnt_head_step_fused']
+    alg['dsnt_head_fwd_stacked'] = alg['dsnt_head_fwd']
+    alg['dsnt_head_bwd_stacked'] = alg['dsnt_head_bwd']
+    ran = [k for k in alg if kernel_ms.get(k)]
+    if not ran:
+        raise RuntimeError('bench.py: none of the timed entry points ran (%r)' % (sorted(kernel_ms),))
+    dominant = max(ran, key=lambda k: kernel_ms[k])
+    per = {}
+    for k in ran:
+        ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
+        per[k] = {'ms': kernel_ms[k], 'algorithmic_bytes': alg[k], 'achieved_gbs': ach, 'frac': ach / cx.peak}
+    small = {k: v for k, v in kernel_ms.items() if k not in alg}
+    roof = {'bound': 'hbm', 'kernel': dominant, 'achieved': per[dominant]['achieved_gbs'], 'peak': cx.peak, 'unit': 'GB/s',
+            'frac': per[dominant]['frac'], 'traffic': traffic, 'peak_source': cx.peak_how, 'kernels': per,
+            'small_kernels_ms': small, 'algorithmic_bytes_per_step': sum(alg[k] for k in ran)}
+    return roof
+
+
+def path_note(head, kernel_ms):
+    if not head.one_pass or kernel_ms.get('dsnt_head_bwd') or kernel_ms.get('dsnt_head_bwd_stacked'):
+        return 'two-kernel: dsnt_head_fwd + dsnt_finish_loss + dsnt_head_bwd (3*H*W*sizeof algorithmic bytes)'
+    if kernel_ms.get('dsnt_head_step_fused_peer'):
+        how = ('dsnt_head_step_fused_peer, ONE launch per rank: mask count, step, loss composition and both exchanges between '
+               'the ranks (the count is picked up by each warp before its first backward)')
+    elif kernel_ms.get('dsnt_head_step_fused') or kernel_ms.get('dsnt_head_step_fused_stacked'):
+        how = 'dsnt_head_step_fused, ONE launch: mask count, step and loss composition'
+    else:
+        how = 'dsnt_mask_count + dsnt_head_step + dsnt_finish_loss'
+    return ('one-pass: %s (forward and dL/dZ while the heatmap is in shared memory, 2*H*W*sizeof algorithmic bytes); '
+            'backward only hands the gradient out' % how)
+
+
+def loss_identity(cx, head):
+    """Every rank must hold the bit-identical loss (the exchange adds the ranks' sums in rank order everywhere)."""
+    torch, dist = cx.torch, cx.dist
+    loss = head.last[0].detach().reshape(1).clone()
+    bits = loss.view(torch.int32)
+    if cx.world == 1:
+        return {'checked': True, 'identical': True, 'loss': float(loss.item())}
+    allb = [torch.zeros_like(bits) for _ in range(cx.world)]
+    dist.all_gather(allb, bits)
+    vals = [int(b.item()) for b in allb]
+    same = all(v == vals[0] for v in vals)
+    if not same:
+        raise RuntimeError('bench.py: the ranks disagree on the loss: %r' % (vals,))
+    return {'checked': True, 'identical': True, 'loss': float(loss.item()), 'ranks': cx.world}
+
+
+def exchange_timeline(cx, head, steps=40):
+    """Per-rank timeline of the single-launch step from the %globaltimer stamps the kernel leaves in its workspace
+    (include/dsnt_b200.h: dsnt_finish_trace_offset_bytes): where the time between the ranks goes."""
+    torch, dist, lib = cx.torch, cx.dist, cx.lib
+    ws = lib.finish_workspace(cx.dev)
+    off = lib.LIB.dsnt_finish_trace_offset_bytes() // 4
+    log = torch.zeros(steps, 16, dtype=torch.float32, device=cx.dev)
+    evs = []
+    for i in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        head.step(i)
+        e1.record()
+        log[i].copy_(ws[off:off + 16])
+        evs.append((e0, e1))
+    cx.barrier()
+    st = log.view(torch.int64).cpu()[5:]                      # [steps, 8] ns; skip the first steps
+    step_us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs[5:])
+    if int(st[:, 0].min()) == 0:
+        return None
+
+    def med(col_a, col_b):
+        d = ((st[:, col_b] - st[:, col_a]).double() / 1e3).sort().values
+        return float(d[len(d) // 2])
+    mine = {'rank': cx.rank, 'step_us_median_eager': step_us[len(step_us) // 2],
+            'start_to_local_count_us': med(0, 1), 'count_exchange_us': med(1, 2),
+            'start_to_last_cta_done_us': med(0, 3), 'loss_exchange_and_compose_us': med(3, 4),
+            'kernel_us': med(0, 4)}
+    if cx.world == 1:
+        return [mine]
+    out = [None] * cx.world
+    dist.all_gather_object(out, mine)
+    return out
+
+
+def run_e2e(cx, head, steps):
+    """The step with HOST buffers: pinned Z/target/mask -> device, fused fwd+bwd, loss + coords -> pinned host."""
+    torch, dp = cx.torch, cx.dp
+    zs, target, mask = head.sets[0]
+    z = zs[0]
+    zh = torch.empty(z.shape, dtype=head.tdt).pin_memory()
+    zh.copy_(z.detach())
+    th, mh = target.cpu().pin_memory(), mask.cpu().pin_memory()
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+    coords_h = torch.empty(tuple(z.shape[:2]) + (2,), dtype=torch.float32).pin_memory()
+    zd = torch.empty_like(z.detach())
+    td, md = torch.empty_like(target), torch.empty_like(mask)
+
+    def e2e_step(_i=0):
+        zd.copy_(zh, non_blocking=True)
+        td.copy_(th, non_blocking=True)
+        md.copy_(mh, non_blocking=True)
+        zin = zd.detach().requires_grad_(True)
+        out = dp.dsnt_head(zin, td, md, reg=head.reg, hm_sigma=1.0, reg_coeff=1.0, group=head.group, one_pass=head.one_pass)
+        out.loss.backward()
+        loss_h.copy_(out.loss.detach(), non_blocking=True)
+        coords_h.copy_(out.coords.detach(), non_blocking=True)
+        return zin.grad
+
+    e2e_steps = max(3, min(steps, 20))
+    ms, _, _ = time_steps(cx, e2e_step, e2e_steps, 3)
+    h2d = zh.numel() * head.esize + th.numel() * 4 + mh.numel() * 4
+    d2h = 4 + coords_h.numel() * 4
+    return {'value': head.n_local * cx.world * e2e_steps / (ms * 1e-3), 'unit': UNIT,
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'ms_per_step': ms / e2e_steps,
+            'note': 'pinned host Z/target/mask -> device, fused fwd+bwd, loss+coords -> pinned host; dL/dZ stays on the '
+                    'device for the backbone backward; bound by the PCIe link (%.2f GB per step)' % (h2d / 1e9)}
+
+
+def run_extra(cx, name, steps, warmup):
+    """One of the other BASELINE workloads (N = 1): value, launches, roofline of its dominant kernel, eager vs graph."""
+    torch = cx.torch
+    head = Head(cx, name, group=None)
+    ms, note, graphs, _ = measure(cx, head, steps, warmup, graph=True)
+    kernel_ms, launches = kernel_pass(cx, head, min(steps, 20))
+    entry = {'workload': name, 'config': workload_config(name, 1, 'weak'), 'dtype': head.dtype,
+             'value': head.n_local * steps / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps,
+             'launches_per_step': launches, 'launch': note, 'path': path_note(head, kernel_ms),
+             'roofline': roofline_of(cx, head, kernel_ms, None)}
+    if head.n_rot > 1:           # launch-bound: what the reference's train.py (no CUDA graphs) would see
+        ms_e, _, _ = time_steps(cx, head.step, steps, 3)
+        entry['eager_us_per_step'] = ms_e / steps * 1e3
+        entry['graph_us_per_step'] = ms / steps * 1e3
+    del graphs
+    head.free()
+    torch.cuda.empty_cache()
+    return entry
+
+
+class OpCounter:
+    """Counts ATen ops dispatched (== kernel launches to within a few) by one eager step of the reference chain."""
+
+    def __init__(self, torch):
+        from torch.utils._python_dispatch import TorchDispatchMode
+
+        class Mode(TorchDispatchMode):
+            def __init__(self):
+                super().__init__()
+                self.n = 0
+
+            def __torch_dispatch__(self, func, types, args=(), kwargs=None):
+                self.n += 1
+                return func(*args, **(kwargs or {}))
+        self.mode = Mode()
+
+
+def run_gpu_eager_baseline(cx, ours_by_name):
+    """The reference's op chain on CUDA tensors, eager torch, on this GPU ('what a user gets today')."""
+    torch = cx.torch
+    mod, kind = load_reference()
+    out = {'kind': kind, 'what': ('the unmodified reference dsnt.nn (baseline/_ref) on CUDA tensors' if kind == 'reference'
+                                  else 'oracle/torch_port.py on CUDA tensors') + ', eager torch, fwd+bwd, CUDA events',
+           'workloads': []}
+    for name, iters in (('cfg1_64x64_f32_js', 10), ('cfg4_64x64_f32_js', 3)):
+        bsz, joints, h, w, reg, dtype, stacks = WORKLOADS[name]
+        try:
+            z, target, mask = synth(torch, bsz, joints, h, w, 0, device=cx.dev)
+            for _ in range(2):
+                reference_step(mod, kind, torch, z, target, mask, reg)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                reference_step(mod, kind, torch, z, target, mask, reg)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            counter = OpCounter(torch)
+            with counter.mode:
+                reference_step(mod, kind, torch, z, target, mask, reg)
+            torch.cuda.synchronize()
+            ent = {'workload': name, 'ms_per_step': ms, 'value': bsz * joints / (ms * 1e-3), 'unit': UNIT,
+                   'aten_ops_per_step': counter.mode.n, 'iters': iters,
+                   'peak_mem_gib': torch.cuda.max_memory_allocated() / 2 ** 30}
+            if name in ours_by_name:
+                ent['ours_ms_per_step'] = ours_by_name[name]
+                ent['speedup'] = ms / ours_by_name[name]
+            out['workloads'].append(ent)
+            del z, target, mask
+        except Exception as e:          # noqa: BLE001
+            out['workloads'].append({'workload': name, 'error': str(e).splitlines()[0][:200]})
+        torch.cuda.empty_cache()
+    return out
+
+
+def self_check(cx, head, cpu_sample):
+    """The benched kernel's own output: (a) one-pass against the two-kernel path of this library on the bench inputs (a
+    slice), (b) against the CPU reference of the cpu_baseline leg on its sample."""
+    torch, dp = cx.torch, cx.dp
+    res = {}
+    zs, target, mask = head.sets[0]
+    nb = min(head.b_local, 64)
+    if nb > 0:
+        zz = zs[0][:nb].detach().clone().requires_grad_(True)
+        o1 = dp.dsnt_head(zz, target[:nb], mask[:nb], reg=head.reg, hm_sigma=1.0, one_pass=True)
+        o1.loss.backward()
+        g1 = zz.grad.float().clone()
+        zz2 = zs[0][:nb].detach().clone().requires_grad_(True)
+        o2 = dp.dsnt_head(zz2, target[:nb], mask[:nb], reg=head.reg, hm_sigma=1.0, one_pass=False)
+        o2.loss.backward()
+        g2 = zz2.grad.float()
+        res['one_pass_vs_two_kernel'] = {
+            'heatmaps': nb * head.joints, 'loss_rel': abs(o1.loss.item() - o2.loss.item()) / max(abs(o2.loss.item()), 1e-30),
+            'coords_max_abs': (o1.coords - o2.coords).abs().max().item(),
+            'dz_rel_l2': ((g1 - g2).norm() / g2.norm().clamp_min(1e-30)).item()}
+    if cpu_sample is not None and head.dtype == 'f32':
+        z, t, m, (loss, coords, dz) = cpu_sample
+        zz = z.to(cx.dev).requires_grad_(True)
+        o = dp.dsnt_head(zz, t.to(cx.dev), m.to(cx.dev), reg=head.reg, hm_sigma=1.0, one_pass=True)
+        o.loss.backward()
+        res['vs_cpu_reference_fp32'] = {
+            'heatmaps': z.shape[0] * z.shape[1], 'loss_rel': abs(o.loss.item() - loss.item()) / max(abs(loss.item()), 1e-30),
+            'coords_max_abs': (o.coords.cpu() - coords.view_as(o.coords)).abs().max().item(),
+            'dz_rel_l2': ((zz.grad.cpu() - dz).norm() / dz.norm()).item(),
+            'note': 'the CPU side is itself fp32 (1e-7 ... 4e-5 from fp64, SURVEY 7.5); the 1e-5 gate vs fp64 is in tests/'}
+        bad = [k for k in ('loss_rel', 'coords_max_abs', 'dz_rel_l2') if not (res['vs_cpu_reference_fp32'][k] < 1e-4)]
+        if bad:
+            raise RuntimeError('bench.py self-check failed: %r' % (res,))
+    return res
+
+
+def main_ours(args):
     world_env = int(os.environ.get('WORLD_SIZE', '1'))
     if args.gpus > 1 and world_env == 1:
         # launched as plain `python bench.py --gpus N`: re-exec under torchrun, one rank per GPU
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 2000), os.path.abspath(__file__)]
         return subprocess.call(cmd + sys.argv[1:])
-    rank, local, world = init_from_env('nccl')
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    group = dist.group.WORLD if world > 1 else None
-
-    bsz, joints, h, w, reg, dtype = WORKLOADS[args.workload]
-    tdt = torch.float32 if dtype == 'f32' else torch.bfloat16
-    esize = 4 if dtype == 'f32' else 2
-    n_local = bsz * joints
-    torch.manual_seed(1234 + rank)
-    z = torch.randn(bsz, joints, h, w, device=dev).to(tdt).requires_grad_(True)
-    target = torch.rand(bsz, joints, 2, device=dev) * 1.6 - 0.8
-    mask = (torch.rand(bsz, joints, device=dev) > 0.1).float()
-
-    from dsnt_pose2d_b200.head import step_supported
+    cx = Ctx(args)
+    torch, dist, lib = cx.torch, cx.dist, cx.lib
+    rank, world = cx.rank, cx.world
     from dsnt_pose2d_b200.parallel import PeerExchange
-    one_pass = args.path == 'one-pass' and step_supported(z, reg)
     exchange_note = ('inside the kernels over NVLink peer memory (no collective launch)'
-                     if PeerExchange.get(group, dev) is not None else 'by a 3-float NCCL all-reduce')
+                     if PeerExchange.get(cx.group, cx.dev) is not None else 'by a 3-float NCCL all-reduce')
 
-    def step():
-        z.grad = None
-        out = dp.dsnt_head(z, target, mask, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group, one_pass=one_pass)
-        out.loss.backward()
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- resident-input timing (pass 1: the number of record, nothing but the steps in the region)
-    graph = None
-    graph_note = 'eager autograd'
-    if args.graph:
-        # the step has no host synchronisation, so the whole fwd+bwd (and, sharded, the 3-float all-reduce) is
-        # captured once and replayed; if capture is refused the eager calls are timed instead (and said so)
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step()
-            torch.cuda.current_stream().wait_stream(side)
-            z.grad = None
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-            graph_note = 'cuda-graph replay of the public-API step'
-        except Exception as e:          # noqa: BLE001
-            graph = None
-            graph_note = 'eager autograd (graph capture failed: %s)' % (str(e).splitlines()[0][:120],)
-            torch.cuda.synchronize()
-    run_step = graph.replay if graph is not None else step
-    for _ in range(max(args.warmup, 3)):
-        run_step()
-    barrier()
-    sampler = ClockSampler(local)
+    # ---------------- the line of record: resident inputs, nothing but the steps in the timed region
+    head = Head(cx, args.workload, scaling=args.scaling, path=args.path)
+    sampler = ClockSampler(cx.local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    launches0 = _lib.launch_count
-    barrier()
-    t_wall0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        run_step()
-    ev1.record()
-    barrier()
+    elapsed_ms, graph_note, graphs, (t_wall0, _) = measure(cx, head, args.steps, args.warmup, graph=args.graph)
+    # same steps again, eager, still inside the clock-sampled window: CUDA events around every launch of our kernels
+    kernel_ms, launches_per_step = kernel_pass(cx, head, args.steps)
     t_wall1 = time.time()
-    launches = (_lib.launch_count - launches0) if graph is None else args.steps * launches_per_step(step, _lib)
-    elapsed_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = t.item()
-
-    # ---------------- pass 2 (same steps, still inside the clock-sampled window): CUDA events around every launch of
-    # our kernels, on the stream they are enqueued on, for the per-kernel roofline
-    _lib.event_log = {'dsnt_head_fwd': [], 'dsnt_head_bwd': [], 'dsnt_head_step': [], 'dsnt_head_step_fused': [],
-                      'dsnt_head_step_fused_peer': [],
-                      'dsnt_finish_loss': [], 'dsnt_mask_count': [], 'dsnt_scale_unless_one': [],
-                      'dsnt_finish_loss_peer': [], 'dsnt_mask_count_peer': []}
-    for _ in range(args.steps):
-        step()
-    barrier()
-    t_wall1 = time.time()
-    logs, _lib.event_log = _lib.event_log, None
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    kernel_ms = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v) if v else None) for k, v in logs.items()}
+    identity = loss_identity(cx, head)
+    timeline = None
+    if head.one_pass and (kernel_ms.get('dsnt_head_step_fused') or kernel_ms.get('dsnt_head_step_fused_peer')):
+        timeline = exchange_timeline(cx, head)
 
     # ---------------- end-to-end timing: host buffers in, loss + coords out, copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        zh = torch.empty(bsz, joints, h, w, dtype=tdt).pin_memory()
-        zh.copy_(z.detach())
-        th, mh = target.cpu().pin_memory(), mask.cpu().pin_memory()
-        loss_h = torch.empty((), dtype=torch.float32).pin_memory()
-        coords_h = torch.empty(bsz, joints, 2, dtype=torch.float32).pin_memory()
-        zd = torch.empty_like(z.detach())
-        td, md = torch.empty_like(target), torch.empty_like(mask)
+    e2e = None if args.no_e2e or head.stacks > 1 else run_e2e(cx, head, args.steps)
 
-        def e2e_step():
-            zd.copy_(zh, non_blocking=True)
-            td.copy_(th, non_blocking=True)
-            md.copy_(mh, non_blocking=True)
-            zin = zd.detach().requires_grad_(True)
-            out = dp.dsnt_head(zin, td, md, reg=reg, hm_sigma=1.0, reg_coeff=1.0, group=group, one_pass=one_pass)
-            out.loss.backward()
-            loss_h.copy_(out.loss.detach(), non_blocking=True)
-            coords_h.copy_(out.coords.detach(), non_blocking=True)
-            return zin.grad
+    # ---------------- the config as BASELINE writes it: the SAME batch sliced over the ranks (strong scaling)
+    strong = None
+    if not args.no_extras and args.scaling == 'weak':
+        if world == 1:
+            strong = {'note': 'N = 1: the strong-scaling workload IS the line above (batch 4096 on one GPU)',
+                      'value': head.n_local * args.steps / (elapsed_ms * 1e-3), 'ms_per_step': elapsed_ms / args.steps}
+        else:
+            del graphs
+            graphs = None
+            hs = Head(cx, args.workload, scaling='strong', path=args.path)
+            sms, snote, sgraphs, _ = measure(cx, hs, args.steps, args.warmup, graph=args.graph)
+            sk, sl = kernel_pass(cx, hs, args.steps)
+            n_glob = WORKLOADS[args.workload][0] * hs.joints * hs.stacks
+            strong = {'scaling': 'strong', 'config': workload_config(args.workload, world, 'strong'),
+                      'value': n_glob * args.steps / (sms * 1e-3), 'unit': UNIT, 'ms_per_step': sms / args.steps,
+                      'launch': snote, 'launches_per_step': sl, 'loss_identical_on_all_ranks': loss_identity(cx, hs),
+                      'timeline': exchange_timeline(cx, hs) if (sk.get('dsnt_head_step_fused_peer')) else None}
+            try:
+                strong['roofline'] = roofline_of(cx, hs, sk, None)
+            except RuntimeError:
+                pass
+            del sgraphs
+            hs.free()
 
-        e2e_steps = max(3, min(args.steps, 20))
-        for _ in range(3):
-            e2e_step()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        e1.record()
-        barrier()
-        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = zh.numel() * esize + th.numel() * 4 + mh.numel() * 4
-        d2h = 4 + coords_h.numel() * 4
-        e2e = {'value': n_local * world * e2e_steps / (te.item() * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-               'ms_per_step': te.item() / e2e_steps,
-               'note': 'pinned host Z/target/mask -> device, fused fwd+bwd, loss+coords -> pinned host; '
-                       'dL/dZ stays on the device for the backbone backward'}
-
+    if world > 1:
+        PeerExchange.check_all()
     if rank != 0:
         leave(world, dist, torch)
         return 0
 
-    # ---------------- roofline of the dominant kernel (live CUDA-event durations from the timed region)
-    peak, peak_how = measured_peak()
-    hw = h * w
-    alg = {'dsnt_head_fwd': n_local * (hw * esize + 56),        # read Z; target 8 r, coords 8 w, stats 32 w, terms 8 w
-           'dsnt_head_bwd': n_local * (2 * hw * esize + 44),    # read Z, write dZ; stats 32 r, target 8 r, mask 4 r
-           'dsnt_head_step': n_local * (2 * hw * esize + 68),   # read Z, write dZ; target 8 r, mask 4 r, coords/stats/terms 56 w
-           'dsnt_head_step_fused': n_local * (2 * hw * esize + 60)}   # the same without the terms (8 w); the mask again from L2
-    alg['dsnt_head_step_fused_peer'] = alg['dsnt_head_step_fused']     # + 2 x 16 bytes to every peer
-    ran = [k for k in alg if kernel_ms.get(k)]
-    if not ran:
-        raise RuntimeError('bench.py: none of the timed entry points ran (%r)' % (sorted(kernel_ms),))
-    dominant = max(ran, key=lambda k: kernel_ms[k])
-    per_kernel = {}
-    for k in ran:
-        ach = alg[k] / (kernel_ms[k] * 1e-3) / 1e9
-        per_kernel[k] = {'ms': kernel_ms[k], 'algorithmic_bytes': alg[k], 'achieved_gbs': ach, 'frac': ach / peak}
-    small = {k: kernel_ms[k] for k in ('dsnt_finish_loss', 'dsnt_mask_count', 'dsnt_scale_unless_one',
-                                       'dsnt_finish_loss_peer', 'dsnt_mask_count_peer') if kernel_ms.get(k)}
-    step_bytes = sum(alg[k] for k in ran)
-    step_gbs = step_bytes * world / (elapsed_ms / args.steps * 1e-3) / 1e9
     traffic = committed_traffic(args.workload)
-    if isinstance(traffic, dict) and 'dsnt_head_step' in traffic:
-        for same in ('dsnt_head_step_fused', 'dsnt_head_step_fused_peer'):      # the same kernel (head_step2_kernel)
-            traffic.setdefault(same, traffic['dsnt_head_step'])
-    roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': per_kernel[dominant]['achieved_gbs'], 'peak': peak,
-                'unit': 'GB/s', 'frac': per_kernel[dominant]['frac'],
-                'traffic': (traffic or {}).get(dominant) if isinstance(traffic, dict) else None,
-                'peak_source': peak_how, 'kernels': per_kernel, 'small_kernels_ms': small,
-                'step': {'algorithmic_bytes_per_gpu': step_bytes, 'achieved_gbs_per_gpu': step_gbs / world,
-                         'frac': step_gbs / world / peak}}
+    roofline = roofline_of(cx, head, kernel_ms, None)
+    if isinstance(traffic, dict):
+        if 'dsnt_head_step' in traffic:
+            for same in ('dsnt_head_step_fused', 'dsnt_head_step_fused_peer'):      # the same kernel (head_step2_kernel)
+                traffic.setdefault(same, traffic['dsnt_head_step'])
+        roofline['traffic'] = traffic.get(roofline['kernel'])
+    step_gbs = roofline['algorithmic_bytes_per_step'] / (elapsed_ms / args.steps * 1e-3) / 1e9
+    roofline['step'] = {'algorithmic_bytes_per_gpu': roofline['algorithmic_bytes_per_step'], 'achieved_gbs_per_gpu': step_gbs,
+                        'frac': step_gbs / cx.peak}
 
-    cpu_baseline = None
+    cpu_baseline, cpu_sample = None, None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_cpu_baseline(reg)
+        cpu_baseline, cpu_sample = run_cpu_baseline(head.reg)
+    check = self_check(cx, head, cpu_sample) if head.stacks == 1 else None
 
-    value = n_local * world * args.steps / (elapsed_ms * 1e-3)
+    extras, eager = None, None
+    if world == 1 and not args.no_extras:
+        head_ms = elapsed_ms / args.steps
+        head.free()
+        del graphs
+        torch.cuda.empty_cache()
+        ex_steps = max(10, min(args.steps, 50))
+        extras = []
+        for name in EXTRA_WORKLOADS:
+            if name == args.workload:
+                continue
+            try:
+                extras.append(run_extra(cx, name, ex_steps, args.warmup))
+            except Exception as e:          # noqa: BLE001
+                extras.append({'workload': name, 'error': str(e).splitlines()[0][:200]})
+        ours = {args.workload: head_ms}
+        ours.update({e['workload']: e['ms_per_step'] for e in extras if 'ms_per_step' in e})
+        eager = run_gpu_eager_baseline(cx, ours)
+
+    value = head.n_local * world * args.steps / (elapsed_ms * 1e-3)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
-        'config': {'workload': args.workload, 'heatmaps_per_gpu': n_local, 'batch_per_gpu': bsz, 'joints': joints,
-                   'heatmap': [h, w], 'reg': reg, 'hm_sigma_px': 1.0, 'mask': True,
-                   'parallelism': ('batch-sharded x%d; the three partial sums of masked_average are exchanged %s' % (
-                       world, exchange_note)) if world > 1 else 'single GPU (batch shard = whole batch)',
-                   'l2_policy': 'inputs larger than L2 (%.0f MiB of logits per step vs 126 MB L2)'
-                                % (n_local * hw * esize / 2 ** 20),
-                   'path': ('one-pass: %s (forward and dL/dZ while the heatmap is in shared memory, 2*H*W*sizeof '
-                            'algorithmic bytes); backward only scales in place when d(loss) != 1' % (
-                                'dsnt_head_step_fused_peer, ONE launch per rank: mask count, step, loss composition and '
-                                'both exchanges between the ranks' if kernel_ms.get('dsnt_head_step_fused_peer') else
-                                'dsnt_head_step_fused, ONE launch: mask count, step and loss composition'
-                                if kernel_ms.get('dsnt_head_step_fused') else
-                                'dsnt_mask_count + dsnt_head_step + dsnt_finish_loss')) if one_pass else
-                           'two-kernel: dsnt_head_fwd + dsnt_finish_loss + dsnt_head_bwd (3*H*W*sizeof algorithmic bytes)',
-                   'launch': graph_note},
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': head.dtype, 'data': 'synthetic',
+        'config': workload_config(args.workload, world, args.scaling),
+        'path': path_note(head, kernel_ms), 'launch': graph_note,
+        'exchange': ('the three partial sums of masked_average are exchanged %s' % exchange_note) if world > 1 else None,
         'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks, 'e2e': e2e,
-        'gpu_launches': launches,
+        'gpu_launches': int(round(launches_per_step * args.steps)),
+        'loss_identical_on_all_ranks': identity, 'self_check': check, 'timeline': timeline, 'strong': strong,
+        'extra_workloads': extras, 'gpu_eager_baseline': eager,
     }
     print(json.dumps(line), file=RESULT_OUT)
     RESULT_OUT.flush()
@@ -479,6 +874,6 @@ def claim_stdout():
 
 if __name__ == '__main__':
     a = parse_args()
-    start_watchdog(900)
+    start_watchdog(1500)
     RESULT_OUT = claim_stdout()
     sys.exit(main_reference(a) if a.impl == 'reference' else main_ours(a))

@@ -59,6 +59,7 @@ SIGNATURES = {
     'dsnt_scale_unless_one': (_c_int, [_c_ptr, _c_int, _c_long, _c_ptr, _c_ptr]),
     'dsnt_finish_loss_stacked': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_finish_workspace_bytes': (_c_int, []),
+    'dsnt_finish_trace_offset_bytes': (_c_int, []),
     'dsnt_finish_loss': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_float, _c_ptr, _c_ptr, _c_ptr]),
     'dsnt_combine_loss': (_c_int, [_c_ptr, _c_float, _c_ptr]),
     'dsnt_peer_exchange_bytes': (_c_int, []),

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
     if (i < n_per) sm += w;
   }
   block_sum4<kFinishBlock>(sd, sr, sm, unused, red);
-  unsigned* ticket = reinterpret_cast<unsigned*>(workspace + kFinishSlots * 4);
+  unsigned* ticket = reinterpret_cast<unsigned*>(workspace + kFinishCtl);
   if (threadIdx.x == 0) {
     float4* part = reinterpret_cast<float4*>(workspace);
     part[blockIdx.x] = make_float4(sd, sr, sm, 0.f);

@@ -135,6 +135,8 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
 
 DSNT_API int dsnt_finish_workspace_bytes(void) { return static_cast<int>(sizeof(float) * kFinishWorkspaceFloats); }
 
+DSNT_API int dsnt_finish_trace_offset_bytes(void) { return static_cast<int>(sizeof(float) * kFinishTrace); }
+
 DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
                                       float* out, float* workspace, void* stream) {
   if (n_stacks < 1 || n_per_stack < 0) { set_error("dsnt_finish_loss: bad arguments"); return DSNT_ERR_BAD_ARG; }
@@ -149,7 +151,7 @@ DSNT_API int dsnt_finish_loss_stacked(const float* terms, const float* mask, lon
   return check_launch("finish_loss_kernel");
 }
 
-DSNT_API int dsnt_peer_exchange_bytes(void) { return static_cast<int>(sizeof(float4) * 2 * kMaxRanks); }
+DSNT_API int dsnt_peer_exchange_bytes(void) { return kPeerExchangeBytes; }
 
 DSNT_API int dsnt_finish_loss_peer(const float* terms, const float* mask, long n_per_stack, int n_stacks, float reg_coeff,
                                    float* out, float* workspace, const void* const* peers, int rank, int world,

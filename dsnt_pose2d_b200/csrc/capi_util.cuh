@@ -11,6 +11,24 @@ namespace dsnt {
 void set_error(const char* fmt, ...);  // capi.cu
 int check_launch(const char* what);    // capi.cu: cudaGetLastError -> DSNT_ERR_LAUNCH
 
+// Launch attributes (shared-memory opt-in, SM count, cluster occupancy) are properties of a DEVICE, and one process may
+// drive several: every cache of them is an array indexed by the current device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+inline int sm_count_of_current_device() {
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // Widest vector the layout allows: a vector must not straddle a row (W % VEC == 0) and every heatmap
@@ -51,7 +69,7 @@ inline int make_peers(const void* const* peers, int rank, int world, unsigned* e
   xc = no_peers();
   for (int r = 0; r < world; ++r) {
     if (!peers[r] || !aligned(peers[r], 16)) { set_error("peer exchange: buffer of rank %d is null or misaligned", r); return DSNT_ERR_BAD_ARG; }
-    xc.peers[r] = static_cast<float4*>(const_cast<void*>(peers[r]));
+    xc.peers[r] = static_cast<unsigned long long*>(const_cast<void*>(peers[r]));
   }
   xc.epoch = epoch; xc.error = error; xc.rank = rank; xc.world = world;
   return DSNT_OK;

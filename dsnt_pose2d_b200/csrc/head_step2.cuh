@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   __shared__ unsigned long long pace_next;        // clock at which the CTA may issue its next bulk load (p.pace)
   __shared__ PendingLoad pend_all[NWMAX];
   __shared__ float fin[NWMAX][2];                  // single-launch form: per-warp sums of mask * (distance, divergence)
-  __shared__ float mask_total, mask_local;     // count over all ranks / over this rank's shard
   __shared__ bool fin_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,15 +236,21 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
       issued[t] = 1;
     }
   }
-  // Single-launch form: no dsnt_mask_count before this kernel.  Every CTA adds up ITS slice of the mask, parks the partial in
-  // the workspace and meets the others at a grid barrier (the grid is one CTA per SM, all co-resident); then every CTA adds
-  // the partials in index order, so all hold the same denominator.  Three global round trips, hidden behind the first
-  // bulk loads, which are already in flight.  (All CTAs reading the whole mask instead -- 148 x 256 KiB out of the same
-  // L2 lines -- delayed the start of the kernel by ~20 us.)
+  // Single-launch form: no dsnt_mask_count before this kernel, and NO grid barrier.  The denominator of masked_average
+  // (src/dsnt/nn.py:88-92) scales the gradient only, so the forward of a warp's first heatmap does not need it.  Every CTA
+  // adds up ITS slice of the mask, parks the partial in the workspace and draws a ticket -- nobody waits; the CTA with the
+  // last ticket adds the partials in index order (sharded batch: exchanges the sum with the other ranks through peer
+  // memory) and publishes the count; every warp picks it up just before its first backward (need_count below).  The
+  // global round trips -- and, sharded, the NVLink hop and the wait for a rank that started later -- are hidden behind the
+  // first bulk loads and the first forward.  Co-residency of the grid (one CTA per SM) is guaranteed by the cooperative
+  // launch attribute (step.cu).
   float mask_count = 0.f;
+  bool have_count = p.denom != nullptr;
   const bool sharded = p.xc.world > 1;
+  unsigned* const ctl = reinterpret_cast<unsigned*>(p.ws + kFinishCtl);   // [end ticket, start ticket, published flag, count]
+  unsigned long long* const trace = reinterpret_cast<unsigned long long*>(p.ws + kFinishTrace);
+  const long nmask = p.st.count > 1 ? p.st.n_per : p.n;       // the stacks share one mask
   if (!p.denom && p.mask) {
-    const long nmask = p.st.count > 1 ? p.st.n_per : p.n;       // the stacks share one mask
     const long chunk = (nmask + gridDim.x - 1) / gridDim.x;
     const long lo = blockIdx.x * chunk, hi = lo + chunk < nmask ? lo + chunk : nmask;
     float sm = 0.f;
@@ -253,64 +258,68 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     sm = warp_sum(sm);
     if (lane == 0) fin[warp][0] = sm;
   }
-  __syncthreads();
+  __syncthreads();           // barriers initialised, issued[] and pace_next set, mask partials in fin[]
   if (!p.denom) {
-    unsigned* bar = reinterpret_cast<unsigned*>(p.ws + kFinishSlots * 4) + 1;
-    unsigned* gflag = bar + 1;                                   // sharded: "the total over the ranks is in gtotal"
-    float* gtotal = reinterpret_cast<float*>(bar + 2);
-    float* mpart = p.ws + kFinishSlots * 4 + 4;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace[0] = global_timer_ns();
     if (warp == 0) {
-      float tot = static_cast<float>(p.st.count > 1 ? p.st.n_per : p.n);       // no mask: every heatmap counts
+      bool publish = blockIdx.x == 0;                            // no mask: every heatmap counts, CTA 0 says so
+      float tot = static_cast<float>(nmask);
       if (p.mask) {
+        float* mpart = p.ws + kFinishMaskPart;
+        unsigned last = 0u;
         if (lane == 0) {
           float t2 = 0.f;
           for (int w2 = 0; w2 < p.nwarps; ++w2) t2 += fin[w2][0];
-          mpart[blockIdx.x] = t2;
+          __stcg(mpart + blockIdx.x, t2);
           __threadfence();
-          atomicAdd(bar, 1u);
-          while (ld_acquire_gpu(bar) < gridDim.x) __nanosleep(64);
+          last = atomicAdd(ctl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
         }
-        __syncwarp();
-        float v[kFinishSlots / 32];
+        publish = __shfl_sync(kFull, last, 0) != 0u;
+        if (publish) {
+          __threadfence();
+          float v[kFinishSlots / 32];
 #pragma unroll
-        for (int k = 0; k < kFinishSlots / 32; ++k) {
-          const int i = lane + 32 * k;
-          v[k] = i < static_cast<int>(gridDim.x) ? __ldcg(mpart + i) : 0.f;
+          for (int k = 0; k < kFinishSlots / 32; ++k) {
+            const int i = lane + 32 * k;
+            v[k] = i < static_cast<int>(gridDim.x) ? __ldcg(mpart + i) : 0.f;
+          }
+          tot = 0.f;
+#pragma unroll
+          for (int k = 0; k < kFinishSlots / 32; ++k) tot += v[k];
+          tot = warp_sum(tot);
         }
-        tot = 0.f;
-#pragma unroll
-        for (int k = 0; k < kFinishSlots / 32; ++k) tot += v[k];
-        tot = warp_sum(tot);
       }
-      if (lane == 0) mask_local = tot;
-      if (sharded) {
-        // the count over ALL ranks: CTA 0 exchanges this rank's total through peer memory and publishes the sum to the
-        // other CTAs of its grid.  Slot layout as in finish_loss_kernel (sum mask*dist, sum mask*D, sum mask), so that a
-        // rank on the three-launch form (an empty shard) meets the others in the same exchanges.
-        if (blockIdx.x == 0) {
+      if (publish) {
+        if (lane == 0) { __stcg(p.ws + kFinishLocal, tot); trace[1] = global_timer_ns(); }
+        if (sharded) {
+          // the count over ALL ranks.  Slot layout as in finish_loss_kernel (sum mask*dist, sum mask*D, sum mask), so that a
+          // rank on the three-launch form (an empty shard) meets the others in the same exchanges.
           float z0 = 0.f, z1 = 0.f;
           peer_exchange_sum3(p.xc, z0, z1, tot);
-          if (lane == 0) {
-            __stcg(gtotal, tot);
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gflag), "r"(1u) : "memory");
-          }
-        } else {
-          if (lane == 0) {
-            while (ld_acquire_gpu(gflag) == 0u) __nanosleep(64);
-            tot = __ldcg(gtotal);
-          }
-          tot = __shfl_sync(kFull, tot, 0);
+        }
+        if (lane == 0) {
+          __stcg(reinterpret_cast<float*>(ctl + 3), tot);
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctl + 2), "r"(1u) : "memory");
+          trace[2] = global_timer_ns();
         }
       }
-      if (lane == 0) mask_total = tot;
     }
-    __syncthreads();
-    mask_count = mask_total;
   }
+  // the count, when a warp first needs it (lane 0 polls the flag in L2; it is long there in the steady case)
+  auto need_count = [&]() {
+    if (have_count) return;
+    float tot = 0.f;
+    if (lane == 0) {
+      while (ld_acquire_gpu(ctl + 2) == 0u) __nanosleep(100);
+      tot = __ldcg(reinterpret_cast<const float*>(ctl + 3));
+    }
+    mask_count = __shfl_sync(kFull, tot, 0);
+    have_count = true;
+  };
   if (p.stagger_ns > 0) __nanosleep(static_cast<unsigned>(warp * p.stagger_ns + (blockIdx.x & 3) * (p.stagger_ns >> 2)));
   const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
-  const float inv_denom = 1.0f / (p.denom ? __ldg(p.denom) : fmaxf(mask_count, 1.0f));
+  float inv_denom = p.denom ? 1.0f / __ldg(p.denom) : 0.f;     // single-launch form: set by the first need_count()
   float acc_d = 0.f, acc_r = 0.f;       // this warp's sums of mask * distance, mask * divergence (single-launch form)
   const float s2 = p.sigma * p.sigma;
 
@@ -366,7 +375,6 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
 
     const float tx = tgt_next.x, ty = tgt_next.y;
     const float mraw = msk_next;
-    const float wgt = mraw * inv_denom;
     if (t + NW < nt32) {
       const long hmn = locate(p.st, (t + NW) * hm_mul + hm_add, hm_bytes).nl;
       if (p.target) tgt_next = __ldg(reinterpret_cast<const float2*>(p.target) + hmn);
@@ -598,6 +606,8 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     }
 
     // ---------------------------------------------------------------- outputs + the scalars of the backward
+    if (!have_count) { need_count(); inv_denom = 1.0f / fmaxf(mask_count, 1.0f); }
+    const float wgt = mraw * inv_denom;
     float dist = 0.f, a = 0.f, b = 0.f;
     if (p.target) {
       const float dx = mux - tx, dy = muy - ty;
@@ -727,17 +737,18 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   if (p.out8) {
     if (lane == 0) { fin[warp][0] = acc_d; fin[warp][1] = acc_r; }
     __syncthreads();
-    unsigned* ticket = reinterpret_cast<unsigned*>(p.ws + kFinishSlots * 4);
     if (threadIdx.x == 0) {
       float sd = 0.f, sr = 0.f;
       for (int w2 = 0; w2 < p.nwarps; ++w2) { sd += fin[w2][0]; sr += fin[w2][1]; }
       reinterpret_cast<float4*>(p.ws)[blockIdx.x] = make_float4(sd, sr, 0.f, 0.f);
       __threadfence();
-      fin_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+      fin_last = atomicAdd(ctl, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (fin_last && warp == 0) {
       __threadfence();
+      if (lane == 0) trace[3] = global_timer_ns();
+      need_count();                 // a warp without heatmaps has not looked yet
       const float4* part = reinterpret_cast<const float4*>(p.ws);
       float4 v[kFinishSlots / 32];
 #pragma unroll
@@ -749,14 +760,18 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
 #pragma unroll
       for (int k = 0; k < kFinishSlots / 32; ++k) { sa += v[k].x; sb += v[k].y; }
       sa = warp_sum(sa); sb = warp_sum(sb);
-      if (sharded) { float cnt = mask_local; peer_exchange_sum3(p.xc, sa, sb, cnt); }   // totals over the ranks
+      if (sharded) {                // totals over the ranks; the count goes round again so that the layout of the exchange
+        float cnt = __ldcg(p.ws + kFinishLocal);      // is that of finish_loss_kernel
+        peer_exchange_sum3(p.xc, sa, sb, cnt);
+      }
       if (lane == 0) {
         p.out8[0] = sa; p.out8[1] = sb;
         p.out8[2] = p.denom ? __ldg(p.denom) : mask_count;   // with an external denominator out8[2..3] repeat it
         write_loss_tail(p.out8, p.reg_coeff);
-        ticket[0] = 0u;
-        ticket[1] = 0u;      // the mask barrier: every CTA passed it long ago
-        ticket[2] = 0u;      // and the flag of the count over the ranks
+        ctl[0] = 0u;         // end ticket
+        ctl[1] = 0u;         // start ticket: every CTA drew it long ago
+        ctl[2] = 0u;         // and the "count published" flag: every warp with a heatmap has read it
+        trace[4] = global_timer_ns();
       }
     }
   }

@@ -21,17 +21,7 @@ int launch_step_pair(const void* z, int dtype, long n, int H, int W, const float
                      const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords, float* stats,
                      float* terms, void* dz, cudaStream_t stream);
 
-static int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
-  }
-  return cached;
-}
+static int sm_count() { return sm_count_of_current_device(); }
 
 static int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
@@ -65,7 +55,8 @@ static int step2_pace_cycles(long hm_bytes, int ctas) {
   if (fixed >= 0) return fixed;
   static const int gbs = env_int("DSNT_TUNE_STEP_PACE_GBS", 6800);
   if (gbs <= 0) return 0;
-  static double ghz = 0.0;
+  static double ghz_of[kMaxDevices] = {};
+  double& ghz = ghz_of[current_device()];
   if (ghz == 0.0) {
     int dev = 0, khz = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0)
@@ -89,15 +80,26 @@ static int launch_step2_nw(HeadStepParams p, cudaStream_t stream) {
   if (p.nwarps > p.nbufs) p.nwarps = p.nbufs;
   if (p.nwarps < 1) p.nwarps = 1;
   const size_t smem = static_cast<size_t>(p.nbufs) * p.buf_bytes;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[kMaxDevices] = {};     // per instantiation and device: the opt-in only ever needs to grow
+  size_t& conf = configured[current_device()];
+  if (smem > conf) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return check_launch("head_step2_kernel (shared-memory opt-in)");
-    configured = smem;
+    conf = smem;
   }
   long ctas = p.n < sm_count() ? p.n : sm_count();
+  if (ctas > kFinishSlots) ctas = kFinishSlots;             // one workspace slot per CTA in the single-launch form
   p.pace = PACED ? step2_pace_cycles(static_cast<long>(H) * W * sizeof(T), static_cast<int>(ctas)) : 0;
-  kern<<<static_cast<unsigned>(ctas), p.nwarps * 32, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas)); cfg.blockDim = dim3(p.nwarps * 32);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  // Single-launch form: the CTAs wait for a count that the LAST of them publishes, so the whole grid must be resident at
+  // once.  The cooperative attribute makes the driver guarantee that (or refuse the launch) instead of the kernel assuming it.
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = (!p.denom) ? 1 : 0;
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return check_launch("head_step2_kernel");
   return check_launch("head_step2_kernel");
 }
 
@@ -133,11 +135,12 @@ static int launch_step_one(HeadStepParams p, cudaStream_t stream) {
   if (p.nwarps > kMaxGroups) p.nwarps = kMaxGroups;
   if (p.nwarps > p.nbufs) p.nwarps = p.nbufs;
   const size_t smem = static_cast<size_t>(p.nbufs) * p.buf_bytes;
-  static size_t configured = 0;     // per instantiation: the opt-in only ever needs to grow
-  if (smem > configured) {
+  static size_t configured[kMaxDevices] = {};     // per instantiation and device: the opt-in only ever needs to grow
+  size_t& conf = configured[current_device()];
+  if (smem > conf) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return check_launch("head_step_kernel (shared-memory opt-in)");
-    configured = smem;
+    conf = smem;
   }
   long ctas = p.n < sm_count() ? p.n : sm_count();   // persistent: one CTA per SM, tiles interleaved across CTAs
   kern<<<static_cast<unsigned>(ctas), p.nwarps * GROUP, smem, stream>>>(p);

@@ -330,12 +330,13 @@ bool step_pair_supported(int dtype, int H, int W, int reg) {
 template <int REG>
 static int launch_pair(const PairParams& p, cudaStream_t stream) {
   auto kern = head_step_pair_kernel<REG>;
-  static int max_clusters = 0;
+  static int max_clusters_of[kMaxDevices] = {};     // per device: 0 = not asked yet, -1 = clusters of this size cannot run
+  int& max_clusters = max_clusters_of[current_device()];
   if (max_clusters == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes) != cudaSuccess)
       return check_launch("head_step_pair_kernel (shared-memory opt-in)");
     cudaLaunchConfig_t probe = {};
-    probe.gridDim = dim3(2 * 148); probe.blockDim = dim3(kPairThreads); probe.dynamicSmemBytes = kPairSmemBytes;
+    probe.gridDim = dim3(2 * sm_count_of_current_device()); probe.blockDim = dim3(kPairThreads); probe.dynamicSmemBytes = kPairSmemBytes;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

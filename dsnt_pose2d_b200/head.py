@@ -18,6 +18,7 @@ single-process op on the concatenated batch.
 """
 
 import collections
+import ctypes
 import os
 
 import torch
@@ -44,7 +45,8 @@ def _as_f32(t, n, last, what):
     if t is None:
         return None
     _lib.require_cuda(t, what)
-    t = t.detach().to(torch.float32).contiguous()
+    if t.dtype is not torch.float32 or t.requires_grad or not t.is_contiguous():     # the usual case converts nothing
+        t = t.detach().to(torch.float32).contiguous()
     expect = n * last
     if t.numel() != expect:
         raise ValueError('%s has %d elements, expected %d' % (what, t.numel(), expect))
@@ -68,26 +70,32 @@ def all_reduce_sums(out8, group):
 def finish_loss(terms, mask, n_per_stack, n_stacks, reg_coeff, out8, ws, group, dev, stream):
     """masked_average + loss composition over the per-heatmap terms; with a sharded batch the partial sums of the ranks
     are exchanged inside the kernel over peer memory (one node) or all-reduced by NCCL.  terms=None: mask count only."""
+    finish_loss_ptr(None if terms is None else terms.data_ptr(), mask, n_per_stack, n_stacks, reg_coeff,
+                    out8.data_ptr(), out8, ws, group, dev, stream)
+
+
+def finish_loss_ptr(terms_ptr, mask, n_per_stack, n_stacks, reg_coeff, out8_ptr, out8_owner, ws, group, dev, stream):
+    """`finish_loss` on raw device addresses (the one-pass step keeps all its small outputs in one allocation);
+    `out8_owner` is a float32 tensor that contains the 8 floats at `out8_ptr` (needed for the NCCL all-reduce only)."""
     peer = PeerExchange.get(group, dev)
     if peer is not None:
-        if terms is None:
-            _lib.call('dsnt_mask_count_peer', _lib.ptr(mask), n_per_stack, out8.data_ptr(), ws.data_ptr(), *peer.args(),
-                      stream)
+        if terms_ptr is None:
+            _lib.call('dsnt_mask_count_peer', _lib.ptr(mask), n_per_stack, out8_ptr, ws.data_ptr(), *peer.args(), stream)
         else:
-            _lib.call('dsnt_finish_loss_peer', terms.data_ptr(), _lib.ptr(mask), n_per_stack, n_stacks, reg_coeff,
-                      out8.data_ptr(), ws.data_ptr(), *peer.args(), stream)
+            _lib.call('dsnt_finish_loss_peer', terms_ptr, _lib.ptr(mask), n_per_stack, n_stacks, reg_coeff,
+                      out8_ptr, ws.data_ptr(), *peer.args(), stream)
         return
-    if terms is None:
-        _lib.call('dsnt_mask_count', _lib.ptr(mask), n_per_stack, out8.data_ptr(), ws.data_ptr(), stream)
+    if terms_ptr is None:
+        _lib.call('dsnt_mask_count', _lib.ptr(mask), n_per_stack, out8_ptr, ws.data_ptr(), stream)
     elif n_stacks == 1:
-        _lib.call('dsnt_finish_loss', terms.data_ptr(), _lib.ptr(mask), n_per_stack, reg_coeff, out8.data_ptr(),
-                  ws.data_ptr(), stream)
+        _lib.call('dsnt_finish_loss', terms_ptr, _lib.ptr(mask), n_per_stack, reg_coeff, out8_ptr, ws.data_ptr(), stream)
     else:
-        _lib.call('dsnt_finish_loss_stacked', terms.data_ptr(), _lib.ptr(mask), n_per_stack, n_stacks, reg_coeff,
-                  out8.data_ptr(), ws.data_ptr(), stream)
-    if group is not None:
-        all_reduce_sums(out8, group)
-        _lib.call('dsnt_combine_loss', out8.data_ptr(), reg_coeff, stream)
+        _lib.call('dsnt_finish_loss_stacked', terms_ptr, _lib.ptr(mask), n_per_stack, n_stacks, reg_coeff,
+                  out8_ptr, ws.data_ptr(), stream)
+    if _is_sharded(group):
+        off = (out8_ptr - out8_owner.data_ptr()) // 4
+        all_reduce_sums(out8_owner[off:off + 8], group)
+        _lib.call('dsnt_combine_loss', out8_ptr, reg_coeff, stream)
 
 
 class _FusedHead(torch.autograd.Function):
@@ -232,8 +240,8 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     if preact not in _lib.PREACT_IDS:
         raise Exception('unrecognised heatmap preactivation function: {}'.format(preact))   # model.py:42-43
     if (one_pass and preact == 'softmax' and threshold is None and eps is None and input_is_logits
-            and z.requires_grad and torch.is_grad_enabled() and step_supported(z, reg)
-            and _step_pays(z, h, w, _lib.REG_IDS[reg], float(sigma), group)):
+            and z.requires_grad and torch.is_grad_enabled()
+            and takes_one_pass(z, reg, float(sigma), _is_sharded(group))):
         coords, loss = _FusedHeadStep.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
                                             flags, group, aux)
     elif preact == 'softmax' and threshold is None and eps is None:
@@ -256,27 +264,39 @@ USE_PAIR_STEP = True          # 256x256 fp32, no / variance regulariser: the clu
 USE_L2_STEP = False           # heatmaps too large for shared memory: take the L2-staged one-pass step (csrc/step_l2.cu)?
                               # Measured on B200 at BASELINE config 5 it does not beat the two-kernel path yet (996 vs 970 us:
                               # two resident CTAs per SM keep the logits in L2 but too few bytes in flight), so it is off.
-# Sharded batch: take the single-launch step with both exchanges inside the kernel (dsnt_head_step_fused_peer)?  Parity-green
-# on 2 B200 (tools/check_sharded.py) but no faster than dsnt_mask_count_peer + dsnt_head_step + dsnt_finish_loss_peer there
-# (0.3687 vs 0.3687-0.3706 ms/step: what separates 2 GPUs from 1 is the slower of the two GPUs, not launches), so off.
-FUSED_PEER_STEP = os.environ.get('DSNT_FUSED_PEER_STEP', '0') != '0'
+# Sharded batch: take the single-launch step with both exchanges inside the kernel (dsnt_head_step_fused_peer).  The count
+# is published by the last CTA to arrive and picked up by every warp only before its first backward, so the exchange --
+# and the wait for a rank that started later -- hides behind the first loads and the first forward.  DSNT_FUSED_PEER_STEP=0
+# keeps dsnt_mask_count_peer + dsnt_head_step + dsnt_finish_loss_peer (three launches, same results).
+FUSED_PEER_STEP = os.environ.get('DSNT_FUSED_PEER_STEP', '1') != '0'
 STEP_MIN_BYTES = 32 << 20     # logits smaller than this take the one-pass step only in its single-launch form
 
 
-def _step_pays(z, h, w, reg_id, sigma, group):
+def _step_pays(z, h, w, reg_id, sigma, group=None, sharded=None):
     """The one-pass step saves a read of the logits.  Where the single-launch form serves the case it also saves launches;
-    where it does not (other shapes, KL, sharded batch) it takes one launch MORE than the two-kernel path, which only pays
-    once the logits no longer sit in L2 (small batches are bound by launches, tools/stepbench.py)."""
-    if _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, reg_id, sigma) and (
-            not _is_sharded(group) or (FUSED_PEER_STEP and PeerExchange.get(group, z.device) is not None)):
+    where it does not (other shapes, KL) it takes one launch MORE than the two-kernel path, which only pays once the logits
+    no longer sit in L2 (small batches are bound by launches, tools/stepbench.py).
+    A sharded batch never decides from the size of the LOCAL shard: the one-pass step exchanges twice per step (mask count,
+    loss sums), the two-kernel path once, and shards may be uneven or empty -- every rank must take the same path."""
+    if _is_sharded(group) if sharded is None else sharded:
+        return True
+    if _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, reg_id, sigma):
         return True
     return z.numel() * z.element_size() >= STEP_MIN_BYTES
 
 
+def takes_one_pass(z, reg, sigma, sharded):
+    """The kernel-selection rule of `dsnt_head(one_pass=True)`: a pure function of dtype, heatmap shape, regulariser and --
+    single process only -- the size of the batch."""
+    h, w = int(z.shape[-2]), int(z.shape[-1])
+    return step_supported(z, reg) and _step_pays(z, h, w, _lib.REG_IDS[reg], sigma, group=None, sharded=sharded)
+
+
 def step_supported(z, reg=None):
-    """True when `dsnt_head_step` (one pass over the logits) can take heatmaps of this dtype and size: at least four of
-    them fit in shared memory, or -- for larger ones, given the regulariser -- the L2-staged form serves the case."""
-    if z.dtype not in (torch.float32, torch.bfloat16) or z.dim() < 2 or z.numel() == 0:
+    """True when `dsnt_head_step` (one pass over the logits) can take heatmaps of this dtype and SHAPE (the batch size plays
+    no part, so that the ranks of a sharded batch agree): at least four of them fit in shared memory, or -- for larger
+    ones, given the regulariser -- the cluster-of-two-CTAs / L2-staged form serves the case."""
+    if z.dtype not in (torch.float32, torch.bfloat16) or z.dim() < 2 or z.shape[-1] == 0 or z.shape[-2] == 0:
         return False
     if reg is not None and USE_PAIR_STEP and _lib.LIB.dsnt_head_step_pair_supported(
             _lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1]), _lib.REG_IDS[reg]):
@@ -287,11 +307,51 @@ def step_supported(z, reg=None):
                                                       _lib.REG_IDS[reg]))
 
 
+class _StepArena:
+    """One allocation for the per-heatmap outputs and the loss blocks of a one-pass step (six torch.empty calls cost more
+    host time than the kernel takes at the small BASELINE configs): floats [stats n*8 | coords n*2 | terms n*2 | out8 | cnt8]."""
+
+    __slots__ = ('buf', 'n', 'base')
+
+    def __init__(self, n, dev):
+        self.n = n
+        self.buf = torch.empty(12 * n + 16, dtype=torch.float32, device=dev)
+        self.base = self.buf.data_ptr()
+
+    @property
+    def stats_ptr(self):
+        return self.base
+
+    @property
+    def coords_ptr(self):
+        return self.base + 32 * self.n
+
+    @property
+    def terms_ptr(self):
+        return self.base + 40 * self.n
+
+    @property
+    def out8_ptr(self):
+        return self.base + 48 * self.n
+
+    @property
+    def cnt8_ptr(self):
+        return self.base + 48 * self.n + 32
+
+    def coords(self):
+        return self.buf[8 * self.n:10 * self.n]
+
+    def out8(self):
+        return self.buf[12 * self.n:12 * self.n + 8]
+
+
 class _FusedHeadStep(torch.autograd.Function):
-    """One pass over the logits for the whole training step (include/dsnt_b200.h: dsnt_mask_count + dsnt_head_step +
-    dsnt_finish_loss).  The forward already writes dL/dz for d(loss) = 1; the backward hands it out, scaled in place by
-    the actual d(loss) (`dsnt_scale_unless_one`: no traffic when it is 1, as in `loss.backward()`).  A gradient
-    w.r.t. the coordinates, if anybody asks for one, goes through the regular backward kernel on the saved statistics."""
+    """One pass over the logits for the whole training step (include/dsnt_b200.h: dsnt_head_step_fused, or dsnt_mask_count +
+    dsnt_head_step + dsnt_finish_loss).  The forward already writes dL/dz for d(loss) = 1; the FIRST backward hands that
+    buffer out, scaled in place by the actual d(loss) (`dsnt_scale_unless_one`: no traffic when it is 1, as in
+    `loss.backward()`), and forgets it: the buffer now belongs to the caller (it usually becomes `z.grad`).  Any further
+    backward through the node (retain_graph=True, two losses sharing the head) and any gradient w.r.t. the coordinates go
+    through the regular backward kernel on the saved statistics, into a fresh tensor."""
 
     @staticmethod
     def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, aux):
@@ -299,43 +359,42 @@ class _FusedHeadStep(torch.autograd.Function):
         dev = zc.device
         with torch.cuda.device(dev):
             stream = _lib.stream_of(zc)
-            coords = torch.empty(n, 2, dtype=torch.float32, device=dev)
-            stats = torch.empty(n, _lib.STATS_K, dtype=torch.float32, device=dev)
-            terms = torch.empty(n, 2, dtype=torch.float32, device=dev)
-            cnt8 = torch.empty(8, dtype=torch.float32, device=dev)
-            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            ar = _StepArena(n, dev)
             dz = torch.empty_like(zc)
             ws = _lib.finish_workspace(dev)
+            dt = _lib.dtype_id(zc)
             sharded = _is_sharded(group)
-            fused = bool(_lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zc), h, w, reg_id, sigma))
-            peer = PeerExchange.get(group, dev) if sharded and fused and n > 0 and FUSED_PEER_STEP else None
-            if peer is not None:
+            fused = n > 0 and bool(_lib.LIB.dsnt_head_step_fused_supported(dt, h, w, reg_id, sigma))
+            peer = PeerExchange.get(group, dev) if sharded and FUSED_PEER_STEP else None
+            if sharded and peer is not None and fused:
                 # one launch per rank: mask count and loss sums cross the ranks inside the kernel (peer memory)
-                _lib.call('dsnt_head_step_fused_peer', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target),
-                          _lib.ptr(mask), None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(),
-                          dz.data_ptr(), out8.data_ptr(), ws.data_ptr(), *peer.args(), stream)
+                _lib.call('dsnt_head_step_fused_peer', zc.data_ptr(), dt, n, h, w, _lib.ptr(target),
+                          _lib.ptr(mask), None, reg_coeff, reg_id, sigma, flags, ar.coords_ptr, ar.stats_ptr,
+                          dz.data_ptr(), ar.out8_ptr, ws.data_ptr(), *peer.args(), stream)
             elif not sharded and fused:
                 # one launch: the kernel adds up the mask itself and its last CTA composes the loss
-                _lib.call('dsnt_head_step_fused', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
-                          None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(), dz.data_ptr(),
-                          out8.data_ptr(), ws.data_ptr(), stream)
+                _lib.call('dsnt_head_step_fused', zc.data_ptr(), dt, n, h, w, _lib.ptr(target), _lib.ptr(mask),
+                          None, reg_coeff, reg_id, sigma, flags, ar.coords_ptr, ar.stats_ptr, dz.data_ptr(),
+                          ar.out8_ptr, ws.data_ptr(), stream)
             else:
-                # the denominator of masked_average depends on the mask alone: known before the forward
-                finish_loss(None, mask, n, 1, reg_coeff, cnt8, ws, group, dev, stream)
-                _lib.call('dsnt_head_step', zc.data_ptr(), _lib.dtype_id(zc), n, h, w, _lib.ptr(target), _lib.ptr(mask),
-                          cnt8[3:4].data_ptr(), None, reg_coeff, reg_id, sigma, flags, coords.data_ptr(), stats.data_ptr(),
-                          terms.data_ptr(), dz.data_ptr(), stream)
-                finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
-        ctx.save_for_backward(zc, target, mask, stats, out8, dz)
+                # the denominator of masked_average depends on the mask alone: known before the forward.  A rank whose
+                # shard is empty (or that the single-launch kernel does not serve) meets the others in the same two exchanges.
+                finish_loss_ptr(None, mask, n, 1, reg_coeff, ar.cnt8_ptr, ar.buf, ws, group, dev, stream)
+                _lib.call('dsnt_head_step', zc.data_ptr(), dt, n, h, w, _lib.ptr(target), _lib.ptr(mask),
+                          ar.cnt8_ptr + 12, None, reg_coeff, reg_id, sigma, flags, ar.coords_ptr, ar.stats_ptr,
+                          ar.terms_ptr, dz.data_ptr(), stream)
+                finish_loss_ptr(ar.terms_ptr, mask, n, 1, reg_coeff, ar.out8_ptr, ar.buf, ws, group, dev, stream)
+        ctx.save_for_backward(zc, target, mask, ar.buf)
+        ctx.dz_box = [dz]          # NOT a saved tensor: handed out once, then gone (see the class docstring)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, z.shape)
         ctx.set_materialize_grads(False)
-        aux['out8'] = out8
+        aux['out8'] = ar.out8()
         aux['dz'] = dz
-        return coords.view(*z.shape[:-2], 2), out8[6]
+        return ar.coords().view(*z.shape[:-2], 2), aux['out8'][6]
 
     @staticmethod
     def backward(ctx, g_coords, g_loss):
-        zc, target, mask, stats, out8, dz = ctx.saved_tensors
+        zc, target, mask, arena = ctx.saved_tensors
         n, h, w, reg_id, sigma, reg_coeff, flags, shape = ctx.meta
         dev = zc.device
         if g_coords is None and g_loss is None:
@@ -344,15 +403,19 @@ class _FusedHeadStep(torch.autograd.Function):
             stream = _lib.stream_of(zc)
             if g_loss is not None:
                 g_loss = g_loss.to(torch.float32).contiguous()
-            if g_coords is None:
+            dz = ctx.dz_box[0]
+            if g_coords is None and dz is not None:
                 # the usual case (train.py:381): the gradient is already there
+                ctx.dz_box[0] = None
                 _lib.call('dsnt_scale_unless_one', dz.data_ptr(), _lib.dtype_id(dz), dz.numel(), g_loss.data_ptr(), stream)
                 return (dz.view(shape),) + (None,) * 8
-            g_coords = g_coords.to(torch.float32).contiguous()
+            if g_coords is not None:
+                g_coords = g_coords.to(torch.float32).contiguous()
             full = torch.empty_like(zc)
+            base = arena.data_ptr()
             _lib.call('dsnt_head_bwd', zc.data_ptr(), _lib.dtype_id(zc), 1, n, h, w,
-                      _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(), g_coords.data_ptr(), None,
-                      _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
+                      _lib.ptr(target), _lib.ptr(mask), base, _lib.ptr(g_coords), None,
+                      _lib.ptr(g_loss), base + 48 * n + 12 if g_loss is not None else None,
                       reg_coeff, reg_id, sigma, flags, full.data_ptr(), 0, stream)
         return (full.view(shape),) + (None,) * 8
 
@@ -415,9 +478,10 @@ class _FusedHeadStacked(torch.autograd.Function):
 
 class _FusedHeadStackedStep(torch.autograd.Function):
     """All hourglass stacks in ONE launch that is forward and backward at once (dsnt_head_step_fused_stacked,
-    include/dsnt_b200.h): coordinates, the summed loss and dL/dz of every stack, each heatmap read once.  The backward hands
-    the stored gradients out (one contiguous buffer for all stacks, scaled in place when d(loss) != 1); gradients w.r.t.
-    the coordinates go through dsnt_head_bwd_stacked on the saved statistics."""
+    include/dsnt_b200.h): coordinates, the summed loss and dL/dz of every stack, each heatmap read once.  The first backward
+    hands the stored gradients out (one contiguous buffer for all stacks, scaled in place when d(loss) != 1) and forgets
+    them; a further backward through the node, or gradients w.r.t. the coordinates, go through dsnt_head_bwd_stacked on the
+    saved statistics (see _FusedHeadStep)."""
 
     @staticmethod
     def forward(ctx, target, mask, reg_id, sigma, reg_coeff, flags, aux, *zs):
@@ -428,25 +492,27 @@ class _FusedHeadStackedStep(torch.autograd.Function):
         dev = zcs[0].device
         with torch.cuda.device(dev):
             stream = _lib.stream_of(zcs[0])
-            coords = torch.empty(s_count, n, 2, dtype=torch.float32, device=dev)
-            stats = torch.empty(s_count * n, _lib.STATS_K, dtype=torch.float32, device=dev)
-            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            ar = _StepArena(s_count * n, dev)
             dz = torch.empty((s_count,) + tuple(zcs[0].shape), dtype=zcs[0].dtype, device=dev)
             ws = _lib.finish_workspace(dev)
-            _lib.call('dsnt_head_step_fused_stacked', _lib.ptr_array(zcs), _lib.ptr_array([dz[i] for i in range(s_count)]),
+            hm_bytes = dz[0].numel() * dz.element_size()
+            dz_ptrs = (ctypes.c_void_p * s_count)(*[dz.data_ptr() + i * hm_bytes for i in range(s_count)])
+            _lib.call('dsnt_head_step_fused_stacked', _lib.ptr_array(zcs), dz_ptrs,
                       s_count, _lib.dtype_id(zcs[0]), n, h, w, _lib.ptr(target), _lib.ptr(mask), None, reg_coeff, reg_id,
-                      sigma, flags, coords.data_ptr(), stats.data_ptr(), out8.data_ptr(), ws.data_ptr(), stream)
-        ctx.save_for_backward(target, mask, stats, out8, dz, *zcs)
+                      sigma, flags, ar.coords_ptr, ar.stats_ptr, ar.out8_ptr, ws.data_ptr(), stream)
+        ctx.save_for_backward(target, mask, ar.buf, *zcs)
+        ctx.dz_box = [dz]
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, [z.shape for z in zs])
         ctx.set_materialize_grads(False)
-        aux['out8'] = out8
+        aux['out8'] = ar.out8()
         lead = zs[0].shape[:-2]
-        return (out8[6],) + tuple(coords[i].view(*lead, 2) for i in range(s_count))
+        coords = ar.coords().view(s_count, n, 2)
+        return (aux['out8'][6],) + tuple(coords[i].view(*lead, 2) for i in range(s_count))
 
     @staticmethod
     def backward(ctx, g_loss, *g_coords):
-        target, mask, stats, out8, dz = ctx.saved_tensors[:5]
-        zcs = ctx.saved_tensors[5:]
+        target, mask, arena = ctx.saved_tensors[:3]
+        zcs = ctx.saved_tensors[3:]
         n, h, w, reg_id, sigma, reg_coeff, flags, shapes = ctx.meta
         s_count = len(zcs)
         dev = zcs[0].device
@@ -456,17 +522,23 @@ class _FusedHeadStackedStep(torch.autograd.Function):
             stream = _lib.stream_of(zcs[0])
             if g_loss is not None:
                 g_loss = g_loss.to(torch.float32).contiguous()
-            if all(g is None for g in g_coords):
+            dz = ctx.dz_box[0]
+            no_gc = all(g is None for g in g_coords)
+            if no_gc and dz is not None:
+                ctx.dz_box[0] = None
                 _lib.call('dsnt_scale_unless_one', dz.data_ptr(), _lib.dtype_id(dz), dz.numel(), g_loss.data_ptr(), stream)
                 return (None,) * 7 + tuple(dz[i].view(shape) for i, shape in enumerate(shapes))
-            gc = torch.zeros(s_count, n, 2, dtype=torch.float32, device=dev)
-            for i, g in enumerate(g_coords):
-                if g is not None:
-                    gc[i] = g.reshape(n, 2).to(torch.float32)
+            gc = None
+            if not no_gc:
+                gc = torch.zeros(s_count, n, 2, dtype=torch.float32, device=dev)
+                for i, g in enumerate(g_coords):
+                    if g is not None:
+                        gc[i] = g.reshape(n, 2).to(torch.float32)
             dzs = [torch.empty_like(z) for z in zcs]
+            base = arena.data_ptr()
             _lib.call('dsnt_head_bwd_stacked', _lib.ptr_array(zcs), _lib.ptr_array(dzs), s_count,
-                      _lib.dtype_id(zcs[0]), 1, n, h, w, _lib.ptr(target), _lib.ptr(mask), stats.data_ptr(),
-                      gc.data_ptr(), None, _lib.ptr(g_loss), out8[3:4].data_ptr() if g_loss is not None else None,
+                      _lib.dtype_id(zcs[0]), 1, n, h, w, _lib.ptr(target), _lib.ptr(mask), base,
+                      _lib.ptr(gc), None, _lib.ptr(g_loss), base + 48 * s_count * n + 12 if g_loss is not None else None,
                       reg_coeff, reg_id, sigma, flags, 0, stream)
         return (None,) * 7 + tuple(d.view(shape) for d, shape in zip(dzs, shapes))
 
@@ -502,6 +574,7 @@ def dsnt_head_stacked(zs, target, mask=None, reg='none', sigma=None, reg_coeff=1
     aux = {}
     sharded = _is_sharded(group)
     if (one_pass and not sharded and target is not None and n > 0
+            and torch.is_grad_enabled() and any(z.requires_grad for z in zs)      # validation under no_grad: forward only
             and _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zs[0]), h, w, _lib.REG_IDS[reg], float(sigma))):
         out = _FusedHeadStackedStep.apply(target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff), flags, aux, *zs)
     else:

@@ -185,12 +185,16 @@ def install_as_dsnt_nn():
     """Register this package's `nn` module as `dsnt.nn` so the reference's own `dsnt/model.py` (which does
     `import dsnt.nn` and `from dsnt.nn import euclidean_loss, thresholded_softmax`, model.py:15-16) binds to the
     CUDA operators.  Must run BEFORE `dsnt.model` is imported (SURVEY.md 8b binding note)."""
+    import importlib
     import sys
     pkg = sys.modules.get('dsnt')
     if pkg is None:
-        pkg = types.ModuleType('dsnt')
-        pkg.__path__ = []
-        sys.modules['dsnt'] = pkg
+        try:
+            pkg = importlib.import_module('dsnt')      # the reference's package (its __init__ is empty): keeps dsnt.model importable
+        except ImportError:
+            pkg = types.ModuleType('dsnt')
+            pkg.__path__ = []
+            sys.modules['dsnt'] = pkg
     sys.modules['dsnt.nn'] = dnn
     pkg.nn = dnn
     return dnn

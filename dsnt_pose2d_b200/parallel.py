@@ -54,7 +54,7 @@ class PeerExchange:
     `PeerExchange.get(group, device)` returns None where that is not possible (single rank, no symmetric memory,
     DSNT_PEER_EXCHANGE=0); the caller then all-reduces with NCCL."""
 
-    _cache = {}
+    _cache = {}        # (ranks of the group, its name, device index) -> (weakref to the group, PeerExchange or None)
 
     def __init__(self, group, device):
         import torch.distributed as dist
@@ -76,12 +76,12 @@ class PeerExchange:
         self.peers = (ctypes.c_void_p * self.world)(*ptrs)
         self.state = torch.zeros(2, dtype=torch.int32, device=device)     # [epoch, error]
         torch.cuda.synchronize(device)
-        dist.barrier(group)            # every buffer is zero before anybody's first exchange can land in it
+        self._args = (ctypes.cast(self.peers, ctypes.c_void_p), self.rank, self.world, self.state[0:1].data_ptr(),
+                      self.state[1:2].data_ptr())
 
     def args(self):
         """(peers, rank, world, epoch*, error*) as the *_peer entry points take them."""
-        return (ctypes.cast(self.peers, ctypes.c_void_p), self.rank, self.world, self.state[0:1].data_ptr(),
-                self.state[1:2].data_ptr())
+        return self._args
 
     def check(self):
         """Host read of the error flag (a peer that never arrived); not called on the hot path."""
@@ -89,7 +89,25 @@ class PeerExchange:
             raise RuntimeError('peer exchange timed out: a rank of the group did not take part')
 
     @classmethod
+    def check_all(cls):
+        """`check()` for every exchange of this process: call where the host synchronises anyway (after a bench run, when
+        the coordinates are copied out, when a loss is not finite)."""
+        for _, px in list(cls._cache.values()):
+            if px is not None:
+                px.check()
+
+    @staticmethod
+    def _key(group, device):
+        import torch.distributed as dist
+        try:
+            ranks = tuple(dist.get_process_group_ranks(group))
+        except Exception:          # noqa: BLE001
+            ranks = (dist.get_world_size(group),)
+        return ranks, getattr(group, 'group_name', None), torch.device(device).index
+
+    @classmethod
     def get(cls, group, device):
+        import weakref
         import torch.distributed as dist
         if group is None or not dist.is_available() or not dist.is_initialized():
             return None
@@ -97,12 +115,28 @@ class PeerExchange:
             return None
         if dist.get_backend(group) != 'nccl' or torch.device(device).type != 'cuda':
             return None
-        key = (id(group), torch.device(device).index)
-        if key not in cls._cache:
-            try:
-                cls._cache[key] = cls(group, torch.device(device))
-            except Exception as e:          # noqa: BLE001  (no symmetric memory on this system: NCCL all-reduce instead)
+        key = cls._key(group, device)
+        hit = cls._cache.get(key)
+        if hit is not None and hit[0]() is group:      # a NEW group with the ranks and name of a destroyed one rebuilds
+            return hit[1]
+        px, why = None, None
+        try:
+            px = cls(group, torch.device(device))
+        except Exception as e:          # noqa: BLE001  (no symmetric memory on this system: NCCL all-reduce instead)
+            why = e
+        # Every rank must end up on the SAME transport: a rank that fell back to NCCL while the others spin in the peer
+        # exchange would hang them until the 20 s timeout.  Agree on the minimum, which is also the barrier that makes sure
+        # every buffer is zero before anybody's first exchange can land in it.
+        ok = torch.tensor([1 if px is not None else 0], dtype=torch.int32, device=torch.device(device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if px is None or why is not None:
                 import warnings
-                warnings.warn('dsnt_pose2d_b200: peer exchange unavailable (%s); using NCCL all-reduce' % (e,))
-                cls._cache[key] = None
-        return cls._cache[key]
+                warnings.warn('dsnt_pose2d_b200: peer exchange unavailable (%s); using NCCL all-reduce' % (why,))
+            px = None
+        try:
+            ref = weakref.ref(group)
+        except TypeError:
+            ref = (lambda g: (lambda: g))(group)
+        cls._cache[key] = (ref, px)
+        return px

@@ -137,14 +137,20 @@ DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, cons
                             float* coords, float* stats, float* terms, void* dz, void* stream);
 DSNT_API int dsnt_mask_count(const float* mask, long n, float* out, float* workspace, void* stream);
 /*
- * The same step in ONE launch (single process; csrc/head_step2.cuh): every CTA adds up the mask itself while its first
- * bulk loads are in flight (no dsnt_mask_count), and the CTA that finishes last composes the loss (no dsnt_finish_loss):
- * out[0..7] exactly as dsnt_finish_loss documents, workspace likewise.  Served for the shapes / regularisers of the
- * shape-specialised kernel (dsnt_head_step_fused_supported: 64x64, not KL, Gaussian window within its register slots);
- * otherwise DSNT_ERR_UNSUPPORTED and the caller uses the three-launch form.  A sharded batch uses the three-launch form
- * with the *_peer reductions (the denominator then needs the other ranks' masks before the step can start).
+ * The same step in ONE launch (csrc/head_step2.cuh): every CTA adds up its slice of the mask while its first bulk loads
+ * are in flight and draws a ticket; the CTA with the last ticket publishes the count, which every warp picks up only
+ * before its first BACKWARD (the forward does not need the denominator) -- no dsnt_mask_count, no grid barrier; and the
+ * CTA that finishes last composes the loss (no dsnt_finish_loss): out[0..7] exactly as dsnt_finish_loss documents,
+ * workspace likewise.  The grid (one CTA per SM) is launched with the cooperative attribute, so its co-residency is
+ * guaranteed by the driver.  Served for the shapes / regularisers of the shape-specialised kernel
+ * (dsnt_head_step_fused_supported: 64x64, not KL, Gaussian window within its register slots); otherwise
+ * DSNT_ERR_UNSUPPORTED and the caller uses the three-launch form.  A sharded batch: dsnt_head_step_fused_peer below.
+ * dsnt_finish_trace_offset_bytes: byte offset inside the workspace of eight uint64 %globaltimer stamps the last
+ *   single-launch step left there (diagnostics; bench.py's per-rank timeline): [0] kernel start, [1] local mask count known,
+ *   [2] count published (sharded: after the exchange with the other ranks), [3] last CTA done, [4] loss block written.
  */
 DSNT_API int dsnt_head_step_fused_supported(int dtype, int H, int W, int reg, float sigma);
+DSNT_API int dsnt_finish_trace_offset_bytes(void);
 DSNT_API int dsnt_head_step_fused(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
                                   const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords,
                                   float* stats, void* dz, float* out, float* workspace, void* stream);
@@ -237,8 +243,9 @@ DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, flo
 /*
  * Sharded batch (one process per GPU of a node): the same reductions with the exchange of the partial sums between
  * the ranks fused into the kernel -- no NCCL launch, no separate combine.  The last CTA stores (out[0], out[1], out[2])
- * into every rank's exchange buffer over NVLink peer mappings, waits for all ranks' slots in its own buffer and adds
- * them in rank order, so every rank finishes with the same out[0..7] as one process on the whole batch would.
+ * into every rank's exchange buffer over NVLink peer mappings (each value as one 64-bit word {float, epoch}: no fence, no
+ * flag), waits for all ranks' words in its own buffer and adds them in rank order, so every rank finishes with the same
+ * out[0..7] as one process on the whole batch would.
  *   replaces: nothing in the reference (single GPU, src/dsnt/bin/train.py:220); it is what makes masked_average
  *             (src/dsnt/nn.py:81-94) mean "over the global batch" when the batch dimension is sharded.
  *   peers     HOST array of `world` DEVICE pointers; peers[r] is rank r's exchange buffer as mapped into this process
@@ -252,9 +259,11 @@ DSNT_API int dsnt_finish_loss_peer(const float* terms, const float* mask, long n
                                    unsigned* epoch, int* error, void* stream);
 DSNT_API int dsnt_mask_count_peer(const float* mask, long n, float* out, float* workspace, const void* const* peers,
                                   int rank, int world, unsigned* epoch, int* error, void* stream);
-/* The single-launch step (dsnt_head_step_fused) on a sharded batch: the mask count crosses the ranks at the start of the
- * kernel (CTA 0 exchanges, the other CTAs of the grid wait for its result) and the loss sums at its end (the CTA with
- * the last ticket) -- one launch per rank and step, no collective call.  n > 0 on every rank. */
+/* The single-launch step (dsnt_head_step_fused) on a sharded batch: the CTA that publishes the mask count first exchanges
+ * it with the other ranks (hidden behind the first loads and the first forward of every warp, as the count itself), and
+ * the CTA with the last ticket exchanges the loss sums at the end -- one launch per rank and step, no collective call.
+ * n > 0 on this rank; a rank with an empty shard issues dsnt_mask_count_peer + dsnt_finish_loss_peer instead and meets
+ * the others in the same two exchanges. */
 DSNT_API int dsnt_head_step_fused_peer(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
                                        const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords,
                                        float* stats, void* dz, float* out, float* workspace, const void* const* peers,

@@ -147,7 +147,7 @@ def test_step_support_queries_are_host_logic(libpath):
     assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['js']) == 0
     assert lib.dsnt_head_step_supported_reg(bf16, 256, 256, reg['js']) == 1                      # L2-staged form
     # exchange buffer of the peer reductions: two parities x 16 ranks x float4
-    assert lib.dsnt_peer_exchange_bytes() == 2 * 16 * 16
+    assert lib.dsnt_peer_exchange_bytes() == 2 * 16 * 4 * 8     # two parities x 16 ranks x 4 words of 8 bytes
     assert lib.dsnt_finish_workspace_bytes() >= (256 * 4 + 4 + 256) * 4
 
 
@@ -194,3 +194,53 @@ def test_one_pass_dispatch_rule_without_gpu():
     assert head._step_pays(big, 64, 64, kl, 2.0 / 64, None)              # KL, 1 GiB: the saved read pays
     odd = FakeZ(1024, 28, 28, torch.float32)
     assert not head._step_pays(odd, 28, 28, js, 2.0 / 28, None)
+
+
+def test_sharded_path_decision_does_not_depend_on_the_local_shard():
+    """the one-pass step exchanges twice per step (mask count, loss sums), the two-kernel path once; with uneven
+    or empty shards a decision taken from the LOCAL shard size made the ranks issue different numbers of exchanges.
+    Sharded, the decision is a function of dtype / shape / regulariser only."""
+    from dsnt_pose2d_b200 import head
+    from dsnt_pose2d_b200.parallel import shard_range
+    sigma = 2.0 / 64
+    # the advisor's example: 255 samples of 16x64x64 fp32 on 2 ranks = 128 | 127 samples, astride the 32 MiB threshold
+    for batch, world in ((255, 2), (7, 8), (1, 2), (4099, 8), (0, 2)):
+        for reg in ('js', 'kl', 'var', 'none', 'mse'):
+            for dtype in (torch.float32, torch.bfloat16):
+                picks = set()
+                for r in range(world):
+                    lo, hi = shard_range(batch, r, world)
+                    z = torch.empty(hi - lo, 16, 64, 64, dtype=dtype)
+                    picks.add(head.takes_one_pass(z, reg, sigma, sharded=True))
+                assert len(picks) == 1, (batch, world, reg, dtype, picks)
+    # single process: the size of the batch still matters (8 MiB of KL logits: two kernels are one launch fewer)
+    assert not head.takes_one_pass(torch.empty(32, 16, 64, 64), 'kl', sigma, sharded=False)
+    assert head.takes_one_pass(torch.empty(32, 16, 64, 64), 'kl', sigma, sharded=True)
+    # the shape decides everywhere: 7x7 has no 16-byte vectors
+    assert not head.takes_one_pass(torch.empty(4, 16, 7, 7), 'js', 2.0 / 7, sharded=True)
+
+
+def test_step_arena_layout():
+    """One allocation for the small outputs of a one-pass step: stats 16-byte aligned, coords / terms 8-byte aligned."""
+    from dsnt_pose2d_b200.head import _StepArena
+    for n in (0, 1, 3, 512, 65536):
+        ar = _StepArena(n, torch.device('cpu'))
+        assert ar.buf.numel() == 12 * n + 16
+        assert ar.stats_ptr % 16 == 0 and ar.coords_ptr % 8 == 0 and ar.terms_ptr % 8 == 0 and ar.out8_ptr % 16 == 0
+        assert ar.coords_ptr == ar.buf[8 * n:].data_ptr() and ar.terms_ptr == ar.buf[10 * n:].data_ptr()
+        assert ar.out8_ptr == ar.out8().data_ptr() and ar.cnt8_ptr == ar.out8_ptr + 32
+        assert ar.coords().numel() == 2 * n and ar.out8().numel() == 8
+
+
+def test_bench_config_is_shared_by_both_arms():
+    """The reference arm is timed 'on your arm's config': bench.py builds the config dict of both arms with one function."""
+    import importlib
+    bench = importlib.import_module('bench')
+    for name in bench.WORKLOADS:
+        for world, scaling in ((1, 'weak'), (8, 'weak'), (8, 'strong')):
+            cfg = bench.workload_config(name, world, scaling)
+            assert cfg['workload'] == name and 'model' not in cfg
+            b = bench.WORKLOADS[name][0]
+            assert cfg['global_batch'] == (b * world if scaling == 'weak' else b)
+    assert bench.rotation(65536, 64, 64, 4) == 1 and bench.rotation(512, 64, 64, 4) > 8
+    assert bench.DEFAULT_WORKLOAD == 'cfg4_64x64_f32_js'

@@ -1,0 +1,240 @@
+"""The reference's OWN model classes (src/dsnt/model.py: ResNetHumanPoseModel, HourglassHumanPoseModel) driven on the GPU
+with this library's head -- BASELINE configs 2 and 3 -- against the same model objects with the reference's own head.
+
+The unmodified reference is pip-installed under baseline/_ref by tools/install_ref.sh (git-ignored, travels to the GPU box);
+without it these tests skip.  `dsnt.model` imports `dsnt.data`, which needs anibali/torchdata's `torchdata.mpii`
+(requirements.txt:18; absent from the image): a five-name stub is registered for it, as SURVEY.md 8c describes.
+Mirrors /root/reference/tests/test_model.py:11-63 (shapes with truncate / dilate, one SGD step moves every parameter).
+
+Tolerances: coordinates 1e-5 max-abs, loss 1e-5 relative, dL/dZ at the head input and every parameter gradient 2e-5
+L2-relative -- against the reference's own fp32 eager result, which is itself 1e-7 ... 4e-5 from fp64."""
+
+import copy
+import os
+import subprocess
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, 'baseline', '_ref')
+DEV = 'cuda:0'
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'dsnt', 'model.py')),
+                                 reason='baseline/_ref is absent (tools/install_ref.sh needs /root/reference)')]
+
+STUB = '''
+import sys, types
+mp = types.ModuleType('torchdata.mpii')
+class MpiiData:            # src/dsnt/data.py:15 only needs the names at import time
+    def __init__(self, *a, **k): raise RuntimeError('stub')
+mp.MpiiData = MpiiData
+mp.MPII_Joint_Horizontal_Flips = [5, 4, 3, 2, 1, 0, 6, 7, 8, 9, 15, 14, 13, 12, 11, 10]
+mp.MPII_Image_Mean = [0.44, 0.40, 0.37]
+mp.MPII_Image_Stddev = [0.25, 0.24, 0.24]
+mp.transform_keypoints = lambda kp, m: kp
+try:
+    import torchdata as td
+except ImportError:
+    td = types.ModuleType('torchdata'); td.__path__ = []; sys.modules['torchdata'] = td
+td.mpii = mp
+sys.modules['torchdata.mpii'] = mp
+'''
+
+
+@pytest.fixture(scope='module')
+def ref_model():
+    """The reference's dsnt.model, bound to the reference's own dsnt.nn."""
+    exec(STUB, {})
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+    warnings.filterwarnings('ignore')
+    for name in [m for m in sys.modules if m == 'dsnt' or m.startswith('dsnt.')]:
+        del sys.modules[name]
+    import dsnt.model as rm
+    assert os.path.realpath(rm.__file__).startswith(os.path.realpath(REF))
+    assert os.path.realpath(rm.dsnt.nn.__file__).startswith(os.path.realpath(REF))      # the reference's own operators
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    return rm
+
+
+@pytest.fixture(scope='module')
+def dp():
+    import dsnt_pose2d_b200
+    return dsnt_pose2d_b200
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _train_step(model, x, target, mask):
+    """model(x) -> forward_loss -> backward, as src/dsnt/bin/train.py:355-381; returns what the comparison needs."""
+    model.zero_grad(set_to_none=True)
+    z = model.forward_part1(x)
+    zs = z if isinstance(z, (list, tuple)) else [z]
+    for t in zs:
+        t.retain_grad()
+    out = model.forward_part2(z)
+    loss = model.forward_loss(out, target, mask)
+    loss.backward()
+    torch.cuda.synchronize()
+    coords = model.compute_coords(out)
+    return {'loss': loss.item(), 'coords': coords, 'dz': [t.grad.clone() for t in zs],
+            'grads': {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None},
+            'heatmaps': model.heatmaps.detach().clone()}
+
+
+def _compare(a, b, what, tol_grad=2e-5):
+    e_loss = abs(a['loss'] - b['loss']) / abs(b['loss'])
+    e_coords = (a['coords'] - b['coords']).abs().max().item()
+    e_dz = max(_rel(x, y) for x, y in zip(a['dz'], b['dz']))
+    assert set(a['grads']) == set(b['grads']) and len(b['grads']) > 0
+    worst = max(((_rel(a['grads'][n], b['grads'][n]), n) for n in b['grads']))
+    e_hm = (a['heatmaps'] - b['heatmaps']).abs().max().item()
+    print('%s: loss %.2e coords %.2e dZ %.2e worst parameter gradient %.2e (%s) of %d; heatmaps %.2e'
+          % (what, e_loss, e_coords, e_dz, worst[0], worst[1], len(b['grads']), e_hm))
+    assert e_loss < 1e-5 and e_coords < 1e-5 and e_dz < tol_grad and worst[0] < tol_grad and e_hm < 1e-6
+
+
+def _head_cost(dp, model, x, target, mask, steps=5):
+    """Head time and launches inside the full training step (CUDA events around every entry point of the library)."""
+    from dsnt_pose2d_b200 import _lib
+    for _ in range(2):
+        _train_step(model, x, target, mask)
+    names = [n for n in _lib.SIGNATURES if n.startswith('dsnt_') and 'supported' not in n and 'bytes' not in n
+             and n not in ('dsnt_b200_version', 'dsnt_b200_last_error')]
+    _lib.event_log = {n: [] for n in names}
+    before = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        _train_step(model, x, target, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    logs, _lib.event_log = _lib.event_log, None
+    head_us = sum(sum(a.elapsed_time(b) for a, b in v) for v in logs.values()) / steps * 1e3
+    used = {k: len(v) // steps for k, v in logs.items() if v}
+    return head_us, (_lib.launch_count - before) / steps, e0.elapsed_time(e1) / steps, used
+
+
+def test_resnet34_cfg2_matches_reference_head(ref_model, dp):
+    """BASELINE config 2: ResNet-34, dilate=2 (28x28 heatmaps), batch 64 at 224x224, JS regulariser."""
+    import torchvision
+    torch.manual_seed(0)
+    ref = ref_model.ResNetHumanPoseModel(torchvision.models.resnet34(), n_chans=16, dilate=2, output_strat='dsnt',
+                                         reg='js', reg_coeff=1.0, hm_sigma=1.0).to(DEV)
+    ours = dp.attach_fused_head(copy.deepcopy(ref))
+    assert type(ours).__name__ == 'ResNetHumanPoseModelB200' and isinstance(ours, ref_model.ResNetHumanPoseModel)
+    x = torch.rand(64, 3, 224, 224, device=DEV)
+    target = torch.rand(64, 16, 2, device=DEV) * 1.6 - 0.8
+    mask = (torch.rand(64, 16, device=DEV) > 0.1).float()
+    a = _train_step(ref, x, target, mask)
+    b = _train_step(ours, x, target, mask)
+    assert b['heatmaps'].shape == (64, 16, 28, 28)
+    _compare(b, a, 'resnet34 dilate=2 batch 64 (cfg 2)')
+    head_us, launches, step_ms, used = _head_cost(dp, ours, x, target, mask)
+    print('cfg 2 full training step %.1f ms; head: %.0f us in %d launches per step %r' % (step_ms, head_us, launches, used))
+
+
+def test_hourglass8_cfg3_matches_reference_head(ref_model, dp):
+    """BASELINE config 3: 8-stack hourglass, 64x64 heatmaps per stack, JS sigma = 1, batch 32 at 256x256."""
+    torch.manual_seed(0)
+    ref = ref_model.build_mpii_pose_model('hg8', output_strat='dsnt', reg='js', reg_coeff=1.0, hm_sigma=1.0).to(DEV)
+    ours = dp.attach_fused_head(copy.deepcopy(ref))
+    x = torch.rand(32, 3, 256, 256, device=DEV)
+    target = torch.rand(32, 16, 2, device=DEV) * 1.6 - 0.8
+    mask = (torch.rand(32, 16, device=DEV) > 0.1).float()
+    a = _train_step(ref, x, target, mask)
+    assert len(a['dz']) == 8 and a['heatmaps'].shape == (32, 16, 64, 64)
+    b = _train_step(ours, x, target, mask)
+    _compare(b, a, 'hourglass hg8 batch 32 (cfg 3)', tol_grad=5e-5)      # 8 stacks of backbone between the heads
+    head_us, launches, step_ms, used = _head_cost(dp, ours, x, target, mask, steps=3)
+    print('cfg 3 full training step %.1f ms; head: %.0f us in %d launches per step %r' % (step_ms, head_us, launches, used))
+    assert launches <= 4          # every stack's head in one fused launch (+ the coordinate kernel of forward_part2)
+
+
+@pytest.mark.parametrize('kw,hm', [({'truncate': 1}, 14), ({'dilate': 2}, 28), ({}, 7)])
+def test_shapes_like_reference_test_model(ref_model, dp, kw, hm):
+    """tests/test_model.py:11-39 with the fused head attached."""
+    import torchvision
+    model = dp.attach_fused_head(ref_model.ResNetHumanPoseModel(torchvision.models.resnet18(), n_chans=16, **kw).to(DEV))
+    sz = model.image_specs.size
+    assert sz == 224
+    out = model(torch.randn(1, 3, sz, sz, device=DEV))
+    assert out.shape == (1, 16, 2)
+    assert model.heatmaps.shape == (1, 16, hm, hm)
+    c = model.compute_coords(out)
+    assert c.device.type == 'cpu' and c.dtype == torch.float32
+
+
+def test_training_step_moves_every_parameter(ref_model, dp):
+    """tests/test_model.py:41-63: resnet18, reg='js', mask None, one SGD step."""
+    import torchvision
+    torch.manual_seed(1)
+    model = dp.attach_fused_head(ref_model.ResNetHumanPoseModel(torchvision.models.resnet18(), n_chans=16,
+                                                                output_strat='dsnt', reg='js').to(DEV))
+    old = [p.detach().clone() for p in model.parameters()]
+    opt = torch.optim.SGD(model.parameters(), lr=1.0)
+    x = torch.rand(1, 3, 224, 224, device=DEV)
+    target = torch.rand(1, 16, 2, device=DEV) * 2 - 1
+    loss = model.forward_loss(model(x), target, None)
+    loss.backward()
+    opt.step()
+    for p, o in zip(model.parameters(), old):
+        assert not torch.equal(p.detach(), o)
+
+
+INSTALL_SCRIPT = STUB + '''
+import sys, warnings
+warnings.filterwarnings('ignore')
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(ref)r)
+import torch, torchvision
+import dsnt_pose2d_b200 as dp
+ours_nn = dp.install_as_dsnt_nn()                 # BEFORE dsnt.model is imported (SURVEY.md 8b binding note)
+import dsnt.model as rm
+assert rm.dsnt.nn is ours_nn and rm.euclidean_loss is ours_nn.euclidean_loss
+assert rm.__file__.startswith(%(ref)r)
+from oracle import torch_port as tp
+torch.manual_seed(0)
+for build in ('resnet', 'hg2'):
+    if build == 'resnet':
+        model = rm.ResNetHumanPoseModel(torchvision.models.resnet18(), n_chans=16, dilate=2, reg='js').cuda()
+        x = torch.rand(2, 3, 224, 224, device='cuda')
+    else:
+        model = rm.build_mpii_pose_model('hg2', output_strat='dsnt', reg='js').cuda()
+        x = torch.rand(2, 3, 256, 256, device='cuda')
+    target = torch.rand(2, 16, 2, device='cuda') * 1.6 - 0.8
+    mask = (torch.rand(2, 16, device='cuda') > 0.2).float()
+    z = model.forward_part1(x)
+    zs = z if isinstance(z, list) else [z]
+    for t in zs: t.retain_grad()
+    out = model.forward_part2(z)                   # the reference's own code, our operators underneath
+    loss = model.forward_loss(out, target, mask)
+    loss.backward()
+    want = 0.0
+    for t in zs:
+        r = tp.head_loss_and_grad(t.detach(), target, mask, 'js', 1.0, 1.0, dtype=torch.float64)
+        want += r['loss'].item()
+        e = ((t.grad.cpu().double() - r['dz']).norm() / r['dz'].norm()).item()
+        assert e < 1e-5, (build, 'dz', e)
+    assert abs(loss.item() - want) / want < 1e-5, (build, loss.item(), want)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    print(build, 'ok', loss.item(), want)
+print('INSTALL-OK')
+'''
+
+
+def test_install_as_dsnt_nn_runs_the_reference_model_code_on_our_operators():
+    """`install_as_dsnt_nn()` before `import dsnt.model`: the reference's unmodified forward_part2 / forward_loss call this
+    library's level-1 operators (dsnt, euclidean_loss, js_reg_loss); loss and dL/dZ against the fp64 oracle."""
+    script = INSTALL_SCRIPT % {'root': ROOT, 'ref': REF}
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0 and 'INSTALL-OK' in r.stdout

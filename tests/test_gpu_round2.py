@@ -1,0 +1,233 @@
+"""Round-2 parity additions for the kernels bench.py times:
+
+  * the one-pass step (dsnt_head_step_fused / dsnt_head_step) at BASELINE cfg 4's FULL size -- 65 536 heatmaps -- against
+    the fp64 oracle: sampled heatmaps with the global denominator, and the global loss accumulated in fp64 over all heatmaps;
+  * autograd semantics of the one-pass node: a second backward (retain_graph) with d(loss) != 1, `z.grad.zero_()` between
+    backwards, two losses sharing one head call;
+  * the grid-wide count hand-off of the single-launch form on a second device / reordered CUDA_VISIBLE_DEVICES;
+  * sharded batch on 2 GPUs (skipped with fewer): both exchange mechanisms, the fused-peer form, uneven and EMPTY shards.
+
+Tolerances as everywhere: fp32 vs fp64 oracle 1e-5 (coords max-abs, loss relative, dZ L2-relative); bf16 dZ 4e-3."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = 'cuda:0'
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def dp():
+    import dsnt_pose2d_b200
+    return dsnt_pose2d_b200
+
+
+@pytest.fixture(scope='module')
+def cf():
+    from oracle import closed_form
+    return closed_form
+
+
+def oracle_chunks(cf, z, target, mask, reg, sigma, coeff, chunk=4096):
+    """fp64 loss of the WHOLE batch, chunk by chunk through the CPU restatement of the reference (oracle/torch_port.py,
+    forward only): each chunk's masked averages are turned back into sums and divided by the GLOBAL denominator.
+    z [N,H,W] on any device; sigma is in normalised units (hm_sigma = sigma * W / 2)."""
+    from oracle import torch_port as tp
+    n, h, w = z.shape
+    mk = torch.ones(n, dtype=torch.float64) if mask is None else mask.double().cpu()
+    denom = max(mk.sum().item(), 1.0)
+    sd = sr = 0.0
+    with torch.no_grad():
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            m = mk[lo:hi].view(1, -1)
+            local = max(m.sum().item(), 1.0)
+            _, _, euc, rv = tp.head_loss(z[lo:hi].double().cpu().view(1, hi - lo, h, w), target[lo:hi].double().cpu().view(1, -1, 2),
+                                         m, reg, sigma * w / 2.0, coeff)
+            sd += float(euc) * local
+            sr += float(rv) * local
+    return {'denom': denom, 'euclid': sd / denom, 'reg': sr / denom, 'loss': sd / denom + coeff * sr / denom}
+
+
+def oracle_slice(cf, z, target, mask, idx, denom, reg, sigma, coeff):
+    """coords and dZ of the heatmaps `idx` under the GLOBAL denominator."""
+    mk = np.ones(len(idx)) if mask is None else mask[idx].double().cpu().numpy()
+    r = cf.head(z[idx].double().cpu().numpy(), target[idx].double().cpu().numpy(), mk, reg=reg, sigma=sigma, reg_coeff=coeff)
+    local = max(mk.sum(), 1.0)
+    return r['coords'], r['dz'] * (local / denom)
+
+
+@pytest.mark.parametrize('reg,dtype', [('js', torch.float32), ('var', torch.float32), ('mse', torch.float32),
+                                       ('js', torch.bfloat16)])
+def test_cfg4_full_size_one_pass_vs_oracle(dp, cf, reg, dtype):
+    """The benched kernel at the benched size: 4096 x 16 x 64x64, one_pass=True."""
+    from dsnt_pose2d_b200 import _lib
+    torch.manual_seed(0)
+    b, c, h, w = 4096, 16, 64, 64
+    z = torch.randn(b, c, h, w, device=DEV).to(dtype)
+    target = torch.rand(b, c, 2, device=DEV) * 1.6 - 0.8
+    mask = (torch.rand(b, c, device=DEV) > 0.1).float()
+    z.requires_grad_(True)
+    before = _lib.launch_count
+    out = dp.dsnt_head(z, target, mask, reg=reg, hm_sigma=1.0, one_pass=True)
+    assert _lib.launch_count - before == 1                     # dsnt_head_step_fused: the single-launch form
+    out.loss.backward()
+    torch.cuda.synchronize()
+    dz = z.grad
+    zf = z.detach().float().view(b * c, h, w)
+    tf, mf = target.view(-1, 2), mask.view(-1)
+    glob = oracle_chunks(cf, zf, tf, mf, reg, 2.0 / w, 1.0)
+    assert abs(out.loss.item() - glob['loss']) / glob['loss'] < TOL
+    assert abs(out.euclid.item() - glob['euclid']) / glob['euclid'] < TOL
+    if glob['reg'] > 0:
+        assert abs(out.reg.item() - glob['reg']) / glob['reg'] < TOL
+    gen = np.random.default_rng(0)
+    idx = np.unique(np.concatenate([gen.integers(0, b * c, 250), [0, 1, 147, 148, 149, b * c - 149, b * c - 2, b * c - 1]]))
+    coords, dzo = oracle_slice(cf, zf, tf, mf, torch.from_numpy(idx).to(DEV), glob['denom'], reg, 2.0 / w, 1.0)
+    got_c = out.coords.detach().view(-1, 2)[idx].double().cpu().numpy()
+    got_dz = dz.view(b * c, h, w)[idx].double().cpu().numpy()
+    assert np.abs(got_c - coords).max() < TOL
+    e = rel_l2(got_dz, dzo)
+    print('cfg4 full size one-pass %s %s: loss %.2e dz %.2e' % (reg, dtype, abs(out.loss.item() - glob['loss']) / glob['loss'], e))
+    assert e < (TOL if dtype == torch.float32 else 4e-3)
+    # size-independent property over ALL heatmaps: every heatmap's gradient sums to zero
+    sums = dz.float().view(b * c, -1).sum(-1)
+    scale = dz.float().view(b * c, -1).abs().sum(-1).clamp_min(1e-30)
+    assert (sums.abs() / scale).max().item() < (1e-4 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize('reg', ['none', 'var', 'kl', 'js', 'mse'])
+def test_many_heatmaps_one_pass_vs_oracle_not_vs_two_kernel(dp, cf, reg):
+    """600 x 16 heatmaps (more than one wave of warps) and the cfg 1 shape: against the ORACLE (global denominator)."""
+    from dsnt_pose2d_b200 import head
+    old, head.STEP_MIN_BYTES = head.STEP_MIN_BYTES, 0
+    try:
+        for (b, c, h, w) in ((600, 16, 64, 64), (32, 16, 64, 64), (64, 16, 28, 28)):
+            gen = torch.Generator().manual_seed(51)
+            z = torch.randn(b, c, h, w, generator=gen).to(DEV).requires_grad_(True)
+            target = (torch.rand(b, c, 2, generator=gen) * 1.6 - 0.8).to(DEV)
+            mask = (torch.rand(b, c, generator=gen) > 0.1).float().to(DEV)
+            out = dp.dsnt_head(z, target, mask, reg=reg, hm_sigma=1.0, one_pass=True)
+            out.loss.backward()
+            zf, tf, mf = z.detach().view(b * c, h, w), target.view(-1, 2), mask.view(-1)
+            glob = oracle_chunks(cf, zf, tf, mf, reg, 2.0 / w, 1.0)
+            assert abs(out.loss.item() - glob['loss']) / glob['loss'] < TOL
+            idx = torch.arange(0, b * c, max(1, (b * c) // 300), device=DEV)
+            coords, dzo = oracle_slice(cf, zf, tf, mf, idx, glob['denom'], reg, 2.0 / w, 1.0)
+            assert np.abs(out.coords.detach().view(-1, 2)[idx].double().cpu().numpy() - coords).max() < TOL
+            assert rel_l2(z.grad.view(b * c, h, w)[idx].double().cpu().numpy(), dzo) < TOL
+    finally:
+        head.STEP_MIN_BYTES = old
+
+
+# ------------------------------------------------------------------------------------------- autograd semantics
+def _inputs(b=8, seed=3, dtype=torch.float32):
+    gen = torch.Generator().manual_seed(seed)
+    z = torch.randn(b, 16, 64, 64, generator=gen).to(DEV).to(dtype)
+    target = (torch.rand(b, 16, 2, generator=gen) * 1.6 - 0.8).to(DEV)
+    mask = (torch.rand(b, 16, generator=gen) > 0.2).float().to(DEV)
+    return z, target, mask
+
+
+@pytest.mark.parametrize('stacked', [False, True])
+def test_second_backward_with_retain_graph_is_not_scaled_twice(dp, stacked):
+    """the stored gradient was scaled in place on every backward."""
+    z, target, mask = _inputs()
+    zs = [z.clone().requires_grad_(True) for _ in range(3 if stacked else 1)]
+
+    def loss_of():
+        if stacked:
+            return dp.dsnt_head_stacked(zs, target, mask, reg='js', hm_sigma=1.0, one_pass=True)[1]
+        return dp.dsnt_head(zs[0], target, mask, reg='js', hm_sigma=1.0, one_pass=True).loss
+    loss = loss_of()
+    (loss * 3.0).backward(retain_graph=True)
+    g1 = [t.grad.clone() for t in zs]
+    for t in zs:
+        t.grad.zero_()                        # must not corrupt what a later backward hands out
+    (loss * 3.0).backward(retain_graph=True)
+    g2 = [t.grad.clone() for t in zs]
+    for t in zs:
+        t.grad = None
+    loss.backward()
+    g3 = [t.grad.clone() for t in zs]
+    # reference: the two-kernel path, which recomputes the gradient on every backward
+    zr = [z.clone().requires_grad_(True) for _ in zs]
+    if stacked:
+        lr = dp.dsnt_head_stacked(zr, target, mask, reg='js', hm_sigma=1.0, one_pass=False)[1]
+    else:
+        lr = dp.dsnt_head(zr[0], target, mask, reg='js', hm_sigma=1.0, one_pass=False).loss
+    lr.backward()
+    for a, b2, c3, r in zip(g1, g2, g3, zr):
+        assert ((a - 3.0 * r.grad).norm() / (3.0 * r.grad.norm())).item() < 2e-6
+        assert ((b2 - 3.0 * r.grad).norm() / (3.0 * r.grad.norm())).item() < 2e-6      # NOT 9x
+        assert ((c3 - r.grad).norm() / r.grad.norm()).item() < 2e-6
+
+
+def test_two_losses_share_one_head_call(dp):
+    z, target, mask = _inputs(seed=4)
+    zz = z.clone().requires_grad_(True)
+    out = dp.dsnt_head(zz, target, mask, reg='js', hm_sigma=1.0, one_pass=True)
+    total = out.loss * 2.0 + out.coords.sum() * 0.5          # coords gradient as well: the regular backward kernel
+    total.backward()
+    zr = z.clone().requires_grad_(True)
+    ref = dp.dsnt_head(zr, target, mask, reg='js', hm_sigma=1.0, one_pass=False)
+    (ref.loss * 2.0 + ref.coords.sum() * 0.5).backward()
+    assert ((zz.grad - zr.grad).norm() / zr.grad.norm()).item() < 2e-6
+
+
+def test_validation_under_no_grad_takes_the_forward_only_path(dp):
+    """the stacked one-pass step ran (and allocated dL/dz for every stack) under torch.no_grad()."""
+    from dsnt_pose2d_b200 import _lib
+    z, target, mask = _inputs(b=4)
+    zs = [z.clone().requires_grad_(True) for _ in range(4)]
+    with torch.no_grad():
+        _lib.event_log = {'dsnt_head_step_fused_stacked': [], 'dsnt_head_fwd_stacked': []}
+        coords, loss = dp.dsnt_head_stacked(zs, target, mask, reg='js', hm_sigma=1.0, one_pass=True)
+        logs, _lib.event_log = _lib.event_log, None
+    assert len(logs['dsnt_head_fwd_stacked']) == 1 and not logs['dsnt_head_step_fused_stacked']
+    coords2, loss2 = dp.dsnt_head_stacked(zs, target, mask, reg='js', hm_sigma=1.0, one_pass=True)
+    assert abs(loss.item() - loss2.item()) / loss2.item() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------- devices
+def test_second_device_in_one_process(dp):
+    """Launch attributes are cached per DEVICE (the shared-memory opt-in was cached once per process)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two devices')
+    z, target, mask = _inputs(b=16)
+    res = []
+    for dev in ('cuda:0', 'cuda:1', 'cuda:0'):
+        zz = z.to(dev).requires_grad_(True)
+        out = dp.dsnt_head(zz, target.to(dev), mask.to(dev), reg='js', hm_sigma=1.0, one_pass=True)
+        out.loss.backward()
+        res.append((out.loss.item(), zz.grad.cpu()))
+    assert res[0][0] == res[1][0] == res[2][0]
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][1], res[2][1])
+
+
+SHARDED = os.path.join(ROOT, 'tools', 'check_sharded.py')
+
+
+@pytest.mark.parametrize('env', [{}, {'DSNT_PEER_EXCHANGE': '0'}, {'DSNT_FUSED_PEER_STEP': '0'}])
+def test_sharded_two_gpus(env):
+    """2 ranks (torchrun, NCCL): sharded loss / gradients == the single-process ones on the concatenated batch, identical
+    loss on every rank; peer-memory exchange, NCCL all-reduce exchange, and the three-launch form."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two devices')
+    e = dict(os.environ)
+    e.update(env)
+    port = 29700 + os.getpid() % 200
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', str(port), SHARDED], env=e, capture_output=True,
+                       text=True, timeout=600)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0 and 'check_sharded: PASS' in r.stdout
