@@ -589,7 +589,7 @@ def exchange_timeline(cx, head, steps=40):
     def med(col_a, col_b):
         d = ((st[:, col_b] - st[:, col_a]).double() / 1e3).sort().values
         return float(d[len(d) // 2])
-    mine = {'rank': cx.rank, 'step_us_median_eager': step_us[len(step_us) // 2],
+    mine = {'rank': cx.rank, 'step_us_median_eager': step_us[len(step_us) // 2], 'entry_to_first_sync_us': med(5, 0), 'entry_to_loads_issued_us': med(5, 6),
             'start_to_local_count_us': med(0, 1), 'count_exchange_us': med(1, 2),
             'start_to_last_cta_done_us': med(0, 3), 'loss_exchange_and_compose_us': med(3, 4),
             'kernel_us': med(0, 4)}

@@ -83,14 +83,28 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
 
 // x *= *g unless *g == 1 (then nothing is read or written): lets the one-pass step hand out the gradient it already
 // computed for d(loss) = 1 and stay exact -- and CUDA-graph capturable -- for any other upstream gradient.
+constexpr int kScaleBlock = 1024;
 template <typename T>
-__global__ void __launch_bounds__(256) scale_unless_one_kernel(T* __restrict__ x, long nvec16, long numel,
-                                                               const float* __restrict__ g) {
+__global__ void __launch_bounds__(kScaleBlock) scale_unless_one_kernel(T* __restrict__ x, long nvec16, long numel,
+                                                                       const float* __restrict__ g) {
   const float s = __ldg(g);
   if (s == 1.0f) return;
   constexpr int PER = 16 / sizeof(T);
+  constexpr int UNROLL = 4;
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec16; i += stride) {
+  long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (UNROLL - 1) * stride < nvec16; i += UNROLL * stride) {
+    float v[UNROLL][PER];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) VecIO<T, PER>::load(x, (i + u * stride) * PER, v[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+      for (int c = 0; c < PER; ++c) v[u][c] *= s;
+      VecIO<T, PER>::store(x, (i + u * stride) * PER, v[u]);
+    }
+  }
+  for (; i < nvec16; i += stride) {
     float v[PER];
     VecIO<T, PER>::load(x, i * PER, v);
 #pragma unroll
@@ -98,11 +112,11 @@ __global__ void __launch_bounds__(256) scale_unless_one_kernel(T* __restrict__ x
     VecIO<T, PER>::store(x, i * PER, v);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (long i = nvec16 * PER; i < numel; ++i) {
+    for (long k = nvec16 * PER; k < numel; ++k) {
       float v[1];
-      VecIO<T, 1>::load(x, i, v);
+      VecIO<T, 1>::load(x, k, v);
       v[0] *= s;
-      VecIO<T, 1>::store(x, i, v);
+      VecIO<T, 1>::store(x, k, v);
     }
   }
 }

@@ -206,12 +206,15 @@ DSNT_API int dsnt_scale_unless_one(void* x, int dtype, long numel, const float* 
   if (numel == 0) return DSNT_OK;
   const bool al = aligned(x, 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // One CTA of 1024 threads per SM: in the usual case (*g == 1) the kernel is pure launch overhead, which grows with the
+  // number of CTAs; when it does scale, 4 independent 128-bit loads per thread keep 64 KiB per SM in flight.
+  const unsigned ctas = static_cast<unsigned>(sm_count_of_current_device());
   if (dtype == DSNT_DTYPE_F32) {
     const long nv = al ? numel / 4 : 0;
-    scale_unless_one_kernel<float><<<148 * 8, 256, 0, s>>>(static_cast<float*>(x), nv, numel, g);
+    scale_unless_one_kernel<float><<<ctas, kScaleBlock, 0, s>>>(static_cast<float*>(x), nv, numel, g);
   } else if (dtype == DSNT_DTYPE_BF16) {
     const long nv = al ? numel / 8 : 0;
-    scale_unless_one_kernel<__nv_bfloat16><<<148 * 8, 256, 0, s>>>(static_cast<__nv_bfloat16*>(x), nv, numel, g);
+    scale_unless_one_kernel<__nv_bfloat16><<<ctas, kScaleBlock, 0, s>>>(static_cast<__nv_bfloat16*>(x), nv, numel, g);
   } else { set_error("unsupported dtype %d", dtype); return DSNT_ERR_UNSUPPORTED; }
   return check_launch("scale_unless_one_kernel");
 }

@@ -223,7 +223,10 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   // was measured slower, profiles/r01_v7_step2_sweeps.txt)
   const long hm_mul = static_cast<long>(gridDim.x), hm_add = static_cast<long>(blockIdx.x);
   const long ntiles = p.n > blockIdx.x ? (p.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  if (threadIdx.x == 0) pace_next = 0;
+  if (threadIdx.x == 0) {
+    pace_next = 0;
+    if (!p.denom && blockIdx.x == 0) reinterpret_cast<unsigned long long*>(p.ws + kFinishTrace)[5] = global_timer_ns();   // kernel entry
+  }
   if (lane == 0) {
     for (int t = warp; t < NB; t += NW) {
       const uint32_t bar = bars0_s + 8 * t;
@@ -250,6 +253,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   unsigned* const ctl = reinterpret_cast<unsigned*>(p.ws + kFinishCtl);   // [end ticket, start ticket, published flag, count]
   unsigned long long* const trace = reinterpret_cast<unsigned long long*>(p.ws + kFinishTrace);
   const long nmask = p.st.count > 1 ? p.st.n_per : p.n;       // the stacks share one mask
+  if (!p.denom && blockIdx.x == 0 && threadIdx.x == 0) trace[6] = global_timer_ns();     // barriers initialised, first loads issued
   if (!p.denom && p.mask) {
     const long chunk = (nmask + gridDim.x - 1) / gridDim.x;
     const long lo = blockIdx.x * chunk, hi = lo + chunk < nmask ? lo + chunk : nmask;

@@ -98,7 +98,8 @@ static int launch_step2_nw(HeadStepParams p, cudaStream_t stream) {
   // once.  The cooperative attribute makes the driver guarantee that (or refuse the launch) instead of the kernel assuming it.
   at[0].id = cudaLaunchAttributeCooperative;
   at[0].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = (!p.denom) ? 1 : 0;
+  static const int coop = env_int("DSNT_TUNE_STEP_COOP", 1);     // 0: measurements only (no co-residency guarantee)
+  cfg.attrs = at; cfg.numAttrs = (!p.denom && coop) ? 1 : 0;
   if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return check_launch("head_step2_kernel");
   return check_launch("head_step2_kernel");
 }

@@ -147,7 +147,8 @@ DSNT_API int dsnt_mask_count(const float* mask, long n, float* out, float* works
  * DSNT_ERR_UNSUPPORTED and the caller uses the three-launch form.  A sharded batch: dsnt_head_step_fused_peer below.
  * dsnt_finish_trace_offset_bytes: byte offset inside the workspace of eight uint64 %globaltimer stamps the last
  *   single-launch step left there (diagnostics; bench.py's per-rank timeline): [0] kernel start, [1] local mask count known,
- *   [2] count published (sharded: after the exchange with the other ranks), [3] last CTA done, [4] loss block written.
+ *   [2] count published (sharded: after the exchange with the other ranks), [3] last CTA done, [4] loss block written,
+ *   [5] entry of CTA 0 (before its barriers are initialised and its first loads issued).
  */
 DSNT_API int dsnt_head_step_fused_supported(int dtype, int H, int W, int reg, float sigma);
 DSNT_API int dsnt_finish_trace_offset_bytes(void);

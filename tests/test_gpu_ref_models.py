@@ -6,8 +6,8 @@ without it these tests skip.  `dsnt.model` imports `dsnt.data`, which needs anib
 (requirements.txt:18; absent from the image): a five-name stub is registered for it, as SURVEY.md 8c describes.
 Mirrors /root/reference/tests/test_model.py:11-63 (shapes with truncate / dilate, one SGD step moves every parameter).
 
-Tolerances: coordinates 1e-5 max-abs, loss 1e-5 relative, dL/dZ at the head input and every parameter gradient 2e-5
-L2-relative -- against the reference's own fp32 eager result, which is itself 1e-7 ... 4e-5 from fp64."""
+Tolerances: coordinates 1e-5 max-abs, loss 1e-5 relative, dL/dZ at the head input 1e-5 L2-relative, against the reference's
+head evaluated in fp64 on the same logits; parameter gradients: no worse than the reference's own fp32 head (see _compare)."""
 
 import copy
 import os
@@ -70,37 +70,90 @@ def dp():
     return dsnt_pose2d_b200
 
 
-def _rel(a, b):
-    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+def _rel(a, b, floor=0.0):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(max(floor, 1e-30))).item()
 
 
-def _train_step(model, x, target, mask):
-    """model(x) -> forward_loss -> backward, as src/dsnt/bin/train.py:355-381; returns what the comparison needs."""
+def _train_step(model, x, target, mask, head_dtype=None):
+    """model(x) -> forward_loss -> backward, as src/dsnt/bin/train.py:355-381; returns what the comparison needs.
+    head_dtype=torch.float64 evaluates the HEAD (forward_part2 + forward_loss) in fp64 on the fp32 logits of the fp32
+    backbone: the arbiter for the head alone, with the backbone's own rounding out of the picture."""
     model.zero_grad(set_to_none=True)
     z = model.forward_part1(x)
     zs = z if isinstance(z, (list, tuple)) else [z]
     for t in zs:
         t.retain_grad()
-    out = model.forward_part2(z)
+    if head_dtype is not None:
+        zin = [t.to(head_dtype) for t in zs]
+        zin = zin if isinstance(z, (list, tuple)) else zin[0]
+        target, mask = target.to(head_dtype), mask.to(head_dtype)
+    else:
+        zin = z
+    out = model.forward_part2(zin)
     loss = model.forward_loss(out, target, mask)
     loss.backward()
     torch.cuda.synchronize()
     coords = model.compute_coords(out)
-    return {'loss': loss.item(), 'coords': coords, 'dz': [t.grad.clone() for t in zs],
-            'grads': {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None},
-            'heatmaps': model.heatmaps.detach().clone()}
+    return {'loss': loss.item(), 'coords': coords.cpu(), 'dz': [t.grad.detach().cpu() for t in zs],
+            'grads': {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None},
+            'heatmaps': model.heatmaps.detach().cpu()}
 
 
-def _compare(a, b, what, tol_grad=2e-5):
+def _errors(a, b):
     e_loss = abs(a['loss'] - b['loss']) / abs(b['loss'])
-    e_coords = (a['coords'] - b['coords']).abs().max().item()
+    e_coords = (a['coords'].double() - b['coords'].double()).abs().max().item()
     e_dz = max(_rel(x, y) for x, y in zip(a['dz'], b['dz']))
     assert set(a['grads']) == set(b['grads']) and len(b['grads']) > 0
-    worst = max(((_rel(a['grads'][n], b['grads'][n]), n) for n in b['grads']))
-    e_hm = (a['heatmaps'] - b['heatmaps']).abs().max().item()
-    print('%s: loss %.2e coords %.2e dZ %.2e worst parameter gradient %.2e (%s) of %d; heatmaps %.2e'
-          % (what, e_loss, e_coords, e_dz, worst[0], worst[1], len(b['grads']), e_hm))
-    assert e_loss < 1e-5 and e_coords < 1e-5 and e_dz < tol_grad and worst[0] < tol_grad and e_hm < 1e-6
+    # a conv bias in front of a batch norm has an analytically ZERO gradient: its relative error means nothing
+    # (its computed value is pure rounding noise of the backbone): per-parameter norms are floored at 1 % of the largest
+    # parameter-gradient norm, and the error over ALL parameters taken as one vector is reported as well
+    floor = 1e-2 * max(g.double().norm().item() for g in b['grads'].values())
+    worst = max(((_rel(a['grads'][n], b['grads'][n], floor), n) for n in b['grads']))
+    num = sum((a['grads'][n].double() - b['grads'][n].double()).pow(2).sum().item() for n in b['grads']) ** 0.5
+    den = sum(b['grads'][n].double().pow(2).sum().item() for n in b['grads']) ** 0.5
+    worst = (max(worst[0], num / den), worst[1] + '; all parameters as one vector %.2e' % (num / den))
+    e_hm = (a['heatmaps'].double() - b['heatmaps'].double()).abs().max().item()
+    return e_loss, e_coords, e_dz, worst, e_hm
+
+
+def _compare(ours, ref32, ref64, what):
+    """ours (fused head) against the same model object with the reference's own head, both on the same fp32 backbone, and
+    both against that model with the reference's head evaluated in fp64 (the arbiter for the head).  The head's outputs --
+    loss, coords, dL/dZ at the head input -- carry north_star's 1e-5 bar against the arbiter.  A parameter gradient is
+    dL/dZ pushed through dozens of cuDNN layers, which amplifies any rounding of the head by the backbone's conditioning:
+    the bar there is the reference head's OWN fp32 rounding pushed through the same backbone (printed beside ours) --
+    ours-vs-arbiter <= 1.5 x reference-vs-arbiter (or 2e-5 where that is smaller): the fused head adds no noise."""
+    o32 = _errors(ours, ref32)
+    o64 = _errors(ours, ref64)
+    r64 = _errors(ref32, ref64)
+    print('%s\n  ours vs reference head fp32          : loss %.2e coords %.2e dZ %.2e worst parameter gradient %.2e (%s); heatmaps %.2e'
+          % ((what,) + o32[:3] + (o32[3][0], o32[3][1], o32[4])))
+    print('  ours vs reference head in fp64       : loss %.2e coords %.2e dZ %.2e worst parameter gradient %.2e (%s)'
+          % (o64[:3] + (o64[3][0], o64[3][1])))
+    print('  reference head fp32 vs the same fp64 : loss %.2e coords %.2e dZ %.2e worst parameter gradient %.2e (%s) of %d parameters'
+          % (r64[:3] + (r64[3][0], r64[3][1], len(ref64['grads']))))
+    assert o64[0] < 1e-5 and o64[1] < 1e-5 and o64[2] < 1e-5 and o64[4] < 1e-6          # the head itself, against the arbiter
+    assert o32[0] < 1e-5 and o32[1] < 1e-5 and o32[2] < 1e-5
+    bar = max(2e-5, 1.5 * r64[3][0])
+    assert o64[3][0] < bar, (o64[3], r64[3])
+
+
+def _three_way(ref, dp, x, target, mask):
+    """the reference's head in fp64 on the fp32 backbone (arbiter), the reference in fp32, ours: one backbone, three heads."""
+    import gc
+    ours = dp.attach_fused_head(copy.deepcopy(ref))
+    r64 = _train_step(ref, x, target, mask, head_dtype=torch.float64)
+    r32 = _train_step(ref, x, target, mask)
+    ref.zero_grad(set_to_none=True)
+    for name in ('heatmaps_array', 'heatmaps'):          # drop the reference's materialised heatmaps (hourglass: a property)
+        try:
+            setattr(ref, name, None)
+        except AttributeError:
+            pass
+    gc.collect()
+    torch.cuda.empty_cache()
+    o32 = _train_step(ours, x, target, mask)
+    return ours, o32, r32, r64
 
 
 def _head_cost(dp, model, x, target, mask, steps=5):
@@ -130,15 +183,13 @@ def test_resnet34_cfg2_matches_reference_head(ref_model, dp):
     torch.manual_seed(0)
     ref = ref_model.ResNetHumanPoseModel(torchvision.models.resnet34(), n_chans=16, dilate=2, output_strat='dsnt',
                                          reg='js', reg_coeff=1.0, hm_sigma=1.0).to(DEV)
-    ours = dp.attach_fused_head(copy.deepcopy(ref))
-    assert type(ours).__name__ == 'ResNetHumanPoseModelB200' and isinstance(ours, ref_model.ResNetHumanPoseModel)
     x = torch.rand(64, 3, 224, 224, device=DEV)
     target = torch.rand(64, 16, 2, device=DEV) * 1.6 - 0.8
     mask = (torch.rand(64, 16, device=DEV) > 0.1).float()
-    a = _train_step(ref, x, target, mask)
-    b = _train_step(ours, x, target, mask)
-    assert b['heatmaps'].shape == (64, 16, 28, 28)
-    _compare(b, a, 'resnet34 dilate=2 batch 64 (cfg 2)')
+    ours, o32, r32, r64 = _three_way(ref, dp, x, target, mask)
+    assert type(ours).__name__ == 'ResNetHumanPoseModelB200' and isinstance(ours, ref_model.ResNetHumanPoseModel)
+    assert o32['heatmaps'].shape == (64, 16, 28, 28)
+    _compare(o32, r32, r64, 'resnet34 dilate=2 batch 64 (cfg 2)')
     head_us, launches, step_ms, used = _head_cost(dp, ours, x, target, mask)
     print('cfg 2 full training step %.1f ms; head: %.0f us in %d launches per step %r' % (step_ms, head_us, launches, used))
 
@@ -147,14 +198,12 @@ def test_hourglass8_cfg3_matches_reference_head(ref_model, dp):
     """BASELINE config 3: 8-stack hourglass, 64x64 heatmaps per stack, JS sigma = 1, batch 32 at 256x256."""
     torch.manual_seed(0)
     ref = ref_model.build_mpii_pose_model('hg8', output_strat='dsnt', reg='js', reg_coeff=1.0, hm_sigma=1.0).to(DEV)
-    ours = dp.attach_fused_head(copy.deepcopy(ref))
     x = torch.rand(32, 3, 256, 256, device=DEV)
     target = torch.rand(32, 16, 2, device=DEV) * 1.6 - 0.8
     mask = (torch.rand(32, 16, device=DEV) > 0.1).float()
-    a = _train_step(ref, x, target, mask)
-    assert len(a['dz']) == 8 and a['heatmaps'].shape == (32, 16, 64, 64)
-    b = _train_step(ours, x, target, mask)
-    _compare(b, a, 'hourglass hg8 batch 32 (cfg 3)', tol_grad=5e-5)      # 8 stacks of backbone between the heads
+    ours, o32, r32, r64 = _three_way(ref, dp, x, target, mask)
+    assert len(r32['dz']) == 8 and r32['heatmaps'].shape == (32, 16, 64, 64)
+    _compare(o32, r32, r64, 'hourglass hg8 batch 32 (cfg 3)')
     head_us, launches, step_ms, used = _head_cost(dp, ours, x, target, mask, steps=3)
     print('cfg 3 full training step %.1f ms; head: %.0f us in %d launches per step %r' % (step_ms, head_us, launches, used))
     assert launches <= 4          # every stack's head in one fused launch (+ the coordinate kernel of forward_part2)

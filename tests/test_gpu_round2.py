@@ -206,7 +206,7 @@ def test_second_device_in_one_process(dp):
     z, target, mask = _inputs(b=16)
     res = []
     for dev in ('cuda:0', 'cuda:1', 'cuda:0'):
-        zz = z.to(dev).requires_grad_(True)
+        zz = z.detach().to(dev).clone().requires_grad_(True)
         out = dp.dsnt_head(zz, target.to(dev), mask.to(dev), reg='js', hm_sigma=1.0, one_pass=True)
         out.loss.backward()
         res.append((out.loss.item(), zz.grad.cpu()))

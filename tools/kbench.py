@@ -119,9 +119,30 @@ def main():
                                       coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), dzs[i % len(dzs)].data_ptr(),
                                       stream)
                         ts, _ = time_calls(step, args.iters)
+                    fused_note = ''
+                    if _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(zs[0]), h, w, rid, sigma):
+                        def fused(i):
+                            _lib.call('dsnt_head_step_fused', zs[i % nbuf].data_ptr(), _lib.dtype_id(zs[0]), n, h, w,
+                                      target.data_ptr(), mask.data_ptr(), None, 1.0, rid, sigma, 0, coords.data_ptr(),
+                                      stats.data_ptr(), dzs[i % len(dzs)].data_ptr(), out8.data_ptr(), ws.data_ptr(), stream)
+                        tfu, _ = time_calls(fused, args.iters)
+                        # back to back: one pair of events around all launches (no event between two kernels)
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for i in range(args.iters):
+                            fused(i)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        tb2b = e0.elapsed_time(e1) / args.iters
+                        off = _lib.LIB.dsnt_finish_trace_offset_bytes() // 4
+                        st = ws[off:off + 16].view(torch.int64).cpu()
+                        fused_note = ' || single launch %7.1f us (%5.3f), back to back %7.1f us (%5.3f), inside the kernel %7.1f us' % (
+                            tfu * 1e3, (2 * nbytes + 60 * n) / tfu / 1e6 / peak, tb2b * 1e3,
+                            (2 * nbytes + 60 * n) / tb2b / 1e6 / peak, (st[4] - st[0]).item() / 1e3)
                     if tf is None:
                         print('%-6s %-5s %-5s || one-pass step %7.1f us %6.0f GB/s %5.3f %8.2f Mhm/s' % (
-                            cfg, dt, reg, ts * 1e3, 2 * nbytes / ts / 1e6, 2 * nbytes / ts / 1e6 / peak, n / ts / 1e3))
+                            cfg, dt, reg, ts * 1e3, 2 * nbytes / ts / 1e6, 2 * nbytes / ts / 1e6 / peak, n / ts / 1e3) + fused_note)
                         continue
                     gf = nbytes / tf / 1e6
                     gb = 2 * nbytes / tb / 1e6
@@ -130,7 +151,7 @@ def main():
                         cfg, dt, reg, variant, tf * 1e3, gf, gf / peak, tb * 1e3, gb, gb / peak,
                         n / (tf + tb) / 1e3, tot / peak) + (
                         '' if ts is None else ' || one-pass step %7.1f us %6.0f GB/s %5.3f %8.2f Mhm/s' % (
-                            ts * 1e3, 2 * nbytes / ts / 1e6, 2 * nbytes / ts / 1e6 / peak, n / ts / 1e3)))
+                            ts * 1e3, 2 * nbytes / ts / 1e6, 2 * nbytes / ts / 1e6 / peak, n / ts / 1e3)) + fused_note)
             del zs, dzs
             torch.cuda.empty_cache()
 
