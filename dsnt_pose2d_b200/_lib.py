@@ -105,19 +105,26 @@ def last_error():
     return LIB.dsnt_b200_last_error().decode('utf-8', 'replace')
 
 
+_FN = {name: getattr(LIB, name) for name in SIGNATURES}        # bound once: no attribute lookup per launch
+
+
 def call(name, *args, launches=1):
     """Invoke an entry point; a non-zero return raises RuntimeError with the library's message."""
     global launch_count
-    log = event_log.get(name) if event_log is not None else None
-    if log is not None:            # time this launch on the stream it is enqueued on (torch's current stream)
-        start = torch.cuda.Event(enable_timing=True)
-        stop = torch.cuda.Event(enable_timing=True)
-        start.record()
-        rc = getattr(LIB, name)(*args)
-        stop.record()
-        log.append((start, stop))
-    else:
-        rc = getattr(LIB, name)(*args)
+    if event_log is not None:
+        log = event_log.get(name)
+        if log is not None:            # time this launch on the stream it is enqueued on (torch's current stream)
+            start = torch.cuda.Event(enable_timing=True)
+            stop = torch.cuda.Event(enable_timing=True)
+            start.record()
+            rc = _FN[name](*args)
+            stop.record()
+            log.append((start, stop))
+            if rc != 0:
+                raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))
+            launch_count += launches
+            return
+    rc = _FN[name](*args)
     if rc != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))
     launch_count += launches
@@ -135,7 +142,14 @@ def ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream_of(t):
+    """The raw cudaStream_t of torch's current stream on the tensor's device."""
+    if _raw_stream is not None:
+        idx = t.device.index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
@@ -159,12 +173,32 @@ def require_cuda(t, what):
 _workspaces = {}
 
 
-def finish_workspace(device):
+def finish_workspace(device, stream=None):
     """Per-(device, stream) zero-initialised scratch for dsnt_finish_loss (the kernel re-zeroes its ticket)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+    if stream is None:
+        stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
     ws = _workspaces.get(key)
     if ws is None:
         ws = torch.zeros(LIB.dsnt_finish_workspace_bytes() // 4, dtype=torch.float32, device=device)
         _workspaces[key] = ws
     return ws
+
+
+class on_device:
+    """`with on_device(dev):` = torch.cuda.device(dev) that costs nothing when dev is already current (the usual case)."""
+
+    __slots__ = ('guard',)
+
+    def __init__(self, dev):
+        idx = dev.index
+        self.guard = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False

@@ -173,13 +173,17 @@ __device__ __forceinline__ unsigned long long pace_reserve(unsigned long long* s
   return mine;
 }
 
-// window slots per lane: the compact mapping covers 32 * slots vectors (host-checked bound, step2_window_fits)
+// window slots per lane: the compact mapping covers 32 * MAXS vectors (host-checked bound, step2_window_fits).  Two builds
+// per dtype: the small one serves sigma = 1 px (the reference's default: 16 x 16 pixels = 48 bf16 / 80 fp32 vectors), the
+// large one up to ~1.4 px; its window arrays are what sets the register count of the kernel.
 template <typename T>
-__host__ __device__ constexpr int step2_slots() { return sizeof(T) == 2 ? 3 : 4; }
+__host__ __device__ constexpr int step2_slots_small() { return sizeof(T) == 2 ? 2 : 3; }
+template <typename T>
+__host__ __device__ constexpr int step2_slots_large() { return sizeof(T) == 2 ? 3 : 4; }
 
 // PACED = false compiles the pacing out (loads are re-issued the moment a buffer is free): for the instantiations that
 // are bound by arithmetic anyway (bf16 with a Gaussian window), where the bookkeeping costs more than it brings.
-template <typename T, int REG, int H, int W, int NWMAX, bool PACED>
+template <typename T, int REG, int H, int W, int NWMAX, bool PACED, int MAXS>
 __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadStepParams p) {
   constexpr bool kJS = REG == DSNT_REG_JS;
   constexpr bool kVar = REG == DSNT_REG_VAR;
@@ -193,7 +197,6 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   constexpr int RPI = 32 / WV;             // rows per sweep step
   static_assert(H % RPI == 0, "whole sweep steps");
   constexpr int ITERS = H / RPI;
-  constexpr int MAXS = step2_slots<T>();
   constexpr uint32_t hm_bytes = static_cast<uint32_t>(H) * W * sizeof(T);
   constexpr float tow = 2.0f / W, bw = 1.0f / W - 1.0f, toh = 2.0f / H, bh = 1.0f / H - 1.0f;
   constexpr float dyi = RPI * toh;

@@ -30,7 +30,11 @@
 
 namespace dsnt {
 
-constexpr float kThetaJS = 1e-14f;   // G below this is dropped from P-weighted terms (abs. error <= W*H*theta*140); also MSE
+// JS / MSE: pixels whose Gaussian weight is below theta * max along EITHER axis take the closed forms (ln P - ln M = ln 2,
+// (P - G)^2 = P^2).  theta = 1e-10 is a window of +-6.8 sigma (16 pixels wide at sigma = 1 px, one pixel of padding included); measured
+// in fp64 over random / peaked / trained-like heatmaps the truncation changes D by < 1e-11 and dL/dz by < 3e-10 relative
+// (1e-14, the first choice, gave a 19-pixel window: a third more window work for nothing).
+constexpr float kThetaJS = 1e-10f;
 constexpr float kThetaKL = 3e-32f;   // G + 1e-24 == 1e-24 exactly in fp32 below this
 constexpr float kLog2Eps = -79.726274277296700f;   // log2(1e-24)
 constexpr float kLnEps = -55.262042231857095f;     // ln(1e-24)

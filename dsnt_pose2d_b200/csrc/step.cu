@@ -35,17 +35,20 @@ static int step_v2() { static const int v = env_int("DSNT_TUNE_STEP_V2", 1); ret
 static int step_spare() { static const int v = env_int("DSNT_TUNE_STEP_SPARE", -1); return v; }
 
 // ---------------------------------------------------------------------------------- shape-specialised kernel (head_step2.cuh)
-// The compact window mapping holds 32 * step2_slots() vectors in registers: the window of ANY target (upper bound as in
+// The compact window mapping holds 32 * MAXS vectors in registers: the window of ANY target (upper bound as in
 // launch.cuh:stash_fits -- floor(n sqrt(r2 + 1/n^2)) + 4 pixels per axis, widened to whole vectors along x) must fit.
+// Returns the number of slots the launch needs: 0 = no window, -1 = does not fit the largest build.
 template <typename T>
-static bool step2_window_fits(int H, int W, int vec, int reg, float r2_win) {
-  if (!reg_needs_gauss(reg)) return true;
+static int step2_window_slots(int H, int W, int vec, int reg, float r2_win) {
+  if (!reg_needs_gauss(reg)) return 0;
   const double r2 = r2_win;
   const int mc = static_cast<int>(std::floor(W * std::sqrt(r2 + 1.0 / (static_cast<double>(W) * W)))) + 4;
   const int mr = static_cast<int>(std::floor(H * std::sqrt(r2 + 1.0 / (static_cast<double>(H) * H)))) + 4;
   const int vecs = std::min(W / vec, (mc + vec - 2) / vec + 1);
   const int rows = std::min(H, mr);
-  return rows * vecs <= 32 * step2_slots<T>();
+  if (rows * vecs <= 32 * step2_slots_small<T>()) return step2_slots_small<T>();
+  if (rows * vecs <= 32 * step2_slots_large<T>()) return step2_slots_large<T>();
+  return -1;
 }
 
 // Load pacing (head_step2.cuh:pace_wait): SM clocks between two bulk loads of a CTA = the time one heatmap (read + write)
@@ -67,9 +70,9 @@ static int step2_pace_cycles(long hm_bytes, int ctas) {
   return static_cast<int>(ns * ghz + 0.5);
 }
 
-template <typename T, int REG, int H, int W, int NWMAX, bool PACED>
+template <typename T, int REG, int H, int W, int NWMAX, bool PACED, int MAXS>
 static int launch_step2_nw(HeadStepParams p, cudaStream_t stream) {
-  auto kern = head_step2_kernel<T, REG, H, W, NWMAX, PACED>;
+  auto kern = head_step2_kernel<T, REG, H, W, NWMAX, PACED, MAXS>;
   p.nbufs = kStepSmemBudget / p.buf_bytes;
   if (p.nbufs > kStepMaxBufs) p.nbufs = kStepMaxBufs;
   static const int nbuf_cap = env_int("DSNT_TUNE_STEP_NBUF2", 0);
@@ -106,20 +109,31 @@ static int launch_step2_nw(HeadStepParams p, cudaStream_t stream) {
 
 // NWMAX only sets the register budget (__launch_bounds__): 65536 / (32 NWMAX) registers per thread.  bf16 heatmaps with a
 // Gaussian window are bound by arithmetic, not by HBM: they run unpaced (DSNT_TUNE_STEP_PACED=1 forces the paced build).
-template <typename T, int REG, int H, int W>
-static int launch_step2(const HeadStepParams& p, cudaStream_t stream) {
-  static const int nwmax = env_int("DSNT_TUNE_STEP_NWMAX", 0);
+// MAXS: window slots per lane (head_step2.cuh); regularisers without a window have one build.
+template <typename T, int REG, int H, int W, int MAXS>
+static int launch_step2_slots(const HeadStepParams& p, cudaStream_t stream) {
   static const int paced = env_int("DSNT_TUNE_STEP_PACED", -1);
+  static const int nwmax = env_int("DSNT_TUNE_STEP_NWMAX", 0);
   if constexpr (sizeof(T) == 2) {
-    if (nwmax == 24) return launch_step2_nw<T, REG, H, W, 24, true>(p, stream);
-    if (nwmax == 20) return launch_step2_nw<T, REG, H, W, 20, true>(p, stream);
     if constexpr (REG == DSNT_REG_JS || REG == DSNT_REG_MSE) {
-      if (paced != 1) return launch_step2_nw<T, REG, H, W, 16, false>(p, stream);
+      if constexpr (MAXS == step2_slots_small<T>()) {
+        if (nwmax != 16) return launch_step2_nw<T, REG, H, W, 20, false, MAXS>(p, stream);    // fewer window registers: 20 warps
+      }
+      if (paced != 1) return launch_step2_nw<T, REG, H, W, 16, false, MAXS>(p, stream);
     }
-    return launch_step2_nw<T, REG, H, W, 16, true>(p, stream);
+    return launch_step2_nw<T, REG, H, W, 16, true, MAXS>(p, stream);
   } else {
-    if (nwmax == 16) return launch_step2_nw<T, REG, H, W, 16, true>(p, stream);
-    return launch_step2_nw<T, REG, H, W, 12, true>(p, stream);
+    return launch_step2_nw<T, REG, H, W, 12, true, MAXS>(p, stream);
+  }
+}
+
+template <typename T, int REG, int H, int W>
+static int launch_step2(const HeadStepParams& p, int slots, cudaStream_t stream) {
+  if constexpr (REG == DSNT_REG_JS || REG == DSNT_REG_MSE) {
+    if (slots == step2_slots_small<T>()) return launch_step2_slots<T, REG, H, W, step2_slots_small<T>()>(p, stream);
+    return launch_step2_slots<T, REG, H, W, step2_slots_large<T>()>(p, stream);
+  } else {
+    return launch_step2_slots<T, REG, H, W, 1>(p, stream);
   }
 }
 
@@ -148,22 +162,23 @@ static int launch_step_one(HeadStepParams p, cudaStream_t stream) {
   return check_launch("head_step_kernel");
 }
 
-// does this launch take the shape-specialised kernel (head_step2.cuh)?
-static bool step2_eligible(int dtype, int H, int W, int reg, float sigma) {
-  if (reg == DSNT_REG_KL || H != 64 || W != 64 || !step_v2() || !step_direct_store() || step_group() == 64) return false;
+// does this launch take the shape-specialised kernel (head_step2.cuh)?  Returns the window slots it needs, -1 = no.
+static int step2_eligible(int dtype, int H, int W, int reg, float sigma) {
+  if (reg == DSNT_REG_KL || H != 64 || W != 64 || !step_v2() || !step_direct_store() || step_group() == 64) return -1;
   const int vec = dtype == DSNT_DTYPE_F32 ? 4 : 8;
   const Geom g = make_geom(H, W, vec, 32, sigma > 0.f ? sigma : 1.f, reg);
-  return dtype == DSNT_DTYPE_F32 ? step2_window_fits<float>(H, W, vec, reg, g.r2_win)
-                                 : step2_window_fits<__nv_bfloat16>(H, W, vec, reg, g.r2_win);
+  return dtype == DSNT_DTYPE_F32 ? step2_window_slots<float>(H, W, vec, reg, g.r2_win)
+                                 : step2_window_slots<__nv_bfloat16>(H, W, vec, reg, g.r2_win);
 }
 
 // one warp per heatmap by default (DSNT_TUNE_STEP_GROUP=64 selects two)
 template <typename T, int VEC, int REG>
 static int launch_step_fixc(HeadStepParams p, cudaStream_t stream) {
   if constexpr (REG != DSNT_REG_KL) {
-    if (step2_eligible(sizeof(T) == 4 ? DSNT_DTYPE_F32 : DSNT_DTYPE_BF16, p.H, p.W, REG, p.sigma)) {
+    const int slots = step2_eligible(sizeof(T) == 4 ? DSNT_DTYPE_F32 : DSNT_DTYPE_BF16, p.H, p.W, REG, p.sigma);
+    if (slots >= 0) {
       p.g = make_geom(p.H, p.W, VEC, 32, p.sigma > 0.f ? p.sigma : 1.f, REG);
-      return launch_step2<T, REG, 64, 64>(p, stream);
+      return launch_step2<T, REG, 64, 64>(p, slots, stream);
     }
   }
   if (p.out8 || !p.denom) { set_error("single-launch step: this shape / regulariser takes the generic kernel"); return DSNT_ERR_UNSUPPORTED; }
@@ -286,7 +301,7 @@ DSNT_API int dsnt_head_step_supported_reg(int dtype, int H, int W, int reg) {
 }
 
 DSNT_API int dsnt_head_step_fused_supported(int dtype, int H, int W, int reg, float sigma) {
-  return dsnt_head_step_supported(dtype, H, W) && step2_eligible(dtype, H, W, reg, sigma) ? 1 : 0;
+  return dsnt_head_step_supported(dtype, H, W) && step2_eligible(dtype, H, W, reg, sigma) >= 0 ? 1 : 0;
 }
 
 DSNT_API int dsnt_head_step_fused(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,

@@ -66,6 +66,21 @@ __device__ __forceinline__ void pair_block_sum4(float& a, float& b, float& c, fl
   __syncthreads();      // red may be reused
 }
 
+// ... and of six (the variance path: S, the first and the second moments about the pivot)
+__device__ __forceinline__ void pair_block_sum6(float& a, float& b, float& c, float& d, float& e, float& f, float (*red)[8],
+                                                int warp, int lane) {
+  const float k = warp_sum4_transposed(a, b, c, d, lane);
+  const float k2 = warp_sum2_transposed(e, f, lane);
+  if ((lane & 7) == 0) red[warp][lane >> 3] = k;
+  if ((lane & 15) == 0) red[warp][4 + (lane >> 4)] = k2;
+  __syncthreads();
+  const float q = warp_sum4_transposed(red[lane][0], red[lane][1], red[lane][2], red[lane][3], lane);
+  const float q2 = warp_sum2_transposed(red[lane][4], red[lane][5], lane);
+  a = __shfl_sync(kFull, q, 0); b = __shfl_sync(kFull, q, 8); c = __shfl_sync(kFull, q, 16); d = __shfl_sync(kFull, q, 24);
+  e = __shfl_sync(kFull, q2, 0); f = __shfl_sync(kFull, q2, 16);
+  __syncthreads();      // red may be reused
+}
+
 template <int REG>
 __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const PairParams p) {
   constexpr bool kVar = REG == DSNT_REG_VAR;
@@ -73,7 +88,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
   extern __shared__ __align__(128) unsigned char pair_smem[];
   __shared__ __align__(8) unsigned long long bars[kPairSlots];
   __shared__ float red[32][8];
-  __shared__ __align__(16) float xin[2][4];               // the PEER's partial results, stored here by the peer (st.async over DSMEM)
+  __shared__ __align__(16) float xin[2][2][4];            // the PEER's partial results, stored here by the peer (st.async over DSMEM);
+                                                          // message number n lands in xin[n & 1]: the peer can be one message ahead
   __shared__ __align__(8) unsigned long long xbar[1];     // ... the two stores completing 32 bytes on this mbarrier
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -85,16 +101,18 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
   // with st.async, which completes the bytes on the PEER's xbar; everybody then waits on the local barrier and reads the
   // local xin.  No cluster-wide barrier (whose release fence makes all 1024 threads wait for their global stores: the
   // first version of this kernel, 1053 us at config 5, against 878 us with three such exchanges and less with one).
-  const uint32_t xin_s = smem_u32(&xin[0][0]), xbar_s = smem_u32(&xbar[0]);
+  const uint32_t xin_s = smem_u32(&xin[0][0][0]), xbar_s = smem_u32(&xbar[0]);
   uint32_t peer_xin_s, peer_xbar_s;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xin_s) : "r"(xin_s), "r"(peer));
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xbar_s) : "r"(xbar_s), "r"(peer));
-  auto send = [&](float a, float b, float c, float d, float e, float f) {      // thread 0
+  uint32_t xn = 0;          // messages exchanged so far: the same on both CTAs (they take the same branches on bit-identical totals)
+  auto send = [&](float a, float b, float c, float d, float e, float f) {      // thread 0; message number xn
+    const uint32_t dst = peer_xin_s + (xn & 1u) * 32u;
     mbar_expect_tx(xbar_s, 32);
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(peer_xin_s),
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
                  "f"(a), "f"(b), "f"(c), "f"(d), "r"(peer_xbar_s)
                  : "memory");
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(peer_xin_s + 16),
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst + 16),
                  "f"(e), "f"(f), "f"(0.f), "f"(0.f), "r"(peer_xbar_s)
                  : "memory");
   };
@@ -173,8 +191,13 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     const f2 nm2 = pk1(-m2h);
 
     // ---------------------------------------------------------------- sums; e replaces z in the registers
+    // First and second moments are taken about a PIVOT known before the sweep: the target (a trained model predicts near
+    // it; a diffuse heatmap has a variance far larger than any offset).  var = M2_c / S - (mu - c)^2 then loses
+    // (mu - c)^2 / var digits: checked below, and the rare ill-conditioned heatmap takes the exact second walk about the mean.
+    const float pcx = kVar ? tx : 0.f, pcy = kVar ? ty : 0.f;
     f2 colE[2] = {pk1(0.f), pk1(0.f)};
-    float Sy = 0.f;
+    float Syc = 0.f, Syy = 0.f;
+    const float dyb = y0 - pcy;
 #pragma unroll
     for (int it = 0; it < kPairIters; ++it) {
       ev[it][0] = ex2_2(fma2(ev[it][0], l2e2, nm2));
@@ -182,59 +205,33 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       colE[0] = add2(colE[0], ev[it][0]);
       colE[1] = add2(colE[1], ev[it][1]);
       const float rs = hsum(add2(ev[it][0], ev[it][1]));
-      Sy = fmaf(rs, y0 + static_cast<float>(it) * dyi, Sy);
+      const float dy = dyb + static_cast<float>(it) * dyi;
+      Syc = fmaf(rs, dy, Syc);
+      if constexpr (kVar) Syy = fmaf(rs * dy, dy, Syy);
     }
     float c0, c1, c2, c3;
     upk(colE[0], c0, c1);
     upk(colE[1], c2, c3);
     float Sh = (c0 + c1) + (c2 + c3);
-    float Sxh = fmaf(c0, xs[0], fmaf(c1, xs[1], fmaf(c2, xs[2], c3 * xs[3])));
-    float Syh = Sy;
+    const float dx0 = xs[0] - pcx, dx1 = xs[1] - pcx, dx2 = xs[2] - pcx, dx3 = xs[3] - pcx;
+    float Sxh = fmaf(c0, dx0, fmaf(c1, dx1, fmaf(c2, dx2, c3 * dx3)));
+    float Syh = Syc;
     float axh = 0.f, ayh = 0.f;
     if constexpr (!kVar) {
       float zero = 0.f;
       pair_block_sum4(Sh, Sxh, Syh, zero, red, warp, lane);
     } else {
-      // Variance: second moments about the WARP's own mean first, then ONE block-wide reduction that merges the 32 warps
-      // by the parallel-variance formula (Chan et al.): M2 = sum_w [M2_w + S_w (mu_w - mu)^2] -- no E[x^2] - mu^2 anywhere,
-      // and no second pair of block barriers for the moments.
-      const float kw = warp_sum4_transposed(Sh, Sxh, Syh, 0.f, lane);
-      const float Sw = __shfl_sync(kFull, kw, 0), Sxw = __shfl_sync(kFull, kw, 8), Syw = __shfl_sync(kFull, kw, 16);
-      const float iw = Sw > 0.f ? rcp(Sw) : 0.f;
-      const float mxw = Sxw * iw, myw = Syw * iw;
-      float axt, ayt = 0.f;
-      {
-        const float d0 = xs[0] - mxw, d1 = xs[1] - mxw, d2 = xs[2] - mxw, d3 = xs[3] - mxw;
-        axt = fmaf(c0 * d0, d0, fmaf(c1 * d1, d1, fmaf(c2 * d2, d2, c3 * d3 * d3)));
-      }
-#pragma unroll
-      for (int it = 0; it < kPairIters; ++it) {
-        const float d = (y0 + static_cast<float>(it) * dyi) - myw;
-        ayt = fmaf(hsum(add2(ev[it][0], ev[it][1])) * d, d, ayt);      // the row sum again, from registers
-      }
-      const float km = warp_sum2_transposed(axt, ayt, lane);
-      const float axw = __shfl_sync(kFull, km, 0), ayw = __shfl_sync(kFull, km, 16);
-      if (lane == 0) {
-        red[warp][0] = Sw; red[warp][1] = Sxw; red[warp][2] = Syw; red[warp][3] = axw; red[warp][4] = ayw;
-      }
-      __syncthreads();
-      // every warp merges the 32 per-warp results (lane l holds warp l's) with the same butterflies
-      const float Sl = red[lane][0], Sxl = red[lane][1], Syl = red[lane][2], axl = red[lane][3], ayl = red[lane][4];
-      const float kb = warp_sum4_transposed(Sl, Sxl, Syl, 0.f, lane);
-      Sh = __shfl_sync(kFull, kb, 0); Sxh = __shfl_sync(kFull, kb, 8); Syh = __shfl_sync(kFull, kb, 16);
-      const float ih = rcp(Sh);                       // > 0: the half's maximum contributes 1
-      const float il = Sl > 0.f ? rcp(Sl) : 0.f;
-      const float dxl = Sxl * il - Sxh * ih, dyl = Syl * il - Syh * ih;
-      const float kc = warp_sum2_transposed(fmaf(Sl * dxl, dxl, axl), fmaf(Sl * dyl, dyl, ayl), lane);
-      axh = __shfl_sync(kFull, kc, 0); ayh = __shfl_sync(kFull, kc, 16);
-      __syncthreads();                                // red may be reused
+      axh = fmaf(c0 * dx0, dx0, fmaf(c1 * dx1, dx1, fmaf(c2 * dx2, dx2, c3 * dx3 * dx3)));
+      ayh = Syy;
+      pair_block_sum6(Sh, Sxh, Syh, axh, ayh, Syy, red, warp, lane);      // (the sixth value rides along unused)
     }
-    const uint32_t xphase = static_cast<uint32_t>(k) & 1u;
     if (tid == 0) send(m2h, Sh, Sxh, Syh, axh, ayh);
-    mbar_wait(xbar_s, xphase);
+    mbar_wait(xbar_s, xn & 1u);
     // merge in rank order on both CTAs: bit-identical totals
     const bool first = rank == 0;
-    const float p_m = xin[0][0], p_S = xin[0][1], p_Sx = xin[0][2], p_Sy = xin[0][3], p_ax = xin[1][0], p_ay = xin[1][1];
+    const float (*xm)[4] = xin[xn & 1u];
+    ++xn;
+    const float p_m = xm[0][0], p_S = xm[0][1], p_Sx = xm[0][2], p_Sy = xm[0][3], p_ax = xm[1][0], p_ay = xm[1][1];
     const float h_m[2] = {first ? m2h : p_m, first ? p_m : m2h};
     const float h_S[2] = {first ? Sh : p_S, first ? p_S : Sh};
     const float h_Sx[2] = {first ? Sxh : p_Sx, first ? p_Sx : Sxh};
@@ -243,20 +240,43 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     const float h_ay[2] = {first ? ayh : p_ay, first ? p_ay : ayh};
     const float m2 = fmaxf(h_m[0], h_m[1]);
     const float sc0 = ex2(h_m[0] - m2), sc1 = ex2(h_m[1] - m2);
-    const float S0 = h_S[0] * sc0, S1 = h_S[1] * sc1;
-    const float S = S0 + S1;
-    const float Sx = fmaf(h_Sx[0], sc0, h_Sx[1] * sc1), Sys = fmaf(h_Sy[0], sc0, h_Sy[1] * sc1);
+    // each half was summed relative to ITS OWN maximum: rescaled like two blocks of an online softmax; everything is about
+    // the same pivot, so the halves simply add
+    const float S = fmaf(h_S[0], sc0, h_S[1] * sc1);
+    const float Sxc = fmaf(h_Sx[0], sc0, h_Sx[1] * sc1), Sycm = fmaf(h_Sy[0], sc0, h_Sy[1] * sc1);
     const float invS = rcp(S);
-    const float mux = Sx * invS, muy = Sys * invS;
+    const float mxc = Sxc * invS, myc = Sycm * invS;
+    const float mux = pcx + mxc, muy = pcy + myc;
     const float invSh = (first ? sc0 : sc1) * invS;       // this half's e (relative to its own maximum) -> probability
 
     float D = 0.f, creg = 0.f, vx = 0.f, vy = 0.f;
     if constexpr (kVar) {
-      const float i0 = rcp(h_S[0]), i1 = rcp(h_S[1]);
-      const float dmx = h_Sx[0] * i0 - h_Sx[1] * i1, dmy = h_Sy[0] * i0 - h_Sy[1] * i1;
-      const float cross = S0 * S1 * invS;
-      vx = (fmaf(h_ax[0], sc0, h_ax[1] * sc1) + dmx * dmx * cross) * invS;
-      vy = (fmaf(h_ay[0], sc0, h_ay[1] * sc1) + dmy * dmy * cross) * invS;
+      vx = fmaf(h_ax[0], sc0, h_ax[1] * sc1) * invS - mxc * mxc;
+      vy = fmaf(h_ay[0], sc0, h_ay[1] * sc1) * invS - myc * myc;
+      // conditioning of the pivot form: (mu - c)^2 <= 16 var keeps the cancellation below 17 fp32 roundings (1e-6 relative)
+      const bool ill = !(mxc * mxc <= 16.f * vx) || !(myc * myc <= 16.f * vy);
+      if (ill) {
+        // exact: second moments about the mean itself, from the registers (column sums are still there, the row sums are
+        // formed again), one more block reduction and one more exchange; both CTAs get here together (identical totals)
+        const float ex0 = xs[0] - mux, ex1 = xs[1] - mux, ex2v = xs[2] - mux, ex3 = xs[3] - mux;
+        float axe = fmaf(c0 * ex0, ex0, fmaf(c1 * ex1, ex1, fmaf(c2 * ex2v, ex2v, c3 * ex3 * ex3)));
+        float aye = 0.f;
+        const float eyb = y0 - muy;
+#pragma unroll
+        for (int it = 0; it < kPairIters; ++it) {
+          const float d = eyb + static_cast<float>(it) * dyi;
+          aye = fmaf(hsum(add2(ev[it][0], ev[it][1])) * d, d, aye);
+        }
+        float z0 = 0.f, z1 = 0.f;
+        pair_block_sum4(axe, aye, z0, z1, red, warp, lane);
+        if (tid == 0) send(axe, aye, 0.f, 0.f, 0.f, 0.f);
+        mbar_wait(xbar_s, xn & 1u);
+        const float (*xe)[4] = xin[xn & 1u];
+        ++xn;
+        const float q_ax = xe[0][0], q_ay = xe[0][1];
+        vx = fmaf(first ? axe : q_ax, sc0, (first ? q_ax : axe) * sc1) * invS;
+        vy = fmaf(first ? aye : q_ay, sc0, (first ? q_ay : aye) * sc1) * invS;
+      }
       const float ex = vx - s2, ey = vy - s2;
       D = ex * ex + ey * ey;
       creg = 2.f * (ex * vx + ey * vy);

@@ -26,7 +26,35 @@ import torch
 from . import _lib
 from .parallel import PeerExchange
 
-HeadOutput = collections.namedtuple('HeadOutput', ['coords', 'loss', 'euclid', 'reg'])
+class HeadOutput:
+    """(coords, loss, euclid, reg) of the fused head; behaves like the 4-tuple it used to be.  `euclid` and `reg` are views
+    into the loss block, made only when somebody asks (two tensor slices per call are host time the small configs feel)."""
+
+    __slots__ = ('coords', 'loss', '_out8')
+    _fields = ('coords', 'loss', 'euclid', 'reg')
+
+    def __init__(self, coords, loss, out8):
+        self.coords, self.loss, self._out8 = coords, loss, out8
+
+    @property
+    def euclid(self):
+        return self._out8[4]
+
+    @property
+    def reg(self):
+        return self._out8[5]
+
+    def __iter__(self):
+        return iter((self.coords, self.loss, self.euclid, self.reg))
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, i):
+        return (self.coords, self.loss, self.euclid, self.reg)[i]
+
+    def __repr__(self):
+        return 'HeadOutput(coords=%r, loss=%r, euclid=%r, reg=%r)' % tuple(self)
 
 # Reproduce the reference's NaN gradient at coords == target (sqrt'(0), SURVEY.md Appendix B.1) instead of
 # the default zero gradient.  Test-only switch; real training never wants the NaN.
@@ -54,6 +82,8 @@ def _as_f32(t, n, last, what):
 
 
 def _is_sharded(group):
+    if group is None:
+        return False
     import torch.distributed as dist
     return group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
@@ -98,6 +128,19 @@ def finish_loss_ptr(terms_ptr, mask, n_per_stack, n_stacks, reg_coeff, out8_ptr,
         _lib.call('dsnt_combine_loss', out8_ptr, reg_coeff, stream)
 
 
+_no_loss = {}
+
+
+def _no_loss_block(dev):
+    """The loss block of a call without a target and without a regulariser (forward_part2: coordinates only): every
+    term is zero, the denominator 1 -- a per-device constant instead of a finishing launch over n zeros."""
+    blk = _no_loss.get(dev)
+    if blk is None:
+        blk = torch.tensor([0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        _no_loss[dev] = blk
+    return blk
+
+
 class _FusedHead(torch.autograd.Function):
     """forward: dsnt_head_fwd + dsnt_finish_loss;  backward: dsnt_head_bwd (include/dsnt_b200.h)."""
 
@@ -105,17 +148,20 @@ class _FusedHead(torch.autograd.Function):
     def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, variant, input_is_logits, aux):
         zc, n, h, w = _flat_heatmaps(z)
         dev = zc.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
             coords = torch.empty(n, 2, dtype=torch.float32, device=dev)
             stats = torch.empty(n, _lib.STATS_K, dtype=torch.float32, device=dev)
             terms = torch.empty(n, 2, dtype=torch.float32, device=dev)
-            out8 = torch.empty(8, dtype=torch.float32, device=dev)
             _lib.call('dsnt_head_fwd', zc.data_ptr(), _lib.dtype_id(zc), int(input_is_logits), n, h, w,
                       _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(),
                       variant, stream)
-            ws = _lib.finish_workspace(dev)
-            finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
+            if target is None and reg_id == 0 and not _is_sharded(group):
+                out8 = _no_loss_block(dev)
+            else:
+                out8 = torch.empty(8, dtype=torch.float32, device=dev)
+                ws = _lib.finish_workspace(dev, stream)
+                finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(zc, target, mask, stats, out8)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, variant, input_is_logits, z.shape)
         ctx.set_materialize_grads(False)
@@ -129,7 +175,7 @@ class _FusedHead(torch.autograd.Function):
         dev = zc.device
         if g_coords is None and g_loss is None:
             return (None,) * 11
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
             if g_coords is not None:
                 g_coords = g_coords.to(torch.float32).contiguous()
@@ -151,7 +197,7 @@ class _FusedHeadPreact(torch.autograd.Function):
     def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, preact_id, threshold, eps, variant, aux):
         zc, n, h, w = _flat_heatmaps(z)
         dev = zc.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
             coords = torch.empty(n, 2, dtype=torch.float32, device=dev)
             stats = torch.empty(n, _lib.STATS_K, dtype=torch.float32, device=dev)
@@ -160,7 +206,7 @@ class _FusedHeadPreact(torch.autograd.Function):
             _lib.call('dsnt_head_preact_fwd', zc.data_ptr(), _lib.dtype_id(zc), preact_id, threshold, eps, n, h, w,
                       _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), variant,
                       stream)
-            ws = _lib.finish_workspace(dev)
+            ws = _lib.finish_workspace(dev, stream)
             finish_loss(terms, mask, n, 1, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(zc, target, mask, stats, out8)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, preact_id, threshold, variant, z.shape)
@@ -175,7 +221,7 @@ class _FusedHeadPreact(torch.autograd.Function):
         dev = zc.device
         if g_coords is None and g_loss is None:
             return (None,) * 13
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
             if g_coords is not None:
                 g_coords = g_coords.to(torch.float32).contiguous()
@@ -255,8 +301,7 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
                                               flags, group, _lib.PREACT_IDS[preact],
                                               float(d_thr if threshold is None else threshold),
                                               float(d_eps if eps is None else eps), int(variant), aux)
-    out8 = aux['out8']
-    return HeadOutput(coords, loss, out8[4], out8[5])
+    return HeadOutput(coords, loss, aux['out8'])
 
 
 USE_PAIR_STEP = True          # 256x256 fp32, no / variance regulariser: the cluster-of-two-CTAs one-pass step (csrc/step_pair.cu),
@@ -289,7 +334,16 @@ def takes_one_pass(z, reg, sigma, sharded):
     """The kernel-selection rule of `dsnt_head(one_pass=True)`: a pure function of dtype, heatmap shape, regulariser and --
     single process only -- the size of the batch."""
     h, w = int(z.shape[-2]), int(z.shape[-1])
-    return step_supported(z, reg) and _step_pays(z, h, w, _lib.REG_IDS[reg], sigma, group=None, sharded=sharded)
+    key = (z.dtype, h, w, reg, sigma, sharded, z.numel() * z.element_size() >= STEP_MIN_BYTES, STEP_MIN_BYTES,
+           USE_PAIR_STEP, USE_L2_STEP)
+    hit = _one_pass_cache.get(key)
+    if hit is None:
+        hit = step_supported(z, reg) and _step_pays(z, h, w, _lib.REG_IDS[reg], sigma, group=None, sharded=sharded)
+        _one_pass_cache[key] = hit
+    return hit
+
+
+_one_pass_cache = {}
 
 
 def step_supported(z, reg=None):
@@ -357,11 +411,11 @@ class _FusedHeadStep(torch.autograd.Function):
     def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, aux):
         zc, n, h, w = _flat_heatmaps(z)
         dev = zc.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
             ar = _StepArena(n, dev)
             dz = torch.empty_like(zc)
-            ws = _lib.finish_workspace(dev)
+            ws = _lib.finish_workspace(dev, stream)
             dt = _lib.dtype_id(zc)
             sharded = _is_sharded(group)
             fused = n > 0 and bool(_lib.LIB.dsnt_head_step_fused_supported(dt, h, w, reg_id, sigma))
@@ -399,9 +453,9 @@ class _FusedHeadStep(torch.autograd.Function):
         dev = zc.device
         if g_coords is None and g_loss is None:
             return (None,) * 9
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
-            if g_loss is not None:
+            if g_loss is not None and (g_loss.dtype is not torch.float32 or not g_loss.is_contiguous()):
                 g_loss = g_loss.to(torch.float32).contiguous()
             dz = ctx.dz_box[0]
             if g_coords is None and dz is not None:
@@ -431,23 +485,26 @@ class _FusedHeadStacked(torch.autograd.Function):
         n, h, w = flat[0][1], flat[0][2], flat[0][3]
         s_count = len(zcs)
         dev = zcs[0].device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zcs[0])
             coords = torch.empty(s_count, n, 2, dtype=torch.float32, device=dev)
             stats = torch.empty(s_count * n, _lib.STATS_K, dtype=torch.float32, device=dev)
             terms = torch.empty(s_count * n, 2, dtype=torch.float32, device=dev)
-            out8 = torch.empty(8, dtype=torch.float32, device=dev)
             _lib.call('dsnt_head_fwd_stacked', _lib.ptr_array(zcs), s_count, _lib.dtype_id(zcs[0]), 1, n, h, w,
                       _lib.ptr(target), reg_id, sigma, coords.data_ptr(), stats.data_ptr(), terms.data_ptr(),
                       variant, stream)
-            ws = _lib.finish_workspace(dev)
-            finish_loss(terms, mask, n, s_count, reg_coeff, out8, ws, group, dev, stream)
+            if target is None and reg_id == 0 and not _is_sharded(group):
+                out8 = _no_loss_block(dev)
+            else:
+                out8 = torch.empty(8, dtype=torch.float32, device=dev)
+                ws = _lib.finish_workspace(dev, stream)
+                finish_loss(terms, mask, n, s_count, reg_coeff, out8, ws, group, dev, stream)
         ctx.save_for_backward(target, mask, stats, out8, *zcs)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, variant, [z.shape for z in zs])
         ctx.set_materialize_grads(False)
         aux['out8'] = out8
         lead = zs[0].shape[:-2]
-        return (out8[6],) + tuple(coords[i].view(*lead, 2) for i in range(s_count))
+        return (out8[6],) + coords.view(s_count, *lead, 2).unbind(0)
 
     @staticmethod
     def backward(ctx, g_loss, *g_coords):
@@ -458,7 +515,7 @@ class _FusedHeadStacked(torch.autograd.Function):
         dev = zcs[0].device
         if g_loss is None and all(g is None for g in g_coords):
             return (None,) * (9 + s_count)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zcs[0])
             gc = None
             if any(g is not None for g in g_coords):
@@ -490,11 +547,11 @@ class _FusedHeadStackedStep(torch.autograd.Function):
         n, h, w = flat[0][1], flat[0][2], flat[0][3]
         s_count = len(zcs)
         dev = zcs[0].device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zcs[0])
             ar = _StepArena(s_count * n, dev)
             dz = torch.empty((s_count,) + tuple(zcs[0].shape), dtype=zcs[0].dtype, device=dev)
-            ws = _lib.finish_workspace(dev)
+            ws = _lib.finish_workspace(dev, stream)
             hm_bytes = dz[0].numel() * dz.element_size()
             dz_ptrs = (ctypes.c_void_p * s_count)(*[dz.data_ptr() + i * hm_bytes for i in range(s_count)])
             _lib.call('dsnt_head_step_fused_stacked', _lib.ptr_array(zcs), dz_ptrs,
@@ -506,8 +563,7 @@ class _FusedHeadStackedStep(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         aux['out8'] = ar.out8()
         lead = zs[0].shape[:-2]
-        coords = ar.coords().view(s_count, n, 2)
-        return (aux['out8'][6],) + tuple(coords[i].view(*lead, 2) for i in range(s_count))
+        return (aux['out8'][6],) + ar.coords().view(s_count, *lead, 2).unbind(0)
 
     @staticmethod
     def backward(ctx, g_loss, *g_coords):
@@ -518,7 +574,7 @@ class _FusedHeadStackedStep(torch.autograd.Function):
         dev = zcs[0].device
         if g_loss is None and all(g is None for g in g_coords):
             return (None,) * (7 + s_count)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             stream = _lib.stream_of(zcs[0])
             if g_loss is not None:
                 g_loss = g_loss.to(torch.float32).contiguous()
@@ -527,7 +583,10 @@ class _FusedHeadStackedStep(torch.autograd.Function):
             if no_gc and dz is not None:
                 ctx.dz_box[0] = None
                 _lib.call('dsnt_scale_unless_one', dz.data_ptr(), _lib.dtype_id(dz), dz.numel(), g_loss.data_ptr(), stream)
-                return (None,) * 7 + tuple(dz[i].view(shape) for i, shape in enumerate(shapes))
+                parts = dz.unbind(0)
+                if any(prt.shape != shape for prt, shape in zip(parts, shapes)):
+                    parts = tuple(prt.view(shape) for prt, shape in zip(parts, shapes))
+                return (None,) * 7 + parts
             gc = None
             if not no_gc:
                 gc = torch.zeros(s_count, n, 2, dtype=torch.float32, device=dev)

@@ -231,3 +231,36 @@ def test_sharded_two_gpus(env):
                        text=True, timeout=600)
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0 and 'check_sharded: PASS' in r.stdout
+
+
+@pytest.mark.parametrize('offset', [0.0, 0.004, 0.02, 0.031, 0.3])
+def test_pair_variance_pivot_form_and_exact_fallback(dp, offset):
+    """csrc/step_pair.cu takes the second moments about the TARGET in the one sweep and falls back to an exact second walk
+    about the mean when (mean - target)^2 > 16 var.  Trained-like 256x256 heatmaps (a 2 px Gaussian of logits) whose peak sits
+    `offset` from the target: ratios 0, 0.07, 1.6, 3.9 (pivot form) and 370 (exact walk); the regulariser is weighted so that
+    it shows in loss and gradient."""
+    from oracle import torch_port as tp
+    gen = torch.Generator().manual_seed(97)
+    n, h, w = 5, 256, 256
+    target = torch.rand(n, 1, 2, generator=gen) * 1.2 - 0.6
+    centre = target + offset * torch.tensor([0.6, 0.8])
+    z = (tp.make_gauss(centre, w, h, 2.0 * 2.0 / w) + 1e-12).log() + 0.01 * torch.randn(n, 1, h, w, generator=gen)
+    coeff = 1e4
+    zz = z.to(DEV).requires_grad_(True)
+    out = dp.dsnt_head(zz, target.to(DEV), None, reg='var', hm_sigma=1.0, reg_coeff=coeff, one_pass=True)
+    out.loss.backward()
+    z2 = z.to(DEV).requires_grad_(True)
+    two = dp.dsnt_head(z2, target.to(DEV), None, reg='var', hm_sigma=1.0, reg_coeff=coeff, one_pass=False)
+    two.loss.backward()
+    ref = tp.head_loss_and_grad(z, target, None, 'var', 1.0, coeff, dtype=torch.float64)
+    e_reg = abs(out.reg.item() - ref['reg'].item()) / ref['reg'].item()
+    e_loss = abs(out.loss.item() - ref['loss'].item()) / ref['loss'].item()
+    e_dz = rel_l2(zz.grad.cpu().double().numpy(), ref['dz'].numpy())
+    e_two = rel_l2(z2.grad.cpu().double().numpy(), ref['dz'].numpy())
+    print('offset %.3f: reg %.3e (rel.err %.1e) loss rel.err %.1e dz %.1e (two-kernel path: %.1e)'
+          % (offset, ref['reg'].item(), e_reg, e_loss, e_dz, e_two))
+    assert (out.coords.detach().cpu().double() - ref['coords']).abs().max().item() < TOL
+    assert e_reg < 1e-5 and e_loss < 1e-5
+    # dL/dz of a 2 px peak: (x - mu)^2 - var cancels to a few digits around the peak in ANY fp32 evaluation (the reference's own
+    # fp32 result is 2e-5 from fp64 at this weight); the pivot form must not be worse than the Welford form of the two-kernel path
+    assert e_dz < max(2e-5, 1.5 * e_two)
