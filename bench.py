@@ -565,34 +565,47 @@ def loss_identity(cx, head):
     return {'checked': True, 'identical': True, 'loss': float(loss.item()), 'ranks': cx.world}
 
 
-def exchange_timeline(cx, head, steps=40):
+def exchange_timeline(cx, head, graphs=None, steps=40):
     """Per-rank timeline of the single-launch step from the %globaltimer stamps the kernel leaves in its workspace
-    (include/dsnt_b200.h: dsnt_finish_trace_offset_bytes): where the time between the ranks goes."""
+    (include/dsnt_b200.h: dsnt_finish_trace_offset_bytes): where the time between the ranks goes.  Steps are replayed from
+    the captured graphs when there are any (as in the timed region), else run eagerly."""
     torch, dist, lib = cx.torch, cx.dist, cx.lib
-    ws = lib.finish_workspace(cx.dev)
     off = lib.LIB.dsnt_finish_trace_offset_bytes() // 4
+    run = (lambda i: graphs[i % len(graphs)].replay()) if graphs else head.step
+    run(0)
+    cx.barrier()
+    # the workspace is per (device, stream): the one this step used carries the most recent entry stamp
+    best, ws = -1, None
+    for (dev_index, _), w in list(lib._workspaces.items()):
+        if dev_index != cx.dev.index:
+            continue
+        stamp = int(w[off:off + 16].view(torch.int64)[5].item())
+        if stamp > best:
+            best, ws = stamp, w
+    if ws is None or best <= 0:
+        return None
     log = torch.zeros(steps, 16, dtype=torch.float32, device=cx.dev)
-    evs = []
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for i in range(steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        head.step(i)
-        e1.record()
+        run(i)
         log[i].copy_(ws[off:off + 16])
-        evs.append((e0, e1))
+    e1.record()
     cx.barrier()
     st = log.view(torch.int64).cpu()[5:]                      # [steps, 8] ns; skip the first steps
-    step_us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs[5:])
     if int(st[:, 0].min()) == 0:
         return None
 
     def med(col_a, col_b):
         d = ((st[:, col_b] - st[:, col_a]).double() / 1e3).sort().values
         return float(d[len(d) // 2])
-    mine = {'rank': cx.rank, 'step_us_median_eager': step_us[len(step_us) // 2], 'entry_to_first_sync_us': med(5, 0), 'entry_to_loads_issued_us': med(5, 6),
+    gaps = ((st[1:, 5] - st[:-1, 4]).double() / 1e3).sort().values          # loss block written -> next kernel's entry
+    mine = {'rank': cx.rank, 'mode': 'graph replay' if graphs else 'eager', 'step_us': e0.elapsed_time(e1) / steps * 1e3,
+            'entry_to_first_sync_us': med(5, 0), 'entry_to_loads_issued_us': med(5, 6),
             'start_to_local_count_us': med(0, 1), 'count_exchange_us': med(1, 2),
             'start_to_last_cta_done_us': med(0, 3), 'loss_exchange_and_compose_us': med(3, 4),
-            'kernel_us': med(0, 4)}
+            'kernel_us': med(5, 4), 'between_kernels_us': float(gaps[len(gaps) // 2])}
     if cx.world == 1:
         return [mine]
     out = [None] * cx.world
@@ -752,7 +765,7 @@ def main_ours(args):
         # launched as plain `python bench.py --gpus N`: re-exec under torchrun, one rank per GPU
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 2000), os.path.abspath(__file__)]
-        return subprocess.call(cmd + sys.argv[1:])
+        return subprocess.call(cmd + sys.argv[1:], stdout=RESULT_OUT.fileno())      # the ranks print the JSON line to OUR stdout
     cx = Ctx(args)
     torch, dist, lib = cx.torch, cx.dist, cx.lib
     rank, world = cx.rank, cx.world
@@ -774,7 +787,7 @@ def main_ours(args):
     identity = loss_identity(cx, head)
     timeline = None
     if head.one_pass and (kernel_ms.get('dsnt_head_step_fused') or kernel_ms.get('dsnt_head_step_fused_peer')):
-        timeline = exchange_timeline(cx, head)
+        timeline = exchange_timeline(cx, head, graphs)
 
     # ---------------- end-to-end timing: host buffers in, loss + coords out, copies inside the timed region
     e2e = None if args.no_e2e or head.stacks > 1 else run_e2e(cx, head, args.steps)
@@ -795,7 +808,7 @@ def main_ours(args):
             strong = {'scaling': 'strong', 'config': workload_config(args.workload, world, 'strong'),
                       'value': n_glob * args.steps / (sms * 1e-3), 'unit': UNIT, 'ms_per_step': sms / args.steps,
                       'launch': snote, 'launches_per_step': sl, 'loss_identical_on_all_ranks': loss_identity(cx, hs),
-                      'timeline': exchange_timeline(cx, hs) if (sk.get('dsnt_head_step_fused_peer')) else None}
+                      'timeline': exchange_timeline(cx, hs, sgraphs) if (sk.get('dsnt_head_step_fused_peer')) else None}
             try:
                 strong['roofline'] = roofline_of(cx, hs, sk, None)
             except RuntimeError:

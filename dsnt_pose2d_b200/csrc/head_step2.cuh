@@ -213,6 +213,9 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   __shared__ unsigned long long pace_next;        // clock at which the CTA may issue its next bulk load (p.pace)
   __shared__ PendingLoad pend_all[NWMAX];
   __shared__ float fin[NWMAX][2];                  // single-launch form: per-warp sums of mask * (distance, divergence)
+  __shared__ float fin_mask[NWMAX];                // ... and of the mask slice at the start.  NOT fin[]: a warp without heatmaps
+                                                   // is at the end of the kernel (writing fin) while warp 0 still reads these
+                                                   // (found by compute-sanitizer --tool racecheck, profiles/r02_sanitizer_*)
   __shared__ bool fin_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -257,13 +260,23 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   unsigned long long* const trace = reinterpret_cast<unsigned long long*>(p.ws + kFinishTrace);
   const long nmask = p.st.count > 1 ? p.st.n_per : p.n;       // the stacks share one mask
   if (!p.denom && blockIdx.x == 0 && threadIdx.x == 0) trace[6] = global_timer_ns();     // barriers initialised, first loads issued
-  if (!p.denom && p.mask) {
-    const long chunk = (nmask + gridDim.x - 1) / gridDim.x;
+  // Only the first kCountCtas CTAs add up the mask: they are the first to be launched, so the count does not wait for the
+  // last of 148 CTAs to get going (measured: the local count was there 10 us after kernel entry with all CTAs taking part).
+  constexpr unsigned kCountCtas = 16;
+  const unsigned nct = gridDim.x < kCountCtas ? gridDim.x : kCountCtas;
+  if (!p.denom && p.mask && blockIdx.x < nct) {
+    const long chunk = (nmask + nct - 1) / nct;
     const long lo = blockIdx.x * chunk, hi = lo + chunk < nmask ? lo + chunk : nmask;
-    float sm = 0.f;
-    for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) sm += __ldg(p.mask + i);
-    sm = warp_sum(sm);
-    if (lane == 0) fin[warp][0] = sm;
+    float s0 = 0.f, s1 = 0.f, s2m = 0.f, s3 = 0.f;
+    const long bd = blockDim.x;
+    long i = lo + threadIdx.x;
+    for (; i + 3 * bd < hi; i += 4 * bd) {          // four independent loads in flight
+      const float v0 = __ldg(p.mask + i), v1 = __ldg(p.mask + i + bd), v2 = __ldg(p.mask + i + 2 * bd), v3 = __ldg(p.mask + i + 3 * bd);
+      s0 += v0; s1 += v1; s2m += v2; s3 += v3;
+    }
+    for (; i < hi; i += bd) s0 += __ldg(p.mask + i);
+    const float sm = warp_sum((s0 + s1) + (s2m + s3));
+    if (lane == 0) fin_mask[warp] = sm;
   }
   __syncthreads();           // barriers initialised, issued[] and pace_next set, mask partials in fin[]
   if (!p.denom) {
@@ -274,25 +287,18 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
       if (p.mask) {
         float* mpart = p.ws + kFinishMaskPart;
         unsigned last = 0u;
-        if (lane == 0) {
+        if (lane == 0 && blockIdx.x < nct) {
           float t2 = 0.f;
-          for (int w2 = 0; w2 < p.nwarps; ++w2) t2 += fin[w2][0];
+          for (int w2 = 0; w2 < p.nwarps; ++w2) t2 += fin_mask[w2];
           __stcg(mpart + blockIdx.x, t2);
           __threadfence();
-          last = atomicAdd(ctl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+          last = atomicAdd(ctl + 1, 1u) == nct - 1 ? 1u : 0u;
         }
         publish = __shfl_sync(kFull, last, 0) != 0u;
         if (publish) {
           __threadfence();
-          float v[kFinishSlots / 32];
-#pragma unroll
-          for (int k = 0; k < kFinishSlots / 32; ++k) {
-            const int i = lane + 32 * k;
-            v[k] = i < static_cast<int>(gridDim.x) ? __ldcg(mpart + i) : 0.f;
-          }
-          tot = 0.f;
-#pragma unroll
-          for (int k = 0; k < kFinishSlots / 32; ++k) tot += v[k];
+          static_assert(kCountCtas <= 32, "one partial per lane");
+          tot = lane < static_cast<int>(nct) ? __ldcg(mpart + lane) : 0.f;
           tot = warp_sum(tot);
         }
       }

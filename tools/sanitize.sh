@@ -2,7 +2,7 @@
 # compute-sanitizer over the kernels of the hot path.  Run on the GPU box:
 #   bash tools/sanitize.sh [outdir]          (1 GPU: memcheck, racecheck, synccheck over tools/sanitize_workload.py)
 #   bash tools/sanitize.sh [outdir] peer     (2 GPUs: memcheck + racecheck of the peer exchanges, one sanitizer per rank)
-# Only this library's kernels are instrumented (--kernel-name regex:dsnt); logs go to <outdir>/sanitizer_<tool>_<case>.log and a
+# Only this library's kernels are instrumented (--kernel-name kns=dsnt); logs go to <outdir>/sanitizer_<tool>_<case>.log and a
 # one-line verdict per run to <outdir>/sanitizer_summary.txt.
 set -uo pipefail
 ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
@@ -14,7 +14,7 @@ cd "$ROOT"
 run_one() {   # tool, label, command...
   local tool="$1" label="$2"; shift 2
   local log="$OUT/sanitizer_${tool}_${label}.log"
-  timeout 900 compute-sanitizer --tool "$tool" --kernel-name regex:dsnt --error-exitcode 9 --launch-timeout 120 \
+  timeout 1500 compute-sanitizer --tool "$tool" --kernel-name kns=dsnt --error-exitcode 9 --launch-timeout 120 \
       --print-limit 20 "$@" > "$log" 2>&1
   local rc=$?
   local errs
@@ -24,7 +24,7 @@ run_one() {   # tool, label, command...
 if [ "$MODE" = "peer" ]; then
   for tool in memcheck racecheck; do
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
-      --no-python compute-sanitizer --tool "$tool" --kernel-name regex:dsnt --error-exitcode 9 --launch-timeout 120 \
+      --no-python compute-sanitizer --tool "$tool" --kernel-name kns=dsnt --error-exitcode 9 --launch-timeout 120 \
       --print-limit 20 --log-file "$OUT/sanitizer_${tool}_peer_%q{RANK}.log" python tools/sanitize_workload.py peer \
       > "$OUT/sanitizer_${tool}_peer_stdout.log" 2>&1
     rc=$?
@@ -33,9 +33,9 @@ if [ "$MODE" = "peer" ]; then
     done
   done
 else
-  for tool in memcheck racecheck synccheck; do
-    for c in step stacked generic pair two level1; do
-      run_one "$tool" "$c" python tools/sanitize_workload.py "$c"
-    done
-  done
+  # one process per tool (importing torch under the sanitizer is the slow part): memcheck over every kernel family,
+  # racecheck / synccheck over the kernels with shared-memory protocols (mbarrier rings, DSMEM exchange, block reductions)
+  run_one memcheck all python tools/sanitize_workload.py step stacked generic pair two level1
+  run_one racecheck smem python tools/sanitize_workload.py step stacked generic pair two
+  run_one synccheck smem python tools/sanitize_workload.py step stacked generic pair two
 fi
