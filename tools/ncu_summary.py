@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report into the small JSON summaries kept under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_v1 [--match head_]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_v1 [--match head_] [--all]
+
+--all: one file per captured LAUNCH (suffix _launchN) instead of the first launch of each distinct kernel.
 
 Writes one <prefix>_<short kernel name>.ncu_summary.json per distinct kernel (first captured launch of each)
 with the metrics DESIGN.md quotes (DRAM bytes, durations, pipe utilisation, stall reasons, registers,
@@ -47,24 +49,25 @@ def main():
         print(__doc__)
         return 2
     rep, prefix = sys.argv[1], sys.argv[2]
-    match = sys.argv[4] if len(sys.argv) > 4 and sys.argv[3] == '--match' else ''
+    match = sys.argv[sys.argv.index('--match') + 1] if '--match' in sys.argv else ''
+    every = '--all' in sys.argv
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], check=True, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     header, units, body = rows[0], rows[1], rows[2:]
     name_col = header.index('Kernel Name')
     seen = {}
-    for row in body:
+    for idx, row in enumerate(body):
         kname = row[name_col]
         if match and match not in kname:
             continue
-        if kname in seen:
+        if kname in seen and not every:
             continue
         summary = {'Kernel Name': kname}
         for col, unit, val in zip(header, units, row):
             if KEEP.match(col):
                 summary[col] = {'value': to_number(val), 'unit': unit}
         seen[kname] = summary
-        out = '%s_%s.ncu_summary.json' % (prefix, short_name(kname))
+        out = '%s_%s%s.ncu_summary.json' % (prefix, short_name(kname), '_launch%d' % idx if every else '')
         with open(out, 'w') as f:
             json.dump(summary, f, indent=1, sort_keys=True)
 

@@ -1,7 +1,9 @@
 #!/usr/bin/env bash
 # compute-sanitizer over the kernels of the hot path.  Run on the GPU box:
 #   bash tools/sanitize.sh [outdir]          (1 GPU: memcheck, racecheck, synccheck over tools/sanitize_workload.py)
-#   bash tools/sanitize.sh [outdir] peer     (2 GPUs: memcheck + racecheck of the peer exchanges, one sanitizer per rank)
+#   bash tools/sanitize.sh [outdir] peer     (2 GPUs: memcheck + racecheck of the peer exchanges, one sanitizer per rank;
+#                                             --report-api-errors no: torch's symmetric-memory set-up PROBES for fabric handles with
+#                                             a cuMemCreate that is allowed to fail, which memcheck would count as an error)
 # Only this library's kernels are instrumented (--kernel-name kns=dsnt); logs go to <outdir>/sanitizer_<tool>_<case>.log and a
 # one-line verdict per run to <outdir>/sanitizer_summary.txt.
 set -uo pipefail
@@ -25,7 +27,7 @@ if [ "$MODE" = "peer" ]; then
   for tool in memcheck racecheck; do
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
       --no-python compute-sanitizer --tool "$tool" --kernel-name kns=dsnt --error-exitcode 9 --launch-timeout 120 \
-      --print-limit 20 --log-file "$OUT/sanitizer_${tool}_peer_%q{RANK}.log" python tools/sanitize_workload.py peer \
+      --report-api-errors no --print-limit 20 --log-file "$OUT/sanitizer_${tool}_peer_%q{RANK}.log" python tools/sanitize_workload.py peer \
       > "$OUT/sanitizer_${tool}_peer_stdout.log" 2>&1
     rc=$?
     for r in 0 1; do
