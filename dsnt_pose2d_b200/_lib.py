@@ -76,6 +76,8 @@ SIGNATURES = {
     'dsnt_tsoftmax_bwd': (_c_int, [_c_ptr, _c_ptr, _c_int, _c_long, _c_long, _c_ptr, _c_ptr]),
     'dsnt_make_gauss_fwd': (_c_int, [_c_ptr, _c_long, _c_int, _c_int, _c_float, _c_ptr, _c_ptr]),
     'dsnt_make_gauss_bwd': (_c_int, [_c_ptr, _c_ptr, _c_long, _c_int, _c_int, _c_float, _c_ptr, _c_ptr]),
+    'dsnt_reg_dmu': (_c_int, [_c_ptr, _c_int, _c_int, _c_long, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_float,
+                              _c_int, _c_float, _c_ptr, _c_ptr]),
 }
 
 

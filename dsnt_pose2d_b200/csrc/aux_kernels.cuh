@@ -299,4 +299,79 @@ __global__ void __launch_bounds__(kGaussBlock) make_gauss_bwd_kernel(const float
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gradient of the Gaussian-target regularisers w.r.t. the target centres mu_t.  In the reference kl / js / mse_reg_loss
+// build their target with make_gauss (src/dsnt/nn.py:232,250,268), which is differentiable w.r.t. mu_t (:170), so a
+// caller whose targets require grad gets d(loss)/d(mu_t) from autograd.  Here: one CTA per heatmap evaluates
+//   dD/dG_ij   KL: -P/(G+eps)    JS: 1/2 [ln(G+eps) - ln(M+eps) + G/(G+eps) - M/(M+eps)]    MSE: -2 (P - G)
+// on the fly and pushes it through the Jacobian of the normalised Gaussian exactly as make_gauss_bwd_kernel does:
+//   dmu_x = sum g G u_x - (sum g G)(sum G u_x),  u_x = (x_j - mu_x)/sigma^2,
+// scaled by d(loss) * reg_coeff * mask / denominator.  P comes from normalised heatmaps, or from logits and the saved
+// softmax statistics (m log2e, 1/S).  Not on the bandwidth path: the targets of a training run carry no gradient.
+template <typename T, int REG>
+__global__ void __launch_bounds__(kGaussBlock) reg_dmu_kernel(const T* __restrict__ z, int input_is_logits,
+                                                             const float* __restrict__ stats, const float* __restrict__ mu,
+                                                             const float* __restrict__ mask, const float* __restrict__ g_loss,
+                                                             const float* __restrict__ denom, float reg_coeff, int W, int H,
+                                                             float sigma, float* __restrict__ dmu) {
+  extern __shared__ __align__(16) float dyn_smem[];
+  __shared__ float red_a[4 * kGaussBlock / 32];
+  __shared__ float red_b[2 * kGaussBlock / 32];
+  float* tabx = dyn_smem;
+  float* taby = tabx + ((W + 3) & ~3);
+  float* scal = taby + ((H + 3) & ~3);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long n = blockIdx.x;
+  const float tx = mu[2 * n], ty = mu[2 * n + 1];
+  const float k2 = -0.5f / (sigma * sigma) * kLog2e;
+  if (warp == 0) {
+    float s, h;
+    gauss_axis_table(tabx, W, tx, k2, lane, s, h);
+    if (lane == 0) scal[0] = s;
+  } else if (warp == 1) {
+    float s, h;
+    gauss_axis_table(taby, H, ty, k2, lane, s, h);
+    if (lane == 0) scal[2] = s;
+  }
+  __syncthreads();
+  const float ginv = 1.0f / (scal[0] * scal[2] + kEps);
+  const float is2 = 1.0f / (sigma * sigma);
+  const float two_over_w = 2.0f / W, bias_w = 1.0f / W - 1.0f;
+  const float two_over_h = 2.0f / H, bias_h = 1.0f / H - 1.0f;
+  const T* zr = z + n * static_cast<long>(H) * W;
+  float m2 = 0.f, invS = 1.f;
+  if (input_is_logits) { m2 = stats[n * kStatsK]; invS = stats[n * kStatsK + 1]; }
+  float a1x = 0.f, a1y = 0.f, a0 = 0.f, unused = 0.f, ux = 0.f, uy = 0.f;
+  for (int idx = threadIdx.x; idx < H * W; idx += kGaussBlock) {
+    const int i = idx / W, j = idx - i * W;
+    const float G = tabx[j] * (taby[i] * ginv);
+    const float v = load_as_float(zr, idx);
+    const float P = input_is_logits ? ex2(fmaf(v, kLog2e, -m2)) * invS : v;
+    float g;
+    if constexpr (REG == DSNT_REG_KL) {
+      g = -P / (G + kEps);
+    } else if constexpr (REG == DSNT_REG_JS) {
+      const float M = 0.5f * (P + G);
+      g = 0.5f * (kLn2 * (lg2(G + kEps) - lg2(M + kEps)) + G / (G + kEps) - M / (M + kEps));
+    } else {
+      g = -2.0f * (P - G);
+    }
+    const float vx = (axis_coord(j, two_over_w, bias_w) - tx) * is2;
+    const float vy = (axis_coord(i, two_over_h, bias_h) - ty) * is2;
+    const float gg = g * G;
+    a1x = fmaf(gg, vx, a1x);
+    a1y = fmaf(gg, vy, a1y);
+    a0 += gg;
+    ux = fmaf(G, vx, ux);
+    uy = fmaf(G, vy, uy);
+  }
+  group_sum4<kGaussBlock>(a1x, a1y, a0, unused, red_a, warp, lane);
+  group_sum2<kGaussBlock>(ux, uy, red_b, warp, lane);
+  if (threadIdx.x == 0) {
+    const float sc = __ldg(g_loss) * reg_coeff * (mask ? mask[n] : 1.0f) / __ldg(denom);
+    dmu[2 * n] = sc * (a1x - a0 * ux);
+    dmu[2 * n + 1] = sc * (a1y - a0 * uy);
+  }
+}
+
 }  // namespace dsnt

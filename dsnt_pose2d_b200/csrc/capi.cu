@@ -31,6 +31,26 @@ int check_launch(const char* what) {
 
 using namespace dsnt;
 
+template <typename T>
+static int launch_reg_dmu(const void* z, int input_is_logits, const float* stats, const float* mu, const float* mask,
+                          const float* g_loss, const float* denom, float reg_coeff, long n, int W, int H, float sigma, int reg,
+                          float* dmu, size_t smem, cudaStream_t s) {
+  const T* zt = static_cast<const T*>(z);
+  const unsigned grid = static_cast<unsigned>(n);
+  switch (reg) {
+    case DSNT_REG_KL:
+      reg_dmu_kernel<T, DSNT_REG_KL><<<grid, kGaussBlock, smem, s>>>(zt, input_is_logits, stats, mu, mask, g_loss, denom, reg_coeff, W, H, sigma, dmu);
+      break;
+    case DSNT_REG_JS:
+      reg_dmu_kernel<T, DSNT_REG_JS><<<grid, kGaussBlock, smem, s>>>(zt, input_is_logits, stats, mu, mask, g_loss, denom, reg_coeff, W, H, sigma, dmu);
+      break;
+    default:
+      reg_dmu_kernel<T, DSNT_REG_MSE><<<grid, kGaussBlock, smem, s>>>(zt, input_is_logits, stats, mu, mask, g_loss, denom, reg_coeff, W, H, sigma, dmu);
+      break;
+  }
+  return check_launch("reg_dmu_kernel");
+}
+
 extern "C" {
 
 DSNT_API int dsnt_b200_version(void) { return DSNT_B200_VERSION; }
@@ -283,6 +303,22 @@ DSNT_API int dsnt_make_gauss_bwd(const float* mu, const float* g, long n, int W,
   if (smem > kMaxDynSmem) { set_error("gaussian %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
   make_gauss_bwd_kernel<<<static_cast<unsigned>(n), kGaussBlock, smem, static_cast<cudaStream_t>(stream)>>>(mu, g, W, H, sigma, dmu);
   return check_launch("make_gauss_bwd_kernel");
+}
+
+DSNT_API int dsnt_reg_dmu(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* stats,
+                          const float* mu, const float* mask, const float* g_loss, const float* denom, float reg_coeff,
+                          int reg, float sigma, float* dmu, void* stream) {
+  if (!z || !mu || !g_loss || !denom || !dmu || n < 0 || W <= 0 || H <= 0 || !(sigma > 0.f) || n > 0x7fffffffL) { set_error("dsnt_reg_dmu: bad arguments"); return DSNT_ERR_BAD_ARG; }
+  if (reg != DSNT_REG_KL && reg != DSNT_REG_JS && reg != DSNT_REG_MSE) { set_error("dsnt_reg_dmu: reg %d has no Gaussian target", reg); return DSNT_ERR_BAD_ARG; }
+  if (input_is_logits && !stats) { set_error("dsnt_reg_dmu: logits need the statistics of the forward"); return DSNT_ERR_BAD_ARG; }
+  if (n == 0) return DSNT_OK;
+  const size_t smem = sizeof(float) * table_floats(H, W);
+  if (smem > kMaxDynSmem) { set_error("gaussian %dx%d too large", H, W); return DSNT_ERR_UNSUPPORTED; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == DSNT_DTYPE_F32) return launch_reg_dmu<float>(z, input_is_logits, stats, mu, mask, g_loss, denom, reg_coeff, n, W, H, sigma, reg, dmu, smem, s);
+  if (dtype == DSNT_DTYPE_BF16) return launch_reg_dmu<__nv_bfloat16>(z, input_is_logits, stats, mu, mask, g_loss, denom, reg_coeff, n, W, H, sigma, reg, dmu, smem, s);
+  set_error("unsupported dtype %d", dtype);
+  return DSNT_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

@@ -33,7 +33,7 @@
 //
 // Same mathematics and the same closed forms as head_step.cuh (src/dsnt/nn.py:25-116,168-298,
 // src/dsnt/model.py:24-63,145); the ring of shared-memory buffers, the bulk loads and the barrier protocol are shared
-// with it.  KL keeps the generic kernel (its window, 28x28 at sigma = 1 px, does not fit the register budget).
+// with it.  KL walks its window (28x28 at sigma = 1 px) slot by slot instead of keeping it in registers.
 #pragma once
 
 #include "finish_common.cuh"
@@ -188,8 +188,13 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   constexpr bool kJS = REG == DSNT_REG_JS;
   constexpr bool kVar = REG == DSNT_REG_VAR;
   constexpr bool kMSE = REG == DSNT_REG_MSE;
-  constexpr bool kWin = kJS || kMSE;
-  static_assert(REG != DSNT_REG_KL, "KL takes the generic step kernel");
+  constexpr bool kKL = REG == DSNT_REG_KL;
+  constexpr bool kWin = kJS || kMSE || kKL;      // a Gaussian window exists
+  constexpr bool kWinRegs = kJS || kMSE;         // ... and its per-pixel terms are kept in registers between forward and backward
+  // KL: G is compared with eps = 1e-24, so its window is +-12 sigma (27 x 27 pixels at sigma = 1 px: 7 fp32 vectors per
+  // lane).  Nothing is kept: the window is walked slot by slot in the forward (sum P log2(G + eps)) and again in the
+  // backward, logits re-read from the shared-memory buffer -- which therefore carries no e stash (every pixel's gradient
+  // needs log2 P = t - log2 S, i.e. the logit itself) -- and ANY sigma is served (the loop has a run-time trip count).
   constexpr int VEC = 16 / sizeof(T);      // pixels per 128-bit vector
   constexpr int NP = VEC / 2;              // packed pairs per vector
   constexpr int WV = W / VEC;              // vectors per row
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   constexpr float kBias = sizeof(T) == 2 ? 15.0f : 0.0f;
   // MSE feeds e into its own gradient factor (2 rho (P - G) next to a x + b y - c): where the two nearly cancel, the 2^-12
   // of an fp16 e would be amplified, so bf16 + MSE recomputes e from the logits in the backward sweep instead
-  constexpr bool kStash = !(kMSE && sizeof(T) == 2);
+  constexpr bool kStash = !(kMSE && sizeof(T) == 2) && !kKL;
 
   extern __shared__ __align__(128) unsigned char step_smem[];
   __shared__ __align__(8) unsigned long long bars[kStepMaxBufs];
@@ -480,9 +485,15 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
         unpack_pairs<T>(raw, v);
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
-          e[c] = ex2_2(fma2(v[c], l2e2, nm2));
+          const f2 tt = fma2(v[c], l2e2, nm2);
+          e[c] = ex2_2(tt);
           colE[c] = add2(colE[c], e[c]);
           if (kMSE) tt2 = fma2(e[c], e[c], tt2);
+          if constexpr (kKL) {                       // sum e t; t = -inf (a logit of -inf) contributes 0, not 0 * inf
+            float t0, t1;
+            upk(tt, t0, t1);
+            tt2 = fma2(e[c], pk(fmaxf(t0, -1e30f), fmaxf(t1, -1e30f)), tt2);
+          }
         }
         f2 s = add2(e[0], e[1]);
         if constexpr (NP == 4) s = add2(s, add2(e[2], e[3]));
@@ -541,8 +552,8 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     }
 
     // ---------------------------------------------------------------- forward: divergence on the window (compact mapping)
-    f2 wd[kWin ? MAXS : 1][NP], wP[kWin ? MAXS : 1][NP];   // per window pixel: log2 P - 1 - log2 M (JS) or G (MSE); P
-    float inv_nvw = 0.f;
+    f2 wd[kWinRegs ? MAXS : 1][NP], wP[kWinRegs ? MAXS : 1][NP];   // per window pixel: log2 P - 1 - log2 M (JS) or G (MSE); P
+    float inv_nvw = 0.f, l2ginv = 0.f;
     if constexpr (kWin) {
       f2 qa = pk1(0.f), qb = pk1(0.f), qc = pk1(0.f);
       if (nwv > 0) {
@@ -561,12 +572,34 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
           sy = __shfl_sync(kFull, k, 16);
         }
         ginv = rcp(sx * sy + kEps);
-        const float l2ginv = lg2(ginv);
+        l2ginv = lg2(ginv);
         const f2 tlm1 = pk1(-lg2(S) - 1.0f);         // log2 P - 1 = t + tlm1
         const f2 hinvS = pk1(0.5f * invS), invS2 = pk1(invS), k2p = pk1(g.k2), half2 = pk1(0.5f), eps2 = pk1(kEps);
         inv_nvw = rcp(static_cast<float>(nvw));
+        if constexpr (kKL) {
+          // sum over the window of e log2(G + eps) and of e, slot by slot (run-time trip count: any sigma); nothing is kept
+#pragma unroll 1
+          for (int k = lane; k < nwv; k += 32) {
+            const int r = static_cast<int>((static_cast<float>(k) + 0.5f) * inv_nvw);
+            const int i = i_lo + r, jv = jv_lo + (k - r * nvw);
+            const uint4 raw = bufv[i * WV + jv];
+            f2 v[NP];
+            unpack_pairs<T>(raw, v);
+            const float dy = fmaf(static_cast<float>(i), toh, bh) - ty;
+            const f2 rowt = pk1(fmaf(g.k2 * dy, dy, l2ginv));
+            const f2 dx0 = pk1(fmaf(static_cast<float>(jv * VEC), tow, bw) - tx);
 #pragma unroll
-        for (int s = 0; s < MAXS; ++s) {
+            for (int c = 0; c < NP; ++c) {
+              const f2 dx = add2(dx0, pk((2 * c) * tow, (2 * c + 1) * tow));
+              const f2 L = lg2_2(add2(ex2_2(fma2(mul2(dx, k2p), dx, rowt)), eps2));      // log2(G + eps)
+              const f2 e = ex2_2(fma2(v[c], l2e2, nm2));
+              qa = fma2(e, L, qa);
+              qb = add2(qb, e);
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < (kWinRegs ? MAXS : 0); ++s) {
           const int k = lane + 32 * s;
           if (k < nwv) {
             const int r = static_cast<int>((static_cast<float>(k) + 0.5f) * inv_nvw);
@@ -612,6 +645,11 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
         const float outside = fmaxf(fmaf(Tt * invS, invS, -a1), 0.f);
         D = outside + a0;
         creg = 2.f * (outside + a2);
+      } else if (kKL) {
+        // D = sum P ln P - sum P ln(G + eps); outside the window G + eps = eps exactly (src/dsnt/nn.py:208-211,233)
+        const float plnp = kLn2 * fmaf(Tt, invS, -lg2(S));
+        D = plnp - kLn2 * fmaf(kLog2Eps, 1.0f - a1 * invS, a0 * invS);
+        creg = D + 1.0f;
       } else {
         creg = 0.5f * kLn2 * (1.0f + a0);
         D = fmaf(0.5f * kLn2, a1, creg);
@@ -646,9 +684,48 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     const float cc = fmaf(a, mux, fmaf(b, muy, rho * creg));
     float cbase = -cc;
     if (kJS) cbase = fmaf(0.5f * kLn2, rho, cbase);
+    if (kKL) cbase = fmaf(rho, 1.0f - kLnEps - kLn2 * lg2(S), cbase);      // r = ln2 t + this - [ln(G + eps) - ln eps]
+    const float rho_t = kKL ? rho * kLn2 : 0.f;
+
+    // ---------------------------------------------------------------- KL: backward on the window vectors, walked again
+    if constexpr (kKL) {
+      if (nwv > 0) {
+        const f2 a2p = pk1(a), rt2 = pk1(rho_t), kl2 = pk1(-kLn2 * rho), l2eps2 = pk1(kLog2Eps), invS2 = pk1(invS);
+        const f2 k2p = pk1(g.k2), eps2 = pk1(kEps);
+#pragma unroll 1
+        for (int k = lane; k < nwv; k += 32) {
+          const int r = static_cast<int>((static_cast<float>(k) + 0.5f) * inv_nvw);
+          const int i = i_lo + r, jv = jv_lo + (k - r * nvw);
+          const uint4 raw = bufv[i * WV + jv];
+          f2 v[NP], o[NP];
+          unpack_pairs<T>(raw, v);
+          const float y = fmaf(static_cast<float>(i), toh, bh);
+          const float dy = y - ty;
+          const f2 rowt = pk1(fmaf(g.k2 * dy, dy, l2ginv));
+          const f2 rowc = pk1(fmaf(b, y, cbase));
+          const f2 x0 = pk1(fmaf(static_cast<float>(jv * VEC), tow, bw));
+          const f2 tx2 = pk1(tx);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) {
+            const f2 x = add2(x0, pk((2 * c) * tow, (2 * c + 1) * tow));
+            const f2 dx = sub2(x, tx2);
+            const f2 L = lg2_2(add2(ex2_2(fma2(mul2(dx, k2p), dx, rowt)), eps2));
+            const f2 tt = fma2(v[c], l2e2, nm2);
+            const f2 e = ex2_2(tt);
+            float t0, t1;
+            upk(tt, t0, t1);
+            f2 gm = fma2(a2p, x, rowc);
+            gm = fma2(rt2, pk(fmaxf(t0, -1e30f), fmaxf(t1, -1e30f)), gm);
+            gm = fma2(kl2, sub2(L, l2eps2), gm);
+            o[c] = mul2(mul2(e, invS2), gm);
+          }
+          dzv[i * WV + jv] = pack_pairs<T>(o);
+        }
+      }
+    }
 
     // ---------------------------------------------------------------- backward on the window vectors, from registers
-    if constexpr (kWin) {
+    if constexpr (kWinRegs) {
       if (nwv > 0) {
         const f2 a2p = pk1(a), kw = pk1(kJS ? 0.5f * kLn2 * rho : 2.f * rho);
 #pragma unroll
@@ -691,18 +768,28 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
       const float bS = b * invS, cbS = cbase * invS;
       const float kyS = kVar ? rho * 2.f * (vy - s2) * invS : 0.f;
       const f2 rpS = pk1(kMSE ? 2.f * rho * invS * invS : 0.f);
+      const f2 rtS = pk1(rho_t * invS);
       const float yb = opaque(y0);
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const uint4 raw = bv[32 * it];
         f2 e[NP], o[NP];
+        f2 tk[kKL ? NP : 1];                       // KL: t itself enters the gradient (rho ln2 t)
         if constexpr (kStash) {
           stash_unpack<T>(raw, e);
         } else {
           f2 v[NP];
           unpack_pairs<T>(raw, v);
 #pragma unroll
-          for (int c = 0; c < NP; ++c) e[c] = ex2_2(fma2(v[c], l2e2, nm2));
+          for (int c = 0; c < NP; ++c) {
+            const f2 tt = fma2(v[c], l2e2, nm2);
+            e[c] = ex2_2(tt);
+            if constexpr (kKL) {
+              float t0, t1;
+              upk(tt, t0, t1);
+              tk[c] = pk(fmaxf(t0, -1e30f), fmaxf(t1, -1e30f));
+            }
+          }
         }
         const float y = yb + static_cast<float>(it) * dyi;
         float rc = fmaf(bS, y, cbS);
@@ -712,6 +799,7 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
         for (int c = 0; c < NP; ++c) {
           f2 gm = add2(acol[c], rc2);
           if (kMSE) gm = fma2(rpS, e[c], gm);
+          if constexpr (kKL) gm = fma2(rtS, tk[c], gm);
           o[c] = mul2(e[c], gm);
         }
         const bool inwin = kWin && colin && (it * RPI >= rlo) && (it * RPI <= rhi);

@@ -121,8 +121,15 @@ static int launch_step2_slots(const HeadStepParams& p, cudaStream_t stream) {
       }
       if (paced != 1) return launch_step2_nw<T, REG, H, W, 16, false, MAXS>(p, stream);
     }
+    if constexpr (REG == DSNT_REG_KL) {                // bound by MUFU / issue, not by HBM: more warps, no pacing
+      if (nwmax != 16) return launch_step2_nw<T, REG, H, W, 20, false, MAXS>(p, stream);
+      return launch_step2_nw<T, REG, H, W, 16, false, MAXS>(p, stream);
+    }
     return launch_step2_nw<T, REG, H, W, 16, true, MAXS>(p, stream);
   } else {
+    if constexpr (REG == DSNT_REG_KL) {                // fp32 KL: the window walk is latency-bound with 3 warps per scheduler
+      if (nwmax != 12) return launch_step2_nw<T, REG, H, W, 14, true, MAXS>(p, stream);
+    }
     return launch_step2_nw<T, REG, H, W, 12, true, MAXS>(p, stream);
   }
 }
@@ -164,7 +171,9 @@ static int launch_step_one(HeadStepParams p, cudaStream_t stream) {
 
 // does this launch take the shape-specialised kernel (head_step2.cuh)?  Returns the window slots it needs, -1 = no.
 static int step2_eligible(int dtype, int H, int W, int reg, float sigma) {
-  if (reg == DSNT_REG_KL || H != 64 || W != 64 || !step_v2() || !step_direct_store() || step_group() == 64) return -1;
+  if (H != 64 || W != 64 || !step_v2() || !step_direct_store() || step_group() == 64) return -1;
+  static const int kl_v2 = env_int("DSNT_TUNE_STEP_KL_V2", 1);      // 0: KL on the generic kernel (head_step.cuh), as in round 1
+  if (reg == DSNT_REG_KL) return kl_v2 ? 0 : -1;                    // walks its window slot by slot: any sigma
   const int vec = dtype == DSNT_DTYPE_F32 ? 4 : 8;
   const Geom g = make_geom(H, W, vec, 32, sigma > 0.f ? sigma : 1.f, reg);
   return dtype == DSNT_DTYPE_F32 ? step2_window_slots<float>(H, W, vec, reg, g.r2_win)
@@ -174,7 +183,7 @@ static int step2_eligible(int dtype, int H, int W, int reg, float sigma) {
 // one warp per heatmap by default (DSNT_TUNE_STEP_GROUP=64 selects two)
 template <typename T, int VEC, int REG>
 static int launch_step_fixc(HeadStepParams p, cudaStream_t stream) {
-  if constexpr (REG != DSNT_REG_KL) {
+  {
     const int slots = step2_eligible(sizeof(T) == 4 ? DSNT_DTYPE_F32 : DSNT_DTYPE_BF16, p.H, p.W, REG, p.sigma);
     if (slots >= 0) {
       p.g = make_geom(p.H, p.W, VEC, 32, p.sigma > 0.f ? p.sigma : 1.f, REG);

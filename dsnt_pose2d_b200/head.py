@@ -278,7 +278,10 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     if sigma is None:
         sigma = 2.0 * (1.0 if hm_sigma is None else hm_sigma) / w
     if target is not None and target.requires_grad:
-        raise NotImplementedError('dsnt_head: gradients w.r.t. the target are not implemented')
+        # Not the hot path (the reference's training loop never differentiates its targets): the reference's own composition
+        # (src/dsnt/model.py:138-145) on this library's level-1 operators, every one of which is differentiable w.r.t. the target
+        return _head_with_target_grad(z, target, mask, reg, float(sigma), float(reg_coeff), preact, threshold, eps,
+                                      input_is_logits, group)
     target = _as_f32(target, n, 2, 'target')
     mask = _as_f32(mask, n, 1, 'mask')
     flags = _lib.FLAG_STRICT_NAN if STRICT_NAN else 0
@@ -302,6 +305,29 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
                                               float(d_thr if threshold is None else threshold),
                                               float(d_eps if eps is None else eps), int(variant), aux)
     return HeadOutput(coords, loss, aux['out8'])
+
+
+def _head_with_target_grad(z, target, mask, reg, sigma, reg_coeff, preact, threshold, eps, input_is_logits, group):
+    """`dsnt_head` for a target that requires grad: heatmaps are materialised and the loss composed as the reference does."""
+    from . import nn as dnn
+    from .model import hm_preact
+    if _is_sharded(group):
+        raise NotImplementedError('dsnt_head: gradients w.r.t. the target are not implemented for a sharded batch')
+    if not input_is_logits:
+        p = z
+    elif preact == 'softmax' and threshold is None and eps is None:
+        p = dnn.softmax_2d(z)
+    elif threshold is None and eps is None and z.dim() >= 3:
+        p = hm_preact(z, preact).view(z.shape)
+    else:
+        raise NotImplementedError('dsnt_head: gradients w.r.t. the target need the default threshold / eps of the pre-activation')
+    coords = dnn.dsnt(p)
+    euclid = dnn.euclidean_loss(coords, target, mask)
+    fn = {'var': dnn.variance_reg_loss, 'kl': dnn.kl_reg_loss, 'js': dnn.js_reg_loss, 'mse': dnn.mse_reg_loss}.get(reg)
+    regv = fn(p, target, sigma, mask) if fn is not None else torch.zeros((), dtype=torch.float32, device=z.device)
+    loss = euclid + reg_coeff * regv
+    zero = torch.zeros((), dtype=torch.float32, device=z.device)
+    return HeadOutput(coords, loss, torch.stack([zero, zero, zero, zero, euclid.float(), regv.float(), loss.float(), zero]))
 
 
 USE_PAIR_STEP = True          # 256x256 fp32, no / variance regulariser: the cluster-of-two-CTAs one-pass step (csrc/step_pair.cu),
@@ -626,7 +652,12 @@ def dsnt_head_stacked(zs, target, mask=None, reg='none', sigma=None, reg_coeff=1
     if sigma is None:
         sigma = 2.0 * (1.0 if hm_sigma is None else hm_sigma) / w
     if target is not None and target.requires_grad:
-        raise NotImplementedError('dsnt_head_stacked: gradients w.r.t. the target are not implemented')
+        outs = [_head_with_target_grad(z, target, mask, reg, float(sigma), float(reg_coeff), 'softmax', None, None, True, group)
+                for z in zs]
+        total = outs[0].loss
+        for o in outs[1:]:
+            total = total + o.loss
+        return [o.coords for o in outs], total
     target = _as_f32(target, n, 2, 'target')
     mask = _as_f32(mask, n, 1, 'mask')
     flags = _lib.FLAG_STRICT_NAN if STRICT_NAN else 0

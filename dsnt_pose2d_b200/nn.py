@@ -8,8 +8,8 @@ Differences from the reference, all deliberate:
   * CUDA float32 / bfloat16 tensors only; CPU, float16 and float64 raise NotImplementedError (no fallback).
   * scalar results (coords, losses) are float32 even for bfloat16 heatmaps (the reference returns bf16).
   * d sqrt(0) = 0 instead of NaN in `euclidean_loss` unless `dsnt_pose2d_b200.head.STRICT_NAN` is set.
-  * no gradient w.r.t. `mu_t` through the regularisers (targets never carry gradients in the reference's use);
-    `make_gauss` itself IS differentiable w.r.t. its centres, as in the reference.
+  * gradients w.r.t. `mu_t` / `target` exist (as in the reference, where make_gauss is differentiable) but take one
+    extra small launch (dsnt_reg_dmu); the reference's training loop never asks for them.
 """
 
 import math
@@ -144,7 +144,9 @@ class _EuclideanLoss(torch.autograd.Function):
             ga = torch.empty(n, d, dtype=torch.float32, device=dev)
             _lib.call('dsnt_euclid_bwd', a.data_ptr(), t.data_ptr(), terms.data_ptr(), _lib.ptr(mask),
                       g.data_ptr(), out8[3:4].data_ptr(), n, d, flags, ga.data_ptr(), _lib.stream_of(a))
-        return ga.view(shape).to(dtype), None, None, None
+        g_actual = ga.view(shape).to(dtype) if ctx.needs_input_grad[0] else None
+        g_target = (-ga).view(shape).to(dtype) if ctx.needs_input_grad[1] else None      # d/dtarget = -d/dactual
+        return g_actual, g_target, None, None
 
 
 def euclidean_loss(actual, target, mask=None):
@@ -158,7 +160,7 @@ def euclidean_loss(actual, target, mask=None):
     d = actual.shape[-1]
     mask = _head._as_f32(mask, actual.numel() // d, 1, 'mask')
     flags = _lib.FLAG_STRICT_NAN if _head.STRICT_NAN else 0
-    return _EuclideanLoss.apply(actual, target.detach(), mask, flags)
+    return _EuclideanLoss.apply(actual, target, mask, flags)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -244,36 +246,49 @@ def make_gauss(coords, width, height, sigma):
 
 # --------------------------------------------------------------------------------------------------
 class _RegLoss(torch.autograd.Function):
-    """Per-heatmap divergence + masked average in two launches; backward is one streaming launch."""
+    """Per-heatmap divergence + masked average in two launches; backward is one streaming launch for the heatmaps and,
+    when the target centres require grad (they do not in the reference's training loop, but make_gauss is differentiable:
+    src/dsnt/nn.py:170,232), one small launch for d(loss)/d(mu_t) (dsnt_reg_dmu)."""
 
     @staticmethod
     def forward(ctx, heatmaps, mu_t, mask, reg_id, sigma):
         pc, n, h, w = _head._flat_heatmaps(heatmaps)
         dev = pc.device
+        mu = None if mu_t is None else mu_t.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             stream = _lib.stream_of(pc)
             coords = torch.empty(n, 2, dtype=torch.float32, device=dev)
             stats = torch.empty(n, _lib.STATS_K, dtype=torch.float32, device=dev)
             terms = torch.empty(n, 2, dtype=torch.float32, device=dev)
-            _lib.call('dsnt_head_fwd', pc.data_ptr(), _lib.dtype_id(pc), 0, n, h, w, _lib.ptr(mu_t), reg_id, sigma,
+            _lib.call('dsnt_head_fwd', pc.data_ptr(), _lib.dtype_id(pc), 0, n, h, w, _lib.ptr(mu), reg_id, sigma,
                       coords.data_ptr(), stats.data_ptr(), terms.data_ptr(), 0, stream)
             out8 = _finish(terms, mask, n, dev, stream)
-        ctx.save_for_backward(pc, mu_t, mask, stats, out8)
-        ctx.meta = (n, h, w, reg_id, sigma, heatmaps.shape)
+        ctx.save_for_backward(pc, mu, mask, stats, out8)
+        ctx.meta = (n, h, w, reg_id, sigma, heatmaps.shape, None if mu_t is None else (mu_t.shape, mu_t.dtype))
         return out8[5]
 
     @staticmethod
     def backward(ctx, g):
-        pc, mu_t, mask, stats, out8 = ctx.saved_tensors
-        n, h, w, reg_id, sigma, shape = ctx.meta
+        pc, mu, mask, stats, out8 = ctx.saved_tensors
+        n, h, w, reg_id, sigma, shape, mu_meta = ctx.meta
         dev = pc.device
+        dp = dmu = None
         with torch.cuda.device(dev):
             g = g.to(torch.float32).contiguous()
-            dp = torch.empty_like(pc)
-            _lib.call('dsnt_head_bwd', pc.data_ptr(), _lib.dtype_id(pc), 0, n, h, w, _lib.ptr(mu_t), _lib.ptr(mask),
-                      stats.data_ptr(), None, None, g.data_ptr(), out8[3:4].data_ptr(), 1.0, reg_id, sigma,
-                      _lib.FLAG_NO_EUCLID, dp.data_ptr(), 0, _lib.stream_of(pc))
-        return dp.view(shape), None, None, None, None
+            stream = _lib.stream_of(pc)
+            if ctx.needs_input_grad[0]:
+                dp = torch.empty_like(pc)
+                _lib.call('dsnt_head_bwd', pc.data_ptr(), _lib.dtype_id(pc), 0, n, h, w, _lib.ptr(mu), _lib.ptr(mask),
+                          stats.data_ptr(), None, None, g.data_ptr(), out8[3:4].data_ptr(), 1.0, reg_id, sigma,
+                          _lib.FLAG_NO_EUCLID, dp.data_ptr(), 0, stream)
+                dp = dp.view(shape)
+            if mu is not None and ctx.needs_input_grad[1]:
+                dmu = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+                if reg_id != _lib.REG_IDS['var']:
+                    _lib.call('dsnt_reg_dmu', pc.data_ptr(), _lib.dtype_id(pc), 0, n, h, w, None, mu.data_ptr(),
+                              _lib.ptr(mask), g.data_ptr(), out8[3:4].data_ptr(), 1.0, reg_id, sigma, dmu.data_ptr(), stream)
+                dmu = dmu.view(mu_meta[0]).to(mu_meta[1])
+        return dp, dmu, None, None, None
 
 
 def _reg_loss(name, heatmaps, mu_t, sigma_t, mask):
@@ -283,12 +298,11 @@ def _reg_loss(name, heatmaps, mu_t, sigma_t, mask):
     if name != 'var':
         if mu_t is None:
             raise ValueError('%s_reg_loss needs mu_t' % name)
-        if mu_t.requires_grad:
-            raise NotImplementedError('gradient w.r.t. mu_t is not implemented for the fused regularisers; '
-                                      'compose make_gauss() with the divergence instead')
-        mu_t = _head._as_f32(mu_t, n, 2, 'mu_t')
+        _lib.require_cuda(mu_t, 'mu_t')
+        if mu_t.numel() != 2 * n:
+            raise ValueError('mu_t has %d elements, expected %d' % (mu_t.numel(), 2 * n))
     else:
-        mu_t = None
+        mu_t = None                      # unused by the reference as well (src/dsnt/nn.py:274-298)
     mask = _head._as_f32(mask, n, 1, 'mask')
     return _RegLoss.apply(heatmaps, mu_t, mask, _lib.REG_IDS[name], float(sigma_t))
 

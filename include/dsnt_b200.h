@@ -143,7 +143,8 @@ DSNT_API int dsnt_mask_count(const float* mask, long n, float* out, float* works
  * CTA that finishes last composes the loss (no dsnt_finish_loss): out[0..7] exactly as dsnt_finish_loss documents,
  * workspace likewise.  The grid (one CTA per SM) is launched with the cooperative attribute, so its co-residency is
  * guaranteed by the driver.  Served for the shapes / regularisers of the shape-specialised kernel
- * (dsnt_head_step_fused_supported: 64x64, not KL, Gaussian window within its register slots); otherwise
+ * (dsnt_head_step_fused_supported: 64x64; JS / MSE: Gaussian window within its register slots, i.e. sigma up to ~1.4 px;
+ * KL walks its window and takes any sigma); otherwise
  * DSNT_ERR_UNSUPPORTED and the caller uses the three-launch form.  A sharded batch: dsnt_head_step_fused_peer below.
  * dsnt_finish_trace_offset_bytes: byte offset inside the workspace of eight uint64 %globaltimer stamps the last
  *   single-launch step left there (diagnostics; bench.py's per-rank timeline): [0] kernel start, [1] local mask count known,
@@ -301,6 +302,17 @@ DSNT_API int dsnt_tsoftmax_bwd(const void* out, const void* g, int dtype, long r
 DSNT_API int dsnt_make_gauss_fwd(const float* mu, long n, int W, int H, float sigma, float* out, void* stream);
 DSNT_API int dsnt_make_gauss_bwd(const float* mu, const float* g, long n, int W, int H, float sigma, float* dmu,
                         void* stream);
+/*
+ * d(loss)/d(mu_t) of kl / js / mse_reg_loss: in the reference the target Gaussian is built by make_gauss inside the
+ * regulariser (src/dsnt/nn.py:232,250,268) and is differentiable w.r.t. its centres (:170-205), so targets that require
+ * grad receive one.  dmu[n] = *g_loss * reg_coeff * (mask ? mask[n] : 1) / *denom * dD_n/dmu_n.
+ *   z: normalised heatmaps P (input_is_logits = 0) or logits with the forward's stats [N,DSNT_STATS_K] (= 1)
+ *   reg: DSNT_REG_KL / JS / MSE (the variance regulariser does not depend on mu_t: src/dsnt/nn.py:274-298)
+ */
+DSNT_API int dsnt_reg_dmu(const void* z, int dtype, int input_is_logits, long n, int H, int W, const float* stats,
+                          const float* mu, const float* mask, const float* g_loss, const float* denom, float reg_coeff,
+                          int reg, float sigma, float* dmu, void* stream);
+
 
 /*
  * The 'gauss' output strategy helpers, float32 arithmetic identical to the reference's.

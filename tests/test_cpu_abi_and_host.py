@@ -128,13 +128,15 @@ def test_step_support_queries_are_host_logic(libpath):
     assert lib.dsnt_head_step_supported(f32, 64, 64) == 1 and lib.dsnt_head_step_supported(bf16, 128, 128) == 1
     assert lib.dsnt_head_step_supported(f32, 128, 128) == 0 and lib.dsnt_head_step_supported(f32, 256, 256) == 0
     assert lib.dsnt_head_step_supported(f32, 7, 7) == 0 and lib.dsnt_head_step_supported(5, 64, 64) == 0
-    # single-launch form: 64x64, not KL, and the widest possible Gaussian window must fit the register slots
+    # single-launch form: 64x64; JS / MSE: the widest possible Gaussian window must fit the register slots (KL walks its window)
     sigma_1px = 2.0 / 64
     for r in ('none', 'var', 'js', 'mse'):
         assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg[r], sigma_1px) == 1
         assert lib.dsnt_head_step_fused_supported(bf16, 64, 64, reg[r], sigma_1px) == 1
         assert lib.dsnt_head_step_fused_supported(f32, 32, 32, reg[r], 2.0 / 32) == 0
-    assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg['kl'], sigma_1px) == 0
+    assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg['kl'], sigma_1px) == 1
+    assert lib.dsnt_head_step_fused_supported(bf16, 64, 64, reg['kl'], 20 * sigma_1px) == 1     # any sigma
+    assert lib.dsnt_head_step_fused_supported(f32, 32, 32, reg['kl'], 2.0 / 32) == 0
     assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg['js'], 20 * sigma_1px) == 0      # window = whole image
     assert lib.dsnt_head_step_fused_supported(f32, 64, 64, reg['var'], 20 * sigma_1px) == 1     # no window to fit
     # 256x256 fp32: a pair of CTAs, without a Gaussian window
@@ -166,8 +168,8 @@ def test_peer_entry_points_validate_their_arguments(libpath):
     assert lib.dsnt_finish_loss_peer(addr, None, 4, 1, 1.0, addr, addr, ctypes.cast(bad, ctypes.c_void_p), 0, 2, addr, addr,
                                      None) == -1
     assert 'rank 1' in _lib.last_error()
-    assert lib.dsnt_head_step_fused(addr, 0, 4, 64, 64, addr, None, None, 1.0, _lib.REG_IDS['kl'], 2.0 / 64, 0, addr, addr,
-                                    addr, addr, addr, None) == -2                               # KL: three-launch form
+    assert lib.dsnt_head_step_fused(addr, 0, 4, 32, 32, addr, None, None, 1.0, _lib.REG_IDS['kl'], 2.0 / 32, 0, addr, addr,
+                                    addr, addr, addr, None) == -2                               # 32x32: three-launch form
     assert lib.dsnt_head_step_fused(addr, 0, 4, 64, 64, addr, None, None, 1.0, 0, 1.0, 0, addr, addr, addr, None, addr,
                                     None) == -1                                                 # no loss block
 
@@ -190,8 +192,10 @@ def test_one_pass_dispatch_rule_without_gpu():
     js, kl = _lib.REG_IDS['js'], _lib.REG_IDS['kl']
     small, big = FakeZ(512, 64, 64, torch.float32), FakeZ(65536, 64, 64, torch.float32)
     assert head._step_pays(small, 64, 64, js, 2.0 / 64, None)            # single-launch form: always
-    assert not head._step_pays(small, 64, 64, kl, 2.0 / 64, None)        # KL, 8 MiB: two kernels are one launch fewer
-    assert head._step_pays(big, 64, 64, kl, 2.0 / 64, None)              # KL, 1 GiB: the saved read pays
+    assert head._step_pays(small, 64, 64, kl, 2.0 / 64, None)            # ... KL included (it walks its window)
+    wide = 20 * 2.0 / 64                                                  # JS window = whole image: generic kernel, three launches
+    assert not head._step_pays(small, 64, 64, js, wide, None)            # 8 MiB: two kernels are one launch fewer
+    assert head._step_pays(big, 64, 64, js, wide, None)                  # 1 GiB: the saved read pays
     odd = FakeZ(1024, 28, 28, torch.float32)
     assert not head._step_pays(odd, 28, 28, js, 2.0 / 28, None)
 
@@ -213,9 +217,11 @@ def test_sharded_path_decision_does_not_depend_on_the_local_shard():
                     z = torch.empty(hi - lo, 16, 64, 64, dtype=dtype)
                     picks.add(head.takes_one_pass(z, reg, sigma, sharded=True))
                 assert len(picks) == 1, (batch, world, reg, dtype, picks)
-    # single process: the size of the batch still matters (8 MiB of KL logits: two kernels are one launch fewer)
-    assert not head.takes_one_pass(torch.empty(32, 16, 64, 64), 'kl', sigma, sharded=False)
-    assert head.takes_one_pass(torch.empty(32, 16, 64, 64), 'kl', sigma, sharded=True)
+    # single process: the size of the batch still matters where the single-launch kernel does not serve the case
+    # (a JS window as wide as the image: 8 MiB of logits take two kernels, one launch fewer than three)
+    assert not head.takes_one_pass(torch.empty(32, 16, 64, 64), 'js', 20 * sigma, sharded=False)
+    assert head.takes_one_pass(torch.empty(32, 16, 64, 64), 'js', 20 * sigma, sharded=True)
+    assert head.takes_one_pass(torch.empty(32, 16, 64, 64), 'kl', sigma, sharded=False)
     # the shape decides everywhere: 7x7 has no 16-byte vectors
     assert not head.takes_one_pass(torch.empty(4, 16, 7, 7), 'js', 2.0 / 7, sharded=True)
 

@@ -308,7 +308,7 @@ def test_step64_many_heatmaps_per_cta_and_peaked_logits(dp, tp):
     assert rel_l2(got['dz'][idx.numpy()] * (n / 24.0), ref['dz'].numpy()) < TOL
 
 
-@pytest.mark.parametrize('reg', ['js', 'var', 'none', 'mse'])
+@pytest.mark.parametrize('reg', ['js', 'var', 'none', 'mse', 'kl'])
 @pytest.mark.parametrize('with_mask', [True, False])
 def test_step64_single_launch_form_matches_the_three_launch_form(dp, reg, with_mask):
     """dsnt_head_step_fused (mask count and loss composition inside the step kernel) against dsnt_mask_count +
@@ -322,7 +322,7 @@ def test_step64_single_launch_form_matches_the_three_launch_form(dp, reg, with_m
     mask = (torch.rand(n, generator=gen) > 0.2).float().to(DEV) if with_mask else None
     rid, sigma = _lib.REG_IDS[reg], 2.0 / w
     assert _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, rid, sigma) == 1
-    assert _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, _lib.REG_IDS['kl'], sigma) == 0
+    assert _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), h, w, _lib.REG_IDS['kl'], sigma) == 1     # KL walks its window
     assert _lib.LIB.dsnt_head_step_fused_supported(_lib.dtype_id(z), 32, 32, rid, sigma) == 0
     stream = torch.cuda.current_stream().cuda_stream
     ws = _lib.finish_workspace(torch.device(DEV))
@@ -349,9 +349,9 @@ def test_step64_single_launch_form_matches_the_three_launch_form(dp, reg, with_m
     assert torch.equal(b[3], c[3]) and torch.equal(b[2], c[2])
     assert torch.equal(a[3][2:4], b[3][2:4])                                  # count and denominator: exact
     assert torch.allclose(a[3], b[3], rtol=2e-6, atol=1e-7), (a[3], b[3])
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError):             # a JS window as wide as the image does not fit the register slots
         _lib.call('dsnt_head_step_fused', z.data_ptr(), 0, n, h, w, target.data_ptr(), _lib.ptr(mask), None, 0.7,
-                  _lib.REG_IDS['kl'], sigma, 0, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
+                  _lib.REG_IDS['js'], 20 * sigma, 0, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
                   ws.data_ptr(), stream)
 
 
