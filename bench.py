@@ -63,8 +63,8 @@ WORKLOADS = {
     'cfg3_8x64x64_f32_js': (32, 16, 64, 64, 'js', 'f32', 8),
 }
 DEFAULT_WORKLOAD = 'cfg4_64x64_f32_js'
-EXTRA_WORKLOADS = ['cfg4_64x64_bf16_js', 'cfg4_64x64_f32_var', 'cfg5_256x256_f32_var', 'cfg1_64x64_f32_js',
-                   'cfg2_28x28_f32_js', 'cfg3_8x64x64_f32_js']
+EXTRA_WORKLOADS = ['cfg4_64x64_bf16_js', 'cfg4_64x64_f32_var', 'cfg4_64x64_f32_kl', 'cfg5_256x256_f32_var',
+                   'cfg5_256x256_f32_js', 'cfg1_64x64_f32_js', 'cfg2_28x28_f32_js', 'cfg3_8x64x64_f32_js']
 CPU_SAMPLE = (32, 16, 64, 64)          # BASELINE cfg 1 shape: what the reference's CPU path is timed on in the `ours` run
 REG_FN = {'js': 'js_reg_loss', 'kl': 'kl_reg_loss', 'mse': 'mse_reg_loss', 'var': 'variance_reg_loss'}
 

@@ -53,6 +53,7 @@ struct PairParams {
   long n;
   int flags;
   float sigma, reg_coeff;
+  float k2, r2_win;       // Gaussian window (JS / MSE): -0.5 / sigma^2 * log2(e) and the window radius^2 (head_stream.cuh: make_geom)
 };
 
 // sum over the 1024 threads of one CTA of up to four values, identical on every thread, fixed order
@@ -84,6 +85,13 @@ __device__ __forceinline__ void pair_block_sum6(float& a, float& b, float& c, fl
 template <int REG>
 __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const PairParams p) {
   constexpr bool kVar = REG == DSNT_REG_VAR;
+  constexpr bool kJS = REG == DSNT_REG_JS;
+  constexpr bool kMSE = REG == DSNT_REG_MSE;
+  constexpr bool kWin = kJS || kMSE;
+  // JS / MSE: the Gaussian window (16 x 16 pixels at sigma = 1 px) lies in the registers of the <= 80 threads that hold its
+  // vectors.  Its terms need P = e / S, i.e. the merged sums: they are evaluated AFTER the first exchange, block-reduced
+  // and exchanged in a second message; the backward evaluates them again (nothing per-pixel is kept: the 64 registers of a
+  // thread hold its 32 values of e).  Outside the window the closed forms of head_step2.cuh apply.
   constexpr float tow = 2.0f / kPairW, bw = 1.0f / kPairW - 1.0f, toh = 2.0f / kPairH, bh = 1.0f / kPairH - 1.0f;
   extern __shared__ __align__(128) unsigned char pair_smem[];
   __shared__ __align__(8) unsigned long long bars[kPairSlots];
@@ -106,14 +114,14 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xin_s) : "r"(xin_s), "r"(peer));
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xbar_s) : "r"(xbar_s), "r"(peer));
   uint32_t xn = 0;          // messages exchanged so far: the same on both CTAs (they take the same branches on bit-identical totals)
-  auto send = [&](float a, float b, float c, float d, float e, float f) {      // thread 0; message number xn
+  auto send = [&](float a, float b, float c, float d, float e, float f, float g7 = 0.f) {      // thread 0; message number xn
     const uint32_t dst = peer_xin_s + (xn & 1u) * 32u;
     mbar_expect_tx(xbar_s, 32);
     asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
                  "f"(a), "f"(b), "f"(c), "f"(d), "r"(peer_xbar_s)
                  : "memory");
     asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst + 16),
-                 "f"(e), "f"(f), "f"(0.f), "f"(0.f), "r"(peer_xbar_s)
+                 "f"(e), "f"(f), "f"(g7), "f"(0.f), "r"(peer_xbar_s)
                  : "memory");
   };
   const uint32_t bars_s = smem_u32(&bars[0]), buf_s = smem_u32(pair_smem);
@@ -196,6 +204,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     // (mu - c)^2 / var digits: checked below, and the rare ill-conditioned heatmap takes the exact second walk about the mean.
     const float pcx = kVar ? tx : 0.f, pcy = kVar ? ty : 0.f;
     f2 colE[2] = {pk1(0.f), pk1(0.f)};
+    f2 tt2 = pk1(0.f);                       // MSE: sum e^2 (outside the window (P - G)^2 = P^2)
     float Syc = 0.f, Syy = 0.f;
     const float dyb = y0 - pcy;
 #pragma unroll
@@ -208,6 +217,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       const float dy = dyb + static_cast<float>(it) * dyi;
       Syc = fmaf(rs, dy, Syc);
       if constexpr (kVar) Syy = fmaf(rs * dy, dy, Syy);
+      if constexpr (kMSE) tt2 = fma2(ev[it][0], ev[it][0], fma2(ev[it][1], ev[it][1], tt2));
     }
     float c0, c1, c2, c3;
     upk(colE[0], c0, c1);
@@ -217,21 +227,22 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     float Sxh = fmaf(c0, dx0, fmaf(c1, dx1, fmaf(c2, dx2, c3 * dx3)));
     float Syh = Syc;
     float axh = 0.f, ayh = 0.f;
+    float Tth = 0.f;
     if constexpr (!kVar) {
-      float zero = 0.f;
-      pair_block_sum4(Sh, Sxh, Syh, zero, red, warp, lane);
+      Tth = hsum(tt2);
+      pair_block_sum4(Sh, Sxh, Syh, Tth, red, warp, lane);
     } else {
       axh = fmaf(c0 * dx0, dx0, fmaf(c1 * dx1, dx1, fmaf(c2 * dx2, dx2, c3 * dx3 * dx3)));
       ayh = Syy;
       pair_block_sum6(Sh, Sxh, Syh, axh, ayh, Syy, red, warp, lane);      // (the sixth value rides along unused)
     }
-    if (tid == 0) send(m2h, Sh, Sxh, Syh, axh, ayh);
+    if (tid == 0) send(m2h, Sh, Sxh, Syh, axh, ayh, Tth);
     mbar_wait(xbar_s, xn & 1u);
     // merge in rank order on both CTAs: bit-identical totals
     const bool first = rank == 0;
     const float (*xm)[4] = xin[xn & 1u];
     ++xn;
-    const float p_m = xm[0][0], p_S = xm[0][1], p_Sx = xm[0][2], p_Sy = xm[0][3], p_ax = xm[1][0], p_ay = xm[1][1];
+    const float p_m = xm[0][0], p_S = xm[0][1], p_Sx = xm[0][2], p_Sy = xm[0][3], p_ax = xm[1][0], p_ay = xm[1][1], p_Tt = xm[1][2];
     const float h_m[2] = {first ? m2h : p_m, first ? p_m : m2h};
     const float h_S[2] = {first ? Sh : p_S, first ? p_S : Sh};
     const float h_Sx[2] = {first ? Sxh : p_Sx, first ? p_Sx : Sxh};
@@ -282,6 +293,95 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       creg = 2.f * (ex * vx + ey * vy);
     }
 
+    // ---------------------------------------------------------------- JS / MSE: the Gaussian window, from the registers
+    float ginv = 0.f, l2ginv = 0.f;
+    int wi_lo = 0, wi_hi = -1;
+    bool colin = false;
+    const int rowb = static_cast<int>(rank) * kPairHalfRows + r0;       // this thread's rows: rowb + 16 it
+    const f2 k2p = pk1(p.k2), eps2 = pk1(kEps), half2 = pk1(0.5f), invSh2 = pk1(invSh);
+    const f2 wdx[2] = {pk(xs[0] - tx, xs[1] - tx), pk(xs[2] - tx, xs[3] - tx)};
+    // the window terms of one pair of pixels: P, and d = log2(P + eps) - 1 - log2(M + eps) (JS) or G (MSE); JS also lgG - L
+    auto win_pair = [&](int it, int c, float dyw, f2& P, f2& d, f2& gl) {
+      const f2 lgG = fma2(mul2(wdx[c], k2p), wdx[c], pk1(fmaf(p.k2 * dyw, dyw, l2ginv)));
+      const f2 G = ex2_2(lgG);
+      P = mul2(ev[it][c], invSh2);
+      if constexpr (kJS) {
+        const f2 L = lg2_2(fma2(half2, P, fma2(half2, G, eps2)));
+        d = sub2(sub2(lg2_2(add2(P, eps2)), pk1(1.0f)), L);
+        gl = mul2(G, sub2(lgG, L));
+      } else {
+        d = G;
+        gl = G;
+      }
+    };
+    if constexpr (kWin) {
+      int j_lo, j_hi;
+      axis_window_fast(tx, kPairW, 0.5f * kPairW, tow, bw, p.r2_win, j_lo, j_hi);
+      axis_window_fast(ty, kPairH, 0.5f * kPairH, toh, bh, p.r2_win, wi_lo, wi_hi);
+      const bool has = j_lo <= j_hi && wi_lo <= wi_hi;
+      f2 qa = pk1(0.f), qb = pk1(0.f), qc = pk1(0.f);
+      if (has) {
+        float sx = 0.f, sy = 0.f;                    // every warp for itself: 2 x <= 17 exponentials, no block barrier
+        for (int j = j_lo + lane; j <= j_hi; j += 32) {
+          const float d = fmaf(static_cast<float>(j), tow, bw) - tx;
+          sx += ex2(p.k2 * d * d);
+        }
+        for (int i = wi_lo + lane; i <= wi_hi; i += 32) {
+          const float d = fmaf(static_cast<float>(i), toh, bh) - ty;
+          sy += ex2(p.k2 * d * d);
+        }
+        const float k = warp_sum2_transposed(sx, sy, lane);
+        sx = __shfl_sync(kFull, k, 0);
+        sy = __shfl_sync(kFull, k, 16);
+        ginv = rcp(sx * sy + kEps);
+        l2ginv = lg2(ginv);
+        colin = cv >= (j_lo >> 2) && cv <= (j_hi >> 2);
+      } else {
+        wi_hi = wi_lo - 1;
+      }
+      if (colin) {
+#pragma unroll
+        for (int it = 0; it < kPairIters; ++it) {
+          const int row = rowb + kPairRowsPerStep * it;
+          if (row >= wi_lo && row <= wi_hi) {
+            const float dyw = (y0 + static_cast<float>(it) * dyi) - ty;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              f2 P, d, gl;
+              win_pair(it, c, dyw, P, d, gl);
+              if constexpr (kJS) {
+                qa = fma2(P, d, qa);
+                qb = add2(qb, gl);
+              } else {
+                const f2 df = sub2(P, d);
+                qa = fma2(df, df, qa);
+                qb = fma2(P, P, qb);
+                qc = fma2(P, df, qc);
+              }
+            }
+          }
+        }
+      }
+      float a0 = hsum(qa), a1 = hsum(qb), a2 = hsum(qc), a3 = 0.f;
+      pair_block_sum4(a0, a1, a2, a3, red, warp, lane);
+      if (tid == 0) send(a0, a1, a2, 0.f, 0.f, 0.f);
+      mbar_wait(xbar_s, xn & 1u);
+      const float (*xw)[4] = xin[xn & 1u];
+      ++xn;
+      const float w0 = first ? a0 + xw[0][0] : xw[0][0] + a0;       // rank order on both CTAs
+      const float w1 = first ? a1 + xw[0][1] : xw[0][1] + a1;
+      const float w2 = first ? a2 + xw[0][2] : xw[0][2] + a2;
+      if constexpr (kMSE) {
+        const float Tt = fmaf(first ? Tth : p_Tt, sc0 * sc0, (first ? p_Tt : Tth) * sc1 * sc1);      // sum e^2 over both halves
+        const float outside = fmaxf(fmaf(Tt * invS, invS, -w1), 0.f);
+        D = outside + w0;
+        creg = 2.f * (outside + w2);
+      } else {
+        creg = 0.5f * kLn2 * (1.0f + w0);
+        D = fmaf(0.5f * kLn2, w1, creg);
+      }
+    }
+
     // ---------------------------------------------------------------- outputs + the scalars of the backward
     float dist = 0.f, a = 0.f, b = 0.f;
     if (p.target) {
@@ -299,11 +399,12 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       if (p.stats) {
         float4* st = reinterpret_cast<float4*>(p.stats + hm * kStatsK);
         st[0] = make_float4(m2, invS, mux, muy);
-        st[1] = make_float4(vx, vy, creg, 0.f);
+        st[1] = make_float4(vx, vy, creg, ginv);
       }
       if (p.terms) reinterpret_cast<float2*>(p.terms)[hm] = make_float2(dist, D);
     }
-    const float cbase = -fmaf(a, mux, fmaf(b, muy, rho * creg));
+    float cbase = -fmaf(a, mux, fmaf(b, muy, rho * creg));
+    if (kJS) cbase = fmaf(0.5f * kLn2, rho, cbase);
 
     // ---------------------------------------------------------------- backward: dz = e * (A_col + R_row) / S
     {
@@ -320,6 +421,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       acol[1] = pk(av[2], av[3]);
       const float bS = b * invSh, cbS = cbase * invSh;
       const float kyS = kVar ? rho * 2.f * (vy - s2) * invSh : 0.f;
+      const f2 rpS = pk1(kMSE ? 2.f * rho * invSh * invSh : 0.f);
+      const f2 kwS = pk1(kJS ? 0.5f * kLn2 * rho * invSh : (kMSE ? -2.f * rho * invSh : 0.f));   // JS: rho (ln2/2) d;  MSE: -2 rho G
       uint4* dzv = reinterpret_cast<uint4*>(p.dz + hm * hm_floats) + static_cast<size_t>(rank) * (kPairHalfBytes / 16);
 #pragma unroll
       for (int it = 0; it < kPairIters; ++it) {
@@ -328,8 +431,20 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
         float rc = fmaf(bS, y, cbS);
         if (kVar) { const float d = y - muy; rc = fmaf(kyS * d, d, rc); }
         const f2 rc2 = pk1(rc);
-        o[0] = mul2(ev[it][0], add2(acol[0], rc2));
-        o[1] = mul2(ev[it][1], add2(acol[1], rc2));
+        f2 g0 = add2(acol[0], rc2), g1 = add2(acol[1], rc2);
+        if constexpr (kMSE) { g0 = fma2(rpS, ev[it][0], g0); g1 = fma2(rpS, ev[it][1], g1); }      // 2 rho P
+        if constexpr (kWin) {
+          const int row = rowb + kPairRowsPerStep * it;
+          if (colin && row >= wi_lo && row <= wi_hi) {                 // window pixels: the G-dependent term, evaluated again
+            f2 P, d, gl;
+            win_pair(it, 0, y - ty, P, d, gl);
+            g0 = fma2(kwS, d, g0);
+            win_pair(it, 1, y - ty, P, d, gl);
+            g1 = fma2(kwS, d, g1);
+          }
+        }
+        o[0] = mul2(ev[it][0], g0);
+        o[1] = mul2(ev[it][1], g1);
         dzv[it * kPairThreads + tid] = pack_pairs<float>(o);
       }
     }
@@ -344,7 +459,9 @@ static int pair_enabled() {
 }
 
 bool step_pair_supported(int dtype, int H, int W, int reg) {
-  return pair_enabled() && dtype == DSNT_DTYPE_F32 && H == kPairH && W == kPairW && (reg == DSNT_REG_NONE || reg == DSNT_REG_VAR);
+  static const int win = [] { const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_WIN"); return e ? std::atoi(e) : 1; }();
+  return pair_enabled() && dtype == DSNT_DTYPE_F32 && H == kPairH && W == kPairW &&
+         (reg == DSNT_REG_NONE || reg == DSNT_REG_VAR || (win && (reg == DSNT_REG_JS || reg == DSNT_REG_MSE)));
 }
 
 template <int REG>
@@ -391,7 +508,14 @@ int launch_step_pair(const void* z, int dtype, long n, int H, int W, const float
   p.z = static_cast<const float*>(z); p.dz = static_cast<float*>(dz); p.target = target; p.mask = mask; p.denom = denom;
   p.g_loss = g_loss; p.coords = coords; p.stats = stats; p.terms = terms; p.n = n; p.flags = flags; p.sigma = sigma;
   p.reg_coeff = reg_coeff;
-  return reg == DSNT_REG_VAR ? launch_pair<DSNT_REG_VAR>(p, stream) : launch_pair<DSNT_REG_NONE>(p, stream);
+  const Geom g = make_geom(H, W, 4, 32, sigma > 0.f ? sigma : 1.f, reg);
+  p.k2 = g.k2; p.r2_win = g.r2_win;
+  switch (reg) {
+    case DSNT_REG_VAR: return launch_pair<DSNT_REG_VAR>(p, stream);
+    case DSNT_REG_JS: return launch_pair<DSNT_REG_JS>(p, stream);
+    case DSNT_REG_MSE: return launch_pair<DSNT_REG_MSE>(p, stream);
+    default: return launch_pair<DSNT_REG_NONE>(p, stream);
+  }
 }
 
 }  // namespace dsnt

@@ -142,11 +142,13 @@ def test_step_support_queries_are_host_logic(libpath):
     # 256x256 fp32: a pair of CTAs, without a Gaussian window
     assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['var']) == 1
     assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['none']) == 1
-    assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['js']) == 0
+    assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['js']) == 1                     # window terms from the registers
+    assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['kl']) == 0
     assert lib.dsnt_head_step_pair_supported(bf16, 256, 256, reg['var']) == 0
     assert lib.dsnt_head_step_pair_supported(f32, 128, 128, reg['var']) == 0
     assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['var']) == 1
-    assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['js']) == 0
+    assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['js']) == 1
+    assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['kl']) == 0
     assert lib.dsnt_head_step_supported_reg(bf16, 256, 256, reg['js']) == 1                      # L2-staged form
     # exchange buffer of the peer reductions: two parities x 16 ranks x float4
     assert lib.dsnt_peer_exchange_bytes() == 2 * 16 * 4 * 8     # two parities x 16 ranks x 4 words of 8 bytes

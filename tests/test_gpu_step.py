@@ -81,8 +81,10 @@ def test_step_is_taken_only_where_supported(dp):
     assert head.step_supported(torch.empty(1, 1, 128, 128, device=DEV, dtype=torch.bfloat16))
     assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV))     # 256 KiB: not in shared memory ...
     assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'var')  # ... but staged through L2 (step_l2.cu)
-    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'js')    # fp32 + Gaussian window: two-kernel
-    assert _lib_pair(256, 256, 'var') and _lib_pair(256, 256, 'none') and not _lib_pair(256, 256, 'js') and not _lib_pair(128, 128, 'var')
+    assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'js')        # fp32 + Gaussian window: the pair kernel too
+    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'kl')    # KL at 256x256: two-kernel path
+    assert _lib_pair(256, 256, 'var') and _lib_pair(256, 256, 'none') and _lib_pair(256, 256, 'js') and _lib_pair(256, 256, 'mse')
+    assert not _lib_pair(256, 256, 'kl') and not _lib_pair(128, 128, 'var')
     assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV, dtype=torch.bfloat16), 'js')
     assert not head.step_supported(torch.empty(1, 1, 7, 7, device=DEV))         # no 16-byte vectors
 
@@ -393,6 +395,8 @@ def test_stacked_single_launch_step_matches_stacked_two_kernel_path_and_oracle(d
 
 
 @pytest.mark.parametrize('shape,dtype,reg', [((3, 16, 256, 256), 'f32', 'var'), ((3, 16, 256, 256), 'f32', 'none'),
+                                             ((3, 16, 256, 256), 'f32', 'js'), ((3, 16, 256, 256), 'f32', 'mse'),
+                                             ((40, 16, 256, 256), 'f32', 'js'),
                                              ((2, 16, 256, 256), 'bf16', 'js'), ((2, 16, 256, 256), 'bf16', 'var'),
                                              ((5, 16, 128, 128), 'f32', 'var'), ((40, 16, 256, 256), 'f32', 'var')])
 def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, dtype, reg):
@@ -428,7 +432,8 @@ def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, 
     assert rel_l2(got['dz'][:n_chk], ref['dz'].numpy() * scale) < (4e-3 if dtype == 'bf16' else TOL)
 
 
-@pytest.mark.parametrize('n,reg,with_mask', [(1, 'var', True), (3, 'none', False), (75, 'var', False), (149, 'none', True)])
+@pytest.mark.parametrize('n,reg,with_mask', [(1, 'var', True), (3, 'none', False), (75, 'var', False), (149, 'none', True),
+                                             (1, 'js', True), (75, 'js', False), (149, 'mse', True)])
 def test_pair_step_edge_counts(dp, tp, n, reg, with_mask):
     """csrc/step_pair.cu with fewer heatmaps than clusters, one more than the clusters (74 on a B200), and an odd count;
     without a mask; peaked logits in one half only (the halves are merged like blocks of an online softmax)."""
