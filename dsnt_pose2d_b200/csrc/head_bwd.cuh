@@ -49,8 +49,8 @@ template <bool LOGITS>
 __device__ __forceinline__ BwdScalars load_bwd_scalars(const HeadBwdParams& p, long hm, long nl, int reg) {
   BwdScalars s;
   const float4* st = reinterpret_cast<const float4*>(p.stats + hm * kStatsK);
-  // L2 loads: a persistent kernel (head_step_l2.cuh) reads the statistics it wrote itself a moment ago, which the
-  // read-only path (ld.global.nc) does not promise to see
+  // L2 loads: a caller may have written the statistics a moment ago in the same stream; the read-only path (ld.global.nc)
+  // is for data that is constant for the lifetime of the kernel only, L2 loads cost the same here
   const float4 s0 = __ldcg(st), s1 = __ldcg(st + 1);
   s.m2 = s0.x; s.invS = LOGITS ? s0.y : 1.0f; s.mux = s0.z; s.muy = s0.w;
   const float vx = s1.x, vy = s1.y, creg = s1.z;

@@ -138,8 +138,8 @@ __device__ __forceinline__ StashWin make_stash_window(const Window& w) {
 // (batch + b, perm[c]) of the same tensor; REG must be NONE then (no target at inference).
 // PA != SOFTMAX: P = f(z)/(sum f + eps) for the reference's other pre-activations.  P may be exactly 0 and sum P may
 // differ from 1 (eps), which the closed forms below carry as sumP / om; stats[7] holds om = 1 - sum P for `var`.
-// The body takes the index of the "block" of heatmaps it works on, so that a persistent kernel can call it in a loop
-// (head_step_l2.cuh); head_fwd_fast_kernel passes blockIdx.x.
+// The body takes the index of the "block" of heatmaps it works on (a persistent caller could loop over it);
+// head_fwd_fast_kernel passes blockIdx.x.
 template <typename T, int VEC, int GROUP, int REG, bool FLIP = false, int PA = DSNT_PREACT_SOFTMAX>
 __device__ __forceinline__ void head_fwd_fast_body(const HeadFwdFastParams& ps, long block_index) {
   static_assert(sizeof(T) * VEC == 16, "fast path = 16-byte vectors");

@@ -9,12 +9,6 @@
 
 namespace dsnt {
 
-// step_l2.cu: the L2-staged one-pass step for heatmaps too large for the shared-memory ring
-bool step_l2_supported(int dtype, int H, int W, int reg);
-int launch_step_l2(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask, const float* denom,
-                   const float* g_loss, float reg_coeff, int reg, float sigma, int flags, float* coords, float* stats,
-                   float* terms, void* dz, cudaStream_t stream);
-
 // step_pair.cu: the one-pass step for 256x256 fp32 heatmaps on a cluster of two CTAs (distributed shared memory)
 bool step_pair_supported(int dtype, int H, int W, int reg);
 int launch_step_pair(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask, const float* denom,
@@ -30,7 +24,6 @@ static int env_int(const char* name, int dflt) {
 static int step_direct_store() { static const int v = env_int("DSNT_TUNE_STEP_STG", 1); return v; }
 static int step_group() { static const int v = env_int("DSNT_TUNE_STEP_GROUP", 32); return v; }
 static int step_warps() { static const int v = env_int("DSNT_TUNE_STEP_WARPS", 0); return v; }
-static bool step_l2_first() { static const int v = env_int("DSNT_TUNE_STEP_L2", 0); return v != 0; }
 static int step_v2() { static const int v = env_int("DSNT_TUNE_STEP_V2", 1); return v; }
 static int step_spare() { static const int v = env_int("DSNT_TUNE_STEP_SPARE", -1); return v; }
 
@@ -242,18 +235,11 @@ static int head_step_impl(const void* z, int dtype, long n, int H, int W, const 
     set_error("per-heatmap buffers must be naturally aligned (coords/terms/target 8 B, stats 16 B)");
     return DSNT_ERR_BAD_ARG;
   }
-  if (!out8 && denom && !dsnt_head_step_supported(dtype, H, W) && aligned(z, 16) && aligned(dz, 16) && !step_l2_first()) {
+  if (!out8 && denom && !dsnt_head_step_supported(dtype, H, W) && aligned(z, 16) && aligned(dz, 16)) {
     // 256x256 fp32: each heatmap in the shared memory of a PAIR of CTAs (thread-block cluster), exchanged through DSMEM
     const int prc = launch_step_pair(z, dtype, n, H, W, target, mask, denom, g_loss, reg_coeff, reg, sigma, flags, coords, stats,
                                      terms, dz, static_cast<cudaStream_t>(stream));
     if (prc != 1) return prc;
-  }
-  if (!out8 && denom && (!dsnt_head_step_supported(dtype, H, W) || step_l2_first()) && aligned(z, 16) && aligned(dz, 16) && stats) {
-    // too large for the shared-memory ring (or DSNT_TUNE_STEP_L2=1): forward and backward of each heatmap back to back in
-    // one persistent kernel, the L2 as the staging buffer
-    const int l2rc = launch_step_l2(z, dtype, n, H, W, target, mask, denom, g_loss, reg_coeff, reg, sigma, flags, coords, stats,
-                                    terms, dz, static_cast<cudaStream_t>(stream));
-    if (l2rc != 1) return l2rc;
   }
   if (!dsnt_head_step_supported(dtype, H, W) || !aligned(z, 16) || !aligned(dz, 16)) {
     set_error("dsnt_head_step: heatmap %dx%d (dtype %d) does not fit the one-pass kernel (needs W %% %d == 0, 16-byte "
@@ -302,11 +288,9 @@ DSNT_API int dsnt_head_step_pair_supported(int dtype, int H, int W, int reg) {
 }
 
 DSNT_API int dsnt_head_step_supported_reg(int dtype, int H, int W, int reg) {
+  if (reg < DSNT_REG_NONE || reg > DSNT_REG_MSE) return 0;
   if (dsnt_head_step_supported(dtype, H, W)) return 1;
-  if (step_pair_supported(dtype, H, W, reg)) return 1;
-  if (dtype != DSNT_DTYPE_F32 && dtype != DSNT_DTYPE_BF16) return 0;
-  if (H <= 0 || W <= 0 || reg < DSNT_REG_NONE || reg > DSNT_REG_MSE) return 0;
-  return step_l2_supported(dtype, H, W, reg) ? 1 : 0;
+  return step_pair_supported(dtype, H, W, reg) ? 1 : 0;
 }
 
 DSNT_API int dsnt_head_step_fused_supported(int dtype, int H, int W, int reg, float sigma) {

@@ -125,12 +125,11 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
  * dsnt_mask_count: out[2] = sum mask (n when mask is NULL), out[3] = max(out[2], 1); workspace as dsnt_finish_loss.
  */
 DSNT_API int dsnt_head_step_supported(int dtype, int H, int W);
-/* ... or, for heatmaps too large for shared memory (256x256 fp32), by the L2-staged form (csrc/step_l2.cu): forward and
- * backward of each heatmap back to back in one persistent kernel, so the second read of the logits hits L2 and HBM
- * still sees 2*H*W*sizeof bytes per heatmap.  Serves every regulariser for bf16, none / var for fp32; needs stats. */
+/* ... for a given regulariser: the shared-memory ring above, or the cluster-of-two-CTAs kernel below (256x256 fp32). */
 DSNT_API int dsnt_head_step_supported_reg(int dtype, int H, int W, int reg);
-/* 256x256 fp32 with no or the variance regulariser (BASELINE config 5) is served by a cluster of two CTAs, each holding
- * half the heatmap in shared memory, partial results exchanged through distributed shared memory (csrc/step_pair.cu). */
+/* 256x256 fp32 (BASELINE config 5) with no, the variance, the JS or the MSE regulariser is served by a cluster of two CTAs,
+ * each holding half the heatmap in shared memory, partial results exchanged through distributed shared memory
+ * (csrc/step_pair.cu); KL at this size keeps the two-kernel path. */
 DSNT_API int dsnt_head_step_pair_supported(int dtype, int H, int W, int reg);
 DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
                             const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,

@@ -32,11 +32,9 @@ def always_take_the_step_kernels(dp):
     """These tests are about the step kernels: small logits must not be routed to the two-kernel path (head._step_pays)."""
     from dsnt_pose2d_b200 import head
     old, head.STEP_MIN_BYTES = head.STEP_MIN_BYTES, 0
-    old_l2, head.USE_L2_STEP = head.USE_L2_STEP, True
     old_pair, head.USE_PAIR_STEP = head.USE_PAIR_STEP, True
     yield
     head.STEP_MIN_BYTES = old
-    head.USE_L2_STEP = old_l2
     head.USE_PAIR_STEP = old_pair
 
 
@@ -80,12 +78,12 @@ def test_step_is_taken_only_where_supported(dp):
     assert head.step_supported(torch.empty(1, 1, 28, 28, device=DEV))
     assert head.step_supported(torch.empty(1, 1, 128, 128, device=DEV, dtype=torch.bfloat16))
     assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV))     # 256 KiB: not in shared memory ...
-    assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'var')  # ... but staged through L2 (step_l2.cu)
+    assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'var')  # ... but in that of a PAIR of CTAs (step_pair.cu)
     assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'js')        # fp32 + Gaussian window: the pair kernel too
     assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'kl')    # KL at 256x256: two-kernel path
     assert _lib_pair(256, 256, 'var') and _lib_pair(256, 256, 'none') and _lib_pair(256, 256, 'js') and _lib_pair(256, 256, 'mse')
     assert not _lib_pair(256, 256, 'kl') and not _lib_pair(128, 128, 'var')
-    assert head.step_supported(torch.empty(1, 1, 256, 256, device=DEV, dtype=torch.bfloat16), 'js')
+    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV, dtype=torch.bfloat16), 'js')   # two-kernel path
     assert not head.step_supported(torch.empty(1, 1, 7, 7, device=DEV))         # no 16-byte vectors
 
 
@@ -396,15 +394,13 @@ def test_stacked_single_launch_step_matches_stacked_two_kernel_path_and_oracle(d
 
 @pytest.mark.parametrize('shape,dtype,reg', [((3, 16, 256, 256), 'f32', 'var'), ((3, 16, 256, 256), 'f32', 'none'),
                                              ((3, 16, 256, 256), 'f32', 'js'), ((3, 16, 256, 256), 'f32', 'mse'),
-                                             ((40, 16, 256, 256), 'f32', 'js'),
-                                             ((2, 16, 256, 256), 'bf16', 'js'), ((2, 16, 256, 256), 'bf16', 'var'),
-                                             ((5, 16, 128, 128), 'f32', 'var'), ((40, 16, 256, 256), 'f32', 'var')])
-def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, dtype, reg):
+                                             ((40, 16, 256, 256), 'f32', 'js'), ((40, 16, 256, 256), 'f32', 'var'),
+                                             ((2, 16, 256, 256), 'bf16', 'js'), ((5, 16, 128, 128), 'f32', 'var')])
+def test_step_for_heatmaps_too_large_for_one_ctas_shared_memory(dp, tp, shape, dtype, reg):
     """Heatmaps of which fewer than four fit in one CTA's shared memory (BASELINE config 5: 256x256 with the variance
-    regulariser).  256x256 fp32 with no / the variance regulariser: csrc/step_pair.cu, a cluster of two CTAs holding half a
-    heatmap each, partial results exchanged through distributed shared memory.  The rest: csrc/step_l2.cu, forward and
-    backward of each heatmap back to back in one persistent kernel -- the same device code as the two-kernel path, so the
-    results agree bit for bit.  Both against the fp64 oracle to the usual tolerance."""
+    regulariser).  256x256 fp32, not KL: csrc/step_pair.cu, a cluster of two CTAs holding half a heatmap each, partial
+    results exchanged through distributed shared memory -- one pass over the logits.  The rest (bf16 at this size,
+    128x128 fp32) silently takes the two-kernel path.  Both against the fp64 oracle to the usual tolerance."""
     from dsnt_pose2d_b200 import _lib
     b, c, h, w = shape
     gen = torch.Generator().manual_seed(91)
@@ -415,10 +411,11 @@ def test_l2_staged_step_for_heatmaps_too_large_for_shared_memory(dp, tp, shape, 
     mask = (torch.rand(b, c, generator=gen) > 0.2).float()
     before = _lib.launch_count
     got = run_step(dp, z, target, mask, reg)
-    assert _lib.launch_count - before == 4          # mask count, step, finishing reduction, scale: not fwd + finish + bwd
+    launches = _lib.launch_count - before
     two = run_step(dp, z, target, mask, reg, one_pass=False)
     pair = bool(_lib.LIB.dsnt_head_step_pair_supported(0 if dtype == 'f32' else 1, h, w, _lib.REG_IDS[reg]))
     assert pair == (dtype == 'f32' and (h, w) == (256, 256))
+    assert launches == (4 if pair else 3)      # mask count, step, finishing reduction, scale  |  fwd, finish, bwd
     if pair:
         assert abs(got['loss'] - two['loss']) < 3e-6 * abs(two['loss'])
         assert float(np.abs(got['coords'] - two['coords']).max()) < 2e-6
