@@ -270,17 +270,32 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
   constexpr unsigned kCountCtas = 16;
   const unsigned nct = gridDim.x < kCountCtas ? gridDim.x : kCountCtas;
   if (!p.denom && p.mask && blockIdx.x < nct) {
-    const long chunk = (nmask + nct - 1) / nct;
+    // 128-bit loads, all of a thread's in flight at once: this is the first touch of the mask by this kernel (cold TLB, HBM),
+    // and every dependent round of loads costs another ~2 us before the count can go out
+    const long chunk = ((nmask + nct - 1) / nct + 3) & ~3L;
     const long lo = blockIdx.x * chunk, hi = lo + chunk < nmask ? lo + chunk : nmask;
-    float s0 = 0.f, s1 = 0.f, s2m = 0.f, s3 = 0.f;
     const long bd = blockDim.x;
+    float s0 = 0.f, s1 = 0.f;
     long i = lo + threadIdx.x;
-    for (; i + 3 * bd < hi; i += 4 * bd) {          // four independent loads in flight
-      const float v0 = __ldg(p.mask + i), v1 = __ldg(p.mask + i + bd), v2 = __ldg(p.mask + i + 2 * bd), v3 = __ldg(p.mask + i + 3 * bd);
-      s0 += v0; s1 += v1; s2m += v2; s3 += v3;
+    if ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0 && hi > lo) {
+      const float4* m4 = reinterpret_cast<const float4*>(p.mask + lo);
+      const long n4 = (hi - lo) >> 2;
+      float4 v[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const long idx = threadIdx.x + k * bd;
+        v[k] = idx < n4 ? __ldg(m4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { s0 += v[k].x + v[k].y; s1 += v[k].z + v[k].w; }
+      for (long idx = threadIdx.x + 3 * bd; idx < n4; idx += bd) {
+        const float4 w = __ldg(m4 + idx);
+        s0 += w.x + w.y; s1 += w.z + w.w;
+      }
+      i = lo + 4 * n4 + threadIdx.x;
     }
     for (; i < hi; i += bd) s0 += __ldg(p.mask + i);
-    const float sm = warp_sum((s0 + s1) + (s2m + s3));
+    const float sm = warp_sum(s0 + s1);
     if (lane == 0) fin_mask[warp] = sm;
   }
   __syncthreads();           // barriers initialised, issued[] and pace_next set, mask partials in fin[]

@@ -120,9 +120,6 @@ static int launch_step2_slots(const HeadStepParams& p, cudaStream_t stream) {
     }
     return launch_step2_nw<T, REG, H, W, 16, true, MAXS>(p, stream);
   } else {
-    if constexpr (REG == DSNT_REG_KL) {                // fp32 KL: the window walk is latency-bound with 3 warps per scheduler
-      if (nwmax != 12) return launch_step2_nw<T, REG, H, W, 14, true, MAXS>(p, stream);
-    }
     return launch_step2_nw<T, REG, H, W, 12, true, MAXS>(p, stream);
   }
 }
