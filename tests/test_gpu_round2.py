@@ -359,3 +359,16 @@ def test_pair_kernel_gaussian_window_at_256(dp, reg, kind):
     print('pair %s %s: loss %.1e reg %.1e dz %.1e' % (reg, kind, e_loss, e_reg, e_dz))
     assert (out.coords.detach().cpu().double() - ref['coords']).abs().max().item() < TOL
     assert e_loss < TOL and e_reg < TOL and e_dz < TOL
+
+
+def test_reordered_visible_devices():
+    """CUDA_VISIBLE_DEVICES reordered: device 0 of the process is another physical GPU; the per-device launch
+    caches and the cooperative launch must not care.  Runs the smoke check in a subprocess."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two devices')
+    env = dict(os.environ)
+    env['CUDA_VISIBLE_DEVICES'] = '1,0'
+    r = subprocess.run([sys.executable, '-c', 'import sys; sys.path.insert(0, %r); import __graft_entry__ as g; g.smoke()' % ROOT],
+                       env=env, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-1500:], r.stderr[-1500:])
+    assert r.returncode == 0 and 'one-pass step' in r.stdout
