@@ -372,3 +372,37 @@ def test_reordered_visible_devices():
                        env=env, capture_output=True, text=True, timeout=600)
     print(r.stdout[-1500:], r.stderr[-1500:])
     assert r.returncode == 0 and 'one-pass step' in r.stdout
+
+
+@pytest.mark.parametrize('n', [1, 3, 17, 149])
+@pytest.mark.parametrize('mask_kind', ['binary', 'weights', 'misaligned', 'none'])
+def test_single_launch_count_paths(dp, n, mask_kind):
+    """The mask count inside the single-launch step: fewer heatmaps than counting CTAs (16), one more than the SM count,
+    fractional weights, a mask whose base is not 16-byte aligned (scalar loads instead of 128-bit ones), no mask at all."""
+    from oracle import torch_port as tp
+    from dsnt_pose2d_b200 import _lib
+    gen = torch.Generator().manual_seed(7 + n)
+    z = torch.randn(n, 1, 64, 64, generator=gen)
+    target = torch.rand(n, 1, 2, generator=gen) * 1.6 - 0.8
+    if mask_kind == 'none':
+        mask, mask_dev = None, None
+    else:
+        mask = (torch.rand(n, 1, generator=gen) > 0.3).float()
+        mask[0] = 1.0
+        if mask_kind == 'weights':
+            mask = mask * (0.25 + torch.rand(n, 1, generator=gen))
+        if mask_kind == 'misaligned':
+            big = torch.zeros(n + 3, device=DEV)
+            big[1:n + 1] = mask.view(-1).to(DEV)
+            mask_dev = big[1:n + 1].view(n, 1)
+            assert mask_dev.data_ptr() % 16 != 0 and mask_dev.is_contiguous()
+        else:
+            mask_dev = mask.to(DEV)
+    zz = z.to(DEV).requires_grad_(True)
+    before = _lib.launch_count
+    out = dp.dsnt_head(zz, target.to(DEV), mask_dev, reg='js', hm_sigma=1.0, one_pass=True)
+    assert _lib.launch_count - before == 1
+    out.loss.backward()
+    ref = tp.head_loss_and_grad(z, target, mask, 'js', 1.0, 1.0, dtype=torch.float64)
+    assert abs(out.loss.item() - ref['loss'].item()) / ref['loss'].item() < TOL
+    assert rel_l2(zz.grad.cpu().double().numpy(), ref['dz'].numpy()) < TOL
