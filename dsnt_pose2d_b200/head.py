@@ -628,7 +628,7 @@ def dsnt_head_stacked(zs, target, mask=None, reg='none', sigma=None, reg_coeff=1
 
     zs: list of logits tensors [..., H, W] of identical shape/dtype (one per stack, as hourglass.py:166-177 returns).
     one_pass: a training step (only d(loss) flows back): one launch writes every stack's dL/dz while its heatmaps are on
-    chip (64x64 heatmaps, not KL, single process; other cases take the forward / backward launches as before).
+    chip (64x64 heatmaps, single process; other cases take the forward / backward launches as before).
     Returns (list of coords per stack, total loss = sum_s euclid_s + reg_coeff * reg_s)."""
     zs = list(zs)
     if not zs:
