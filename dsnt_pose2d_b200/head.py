@@ -33,16 +33,17 @@ class HeadOutput:
     __slots__ = ('coords', 'loss', '_out8')
     _fields = ('coords', 'loss', 'euclid', 'reg')
 
-    def __init__(self, coords, loss, out8):
-        self.coords, self.loss, self._out8 = coords, loss, out8
+    def __init__(self, coords, loss, out8, off=0):
+        # out8: a float32 tensor holding the loss block [sum m*d, sum m*D, count, denom, euclid, reg, loss, 0] at offset `off`
+        self.coords, self.loss, self._out8 = coords, loss, (out8, off)
 
     @property
     def euclid(self):
-        return self._out8[4]
+        return self._out8[0][self._out8[1] + 4]
 
     @property
     def reg(self):
-        return self._out8[5]
+        return self._out8[0][self._out8[1] + 5]
 
     def __iter__(self):
         return iter((self.coords, self.loss, self.euclid, self.reg))
@@ -291,8 +292,7 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
     if (one_pass and preact == 'softmax' and threshold is None and eps is None and input_is_logits
             and z.requires_grad and torch.is_grad_enabled()
             and takes_one_pass(z, reg, float(sigma), _is_sharded(group))):
-        coords, loss = _FusedHeadStep.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
-                                            flags, group, aux)
+        coords, loss = _FusedHeadStep.apply(z, target, mask, (_lib.REG_IDS[reg], float(sigma), float(reg_coeff), flags, group, aux))
     elif preact == 'softmax' and threshold is None and eps is None:
         coords, loss = _FusedHead.apply(z, target, mask, _lib.REG_IDS[reg], float(sigma), float(reg_coeff),
                                         flags, group, int(variant), bool(input_is_logits), aux)
@@ -304,7 +304,7 @@ def dsnt_head(z, target, mask=None, reg='none', sigma=None, reg_coeff=1.0, hm_si
                                               flags, group, _lib.PREACT_IDS[preact],
                                               float(d_thr if threshold is None else threshold),
                                               float(d_eps if eps is None else eps), int(variant), aux)
-    return HeadOutput(coords, loss, aux['out8'])
+    return HeadOutput(coords, loss, aux['out8'], aux.get('off', 0))
 
 
 def _head_with_target_grad(z, target, mask, reg, sigma, reg_coeff, preact, threshold, eps, input_is_logits, group):
@@ -428,12 +428,15 @@ class _FusedHeadStep(torch.autograd.Function):
     through the regular backward kernel on the saved statistics, into a fresh tensor."""
 
     @staticmethod
-    def forward(ctx, z, target, mask, reg_id, sigma, reg_coeff, flags, group, aux):
+    def forward(ctx, z, target, mask, cfg):
+        reg_id, sigma, reg_coeff, flags, group, aux = cfg      # one argument: Function.apply walks every one of them
         zc, n, h, w = _flat_heatmaps(z)
         dev = zc.device
         with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
             ar = _StepArena(n, dev)
+            coords = torch.empty(z.shape[:-2] + (2,), dtype=torch.float32, device=dev)     # in its final shape: no views
+            coords_ptr = coords.data_ptr()
             dz = torch.empty_like(zc)
             ws = _lib.finish_workspace(dev, stream)
             dt = _lib.dtype_id(zc)
@@ -443,28 +446,29 @@ class _FusedHeadStep(torch.autograd.Function):
             if sharded and peer is not None and fused:
                 # one launch per rank: mask count and loss sums cross the ranks inside the kernel (peer memory)
                 _lib.call('dsnt_head_step_fused_peer', zc.data_ptr(), dt, n, h, w, _lib.ptr(target),
-                          _lib.ptr(mask), None, reg_coeff, reg_id, sigma, flags, ar.coords_ptr, ar.stats_ptr,
+                          _lib.ptr(mask), None, reg_coeff, reg_id, sigma, flags, coords_ptr, ar.stats_ptr,
                           dz.data_ptr(), ar.out8_ptr, ws.data_ptr(), *peer.args(), stream)
             elif not sharded and fused:
                 # one launch: the kernel adds up the mask itself and its last CTA composes the loss
                 _lib.call('dsnt_head_step_fused', zc.data_ptr(), dt, n, h, w, _lib.ptr(target), _lib.ptr(mask),
-                          None, reg_coeff, reg_id, sigma, flags, ar.coords_ptr, ar.stats_ptr, dz.data_ptr(),
+                          None, reg_coeff, reg_id, sigma, flags, coords_ptr, ar.stats_ptr, dz.data_ptr(),
                           ar.out8_ptr, ws.data_ptr(), stream)
             else:
                 # the denominator of masked_average depends on the mask alone: known before the forward.  A rank whose
                 # shard is empty (or that the single-launch kernel does not serve) meets the others in the same two exchanges.
                 finish_loss_ptr(None, mask, n, 1, reg_coeff, ar.cnt8_ptr, ar.buf, ws, group, dev, stream)
                 _lib.call('dsnt_head_step', zc.data_ptr(), dt, n, h, w, _lib.ptr(target), _lib.ptr(mask),
-                          ar.cnt8_ptr + 12, None, reg_coeff, reg_id, sigma, flags, ar.coords_ptr, ar.stats_ptr,
+                          ar.cnt8_ptr + 12, None, reg_coeff, reg_id, sigma, flags, coords_ptr, ar.stats_ptr,
                           ar.terms_ptr, dz.data_ptr(), stream)
                 finish_loss_ptr(ar.terms_ptr, mask, n, 1, reg_coeff, ar.out8_ptr, ar.buf, ws, group, dev, stream)
         ctx.save_for_backward(zc, target, mask, ar.buf)
         ctx.dz_box = [dz]          # NOT a saved tensor: handed out once, then gone (see the class docstring)
         ctx.meta = (n, h, w, reg_id, sigma, reg_coeff, flags, z.shape)
         ctx.set_materialize_grads(False)
-        aux['out8'] = ar.out8()
+        aux['out8'] = ar.buf       # the loss block sits at float offset 12 n of the arena
+        aux['off'] = 12 * n
         aux['dz'] = dz
-        return ar.coords().view(*z.shape[:-2], 2), aux['out8'][6]
+        return coords, ar.buf[12 * n + 6]
 
     @staticmethod
     def backward(ctx, g_coords, g_loss):
@@ -472,7 +476,7 @@ class _FusedHeadStep(torch.autograd.Function):
         n, h, w, reg_id, sigma, reg_coeff, flags, shape = ctx.meta
         dev = zc.device
         if g_coords is None and g_loss is None:
-            return (None,) * 9
+            return (None,) * 4
         with _lib.on_device(dev):
             stream = _lib.stream_of(zc)
             if g_loss is not None and (g_loss.dtype is not torch.float32 or not g_loss.is_contiguous()):
@@ -482,7 +486,7 @@ class _FusedHeadStep(torch.autograd.Function):
                 # the usual case (train.py:381): the gradient is already there
                 ctx.dz_box[0] = None
                 _lib.call('dsnt_scale_unless_one', dz.data_ptr(), _lib.dtype_id(dz), dz.numel(), g_loss.data_ptr(), stream)
-                return (dz.view(shape),) + (None,) * 8
+                return (dz if dz.shape == shape else dz.view(shape)), None, None, None
             if g_coords is not None:
                 g_coords = g_coords.to(torch.float32).contiguous()
             full = torch.empty_like(zc)
@@ -491,7 +495,7 @@ class _FusedHeadStep(torch.autograd.Function):
                       _lib.ptr(target), _lib.ptr(mask), base, _lib.ptr(g_coords), None,
                       _lib.ptr(g_loss), base + 48 * n + 12 if g_loss is not None else None,
                       reg_coeff, reg_id, sigma, flags, full.data_ptr(), 0, stream)
-        return (full.view(shape),) + (None,) * 8
+        return full.view(shape), None, None, None
 
 
 class _FusedHeadStacked(torch.autograd.Function):
