@@ -31,8 +31,7 @@ __device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& 
 __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* __restrict__ terms,
                                                                   const float* __restrict__ mask, long n, long n_per,
                                                                   float reg_coeff, float* __restrict__ out,
-                                                                  float* __restrict__ workspace, const PeerXchg xc,
-                                                                  const int count_only = 0) {
+                                                                  float* __restrict__ workspace, const PeerXchg xc) {
   __shared__ float red[4 * kFinishBlock / 32];
   __shared__ bool is_last;
   const long chunk = (n + gridDim.x - 1) / gridDim.x;
@@ -73,19 +72,7 @@ __global__ void __launch_bounds__(kFinishBlock) finish_loss_kernel(const float* 
       a += v[k].x; b += v[k].y; c += v[k].z;
     }
     a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-    if (xc.world > 1) {                                   // sharded batch: totals over the ranks
-      if (!count_only) {          // (NOT "terms == nullptr": an empty shard has no terms either, and must still exchange its sums)
-        peer_exchange_sum3(xc, a, b, c);
-      } else {
-        // mask count only: the count exchange (so that this rank meets ranks whose single-launch step posts per CTA)
-        const unsigned e = peer_next_epoch(xc);
-        const float mine = __shfl_sync(kFull, c, 0);
-        for (int slot = 0; slot < kCountSlots; ++slot) peer_post_count(xc, e, slot, slot == 0 ? mine : 0.f);
-        float local;
-        c = peer_collect_count(xc, e, local);
-        a = 0.f; b = 0.f;
-      }
-    }
+    if (xc.world > 1) peer_exchange_sum3(xc, a, b, c);   // sharded batch: totals over the ranks
     if (threadIdx.x == 0) {
       out[0] = a; out[1] = b; out[2] = c;
       write_loss_tail(out, reg_coeff);

@@ -201,7 +201,7 @@ DSNT_API int dsnt_mask_count_peer(const float* mask, long n, float* out, float* 
   if (ctas < 1) ctas = 1;
   if (ctas > kFinishMaxCtas) ctas = kFinishMaxCtas;
   finish_loss_kernel<<<static_cast<unsigned>(ctas), kFinishBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, mask, n, n > 0 ? n : 1, 0.f, out, workspace, xc, 1);
+      nullptr, mask, n, n > 0 ? n : 1, 0.f, out, workspace, xc);
   return check_launch("finish_loss_kernel<count, peer>");
 }
 

@@ -52,13 +52,7 @@ __device__ __forceinline__ void write_loss_tail(float* out, float reg_coeff) {
 // before everybody has read it.
 constexpr int kMaxRanks = DSNT_MAX_RANKS;
 constexpr int kPeerWordsPerSlot = 4;                                     // 3 used, padded to 32 bytes
-constexpr int kPeerSumWords = 2 * kMaxRanks * kPeerWordsPerSlot;         // the three-sum exchange: two parities
-// The mask COUNT has an exchange of its own (peer_post_count / peer_collect_count below): every rank posts up to kCountSlots
-// partial counts, so that the CTAs that add up the mask inside the single-launch step can post theirs to the peers DIRECTLY --
-// no local ticket round before the count can leave the GPU -- and whoever collects adds everything in one fixed order.
-constexpr int kCountSlots = 16;
-constexpr int kPeerCountWords = 2 * kMaxRanks * kCountSlots;             // two parities x ranks x slots
-constexpr int kPeerExchangeBytes = (kPeerSumWords + kPeerCountWords) * 8;
+constexpr int kPeerExchangeBytes = 2 * kMaxRanks * kPeerWordsPerSlot * 8;   // two parities
 struct PeerXchg {
   unsigned long long* peers[kMaxRanks];   // peers[r]: rank r's exchange buffer (kPeerExchangeBytes, zero before first use)
   unsigned* epoch;            // local device counter of exchanges done so far (zero before first use)
@@ -73,63 +67,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// ---- the count exchange.  Epoch e = (exchanges done so far) + 1, read by every poster itself (the counter was last written
-// by the previous exchange of this rank, long ago); the collector advances it.
-__device__ __forceinline__ unsigned peer_next_epoch(const PeerXchg& x) {
-  unsigned e = __ldcg(x.epoch) + 1u;
-  return e == 0u ? 1u : e;
-}
-// Lanes r < world of the calling warp store partial count `v` (slot `slot` of THIS rank) into rank r's buffer.
-__device__ __forceinline__ void peer_post_count(const PeerXchg& x, unsigned e, int slot, float v) {
-  const int lane = threadIdx.x & 31;
-  if (lane < x.world)
-    st_relaxed_sys_u64(x.peers[lane] + kPeerSumWords + (e & 1u) * (kMaxRanks * kCountSlots) + x.rank * kCountSlots + slot,
-                       (static_cast<unsigned long long>(e) << 32) | __float_as_uint(v));
-}
-// ONE full warp: waits for the kCountSlots partials of every rank in its own buffer and adds them -- each rank's partials by
-// the same shuffle tree, the ranks in rank order: bit-identical on every rank.  Returns the count over all ranks on every
-// lane, `local` = this rank's; advances the epoch.
-__device__ __forceinline__ float peer_collect_count(const PeerXchg& x, unsigned e, float& local) {
-  const int lane = threadIdx.x & 31;
-  const unsigned long long* base = x.peers[x.rank] + kPeerSumWords + (e & 1u) * (kMaxRanks * kCountSlots);
-  const int nwords = x.world * kCountSlots;                  // word w = rank * 16 + slot, held by lane w % 32 in got[w / 32]
-  constexpr int kRounds = kMaxRanks * kCountSlots / 32;
-  float got[kRounds];
-  const unsigned long long t0 = global_timer_ns();
-#pragma unroll
-  for (int k = 0; k < kRounds; ++k) {
-    const int w = lane + 32 * k;
-    got[k] = 0.f;
-    if (w < nwords) {
-      unsigned long long word = ld_relaxed_sys_u64(base + w);
-      while (static_cast<unsigned>(word >> 32) != e) {
-        if (global_timer_ns() - t0 > 20000000000ull) {    // 20 s: a rank is gone; do not hang the GPU
-          word = 0x7fc00000ull;
-          *x.error = 1;
-          break;
-        }
-        word = ld_relaxed_sys_u64(base + w);
-      }
-      got[k] = __uint_as_float(static_cast<unsigned>(word));
-    }
-  }
-  float total = 0.f;
-  local = 0.f;
-#pragma unroll
-  for (int k = 0; k < kRounds; ++k) {                      // got[k]: ranks 2k (lanes 0-15) and 2k + 1 (lanes 16-31)
-    float s = got[k];
-    s += __shfl_xor_sync(kFull, s, 8);
-    s += __shfl_xor_sync(kFull, s, 4);
-    s += __shfl_xor_sync(kFull, s, 2);
-    s += __shfl_xor_sync(kFull, s, 1);
-    const float r_even = __shfl_sync(kFull, s, 0), r_odd = __shfl_sync(kFull, s, 16);
-    if (2 * k < x.world) { total += r_even; if (2 * k == x.rank) local = r_even; }
-    if (2 * k + 1 < x.world) { total += r_odd; if (2 * k + 1 == x.rank) local = r_odd; }
-  }
-  if (lane == 0) { __stcg(x.epoch, e); __threadfence(); }
-  return total;
-}
-
 // Called by ONE full warp of one CTA; (a, b, c) are valid on lane 0; returns the totals on every lane.
 __device__ __forceinline__ void peer_exchange_sum3(const PeerXchg& x, float& a, float& b, float& c) {
   const int lane = threadIdx.x & 31;

@@ -299,28 +299,9 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     if (lane == 0) fin_mask[warp] = sm;
   }
   __syncthreads();           // barriers initialised, issued[] and pace_next set, mask partials in fin[]
-  unsigned count_epoch = 0u;                 // sharded: the epoch of this step's count exchange
   if (!p.denom) {
     if (blockIdx.x == 0 && threadIdx.x == 0) trace[0] = global_timer_ns();
-    if (warp == 0 && sharded) {
-      // Sharded batch: every counting CTA posts ITS partial straight into every rank's exchange buffer (no local ticket round
-      // before the count can leave the GPU); CTA 0 also fills the slots nobody owns.  Warp 0 of CTA 0 collects -- not here:
-      // when it needs the count itself (need_count), so that it starts its first heatmap like every other warp.
-      count_epoch = __shfl_sync(kFull, lane == 0 ? peer_next_epoch(p.xc) : 0u, 0);
-      if (p.mask) {
-        if (blockIdx.x < nct) {
-          float t2 = 0.f;
-          for (int w2 = 0; w2 < p.nwarps; ++w2) t2 += fin_mask[w2];
-          peer_post_count(p.xc, count_epoch, static_cast<int>(blockIdx.x), t2);
-        }
-        if (blockIdx.x == 0)
-          for (int slot = static_cast<int>(nct); slot < kCountSlots; ++slot) peer_post_count(p.xc, count_epoch, slot, 0.f);
-      } else if (blockIdx.x == 0) {                              // no mask: every heatmap counts
-        for (int slot = 0; slot < kCountSlots; ++slot)
-          peer_post_count(p.xc, count_epoch, slot, slot == 0 ? static_cast<float>(nmask) : 0.f);
-      }
-      if (blockIdx.x == 0 && lane == 0) trace[1] = global_timer_ns();
-    } else if (warp == 0) {
+    if (warp == 0) {
       bool publish = blockIdx.x == 0;                            // no mask: every heatmap counts, CTA 0 says so
       float tot = static_cast<float>(nmask);
       if (p.mask) {
@@ -336,44 +317,37 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
         publish = __shfl_sync(kFull, last, 0) != 0u;
         if (publish) {
           __threadfence();
-          static_assert(kCountCtas <= 32 && kCountCtas <= kCountSlots, "one partial per lane");
+          static_assert(kCountCtas <= 32, "one partial per lane");
           tot = lane < static_cast<int>(nct) ? __ldcg(mpart + lane) : 0.f;
           tot = warp_sum(tot);
         }
       }
-      if (publish && lane == 0) {
-        __stcg(p.ws + kFinishLocal, tot);
-        trace[1] = global_timer_ns();
-        __stcg(reinterpret_cast<float*>(ctl + 3), tot);
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctl + 2), "r"(1u) : "memory");
-        trace[2] = global_timer_ns();
+      if (publish) {
+        if (lane == 0) { __stcg(p.ws + kFinishLocal, tot); trace[1] = global_timer_ns(); }
+        if (sharded) {
+          // the count over ALL ranks.  Slot layout as in finish_loss_kernel (sum mask*dist, sum mask*D, sum mask), so that a
+          // rank on the three-launch form (an empty shard) meets the others in the same exchanges.
+          float z0 = 0.f, z1 = 0.f;
+          peer_exchange_sum3(p.xc, z0, z1, tot);
+        }
+        if (lane == 0) {
+          __stcg(reinterpret_cast<float*>(ctl + 3), tot);
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctl + 2), "r"(1u) : "memory");
+          trace[2] = global_timer_ns();
+        }
       }
     }
   }
-  // the count, when a warp first needs it (lane 0 polls the flag in L2; it is long there in the steady case).  Sharded: warp 0
-  // of CTA 0 is the one that collects the ranks' partials and publishes the total -- while it would otherwise wait like the rest.
+  // the count, when a warp first needs it (lane 0 polls the flag in L2; it is long there in the steady case)
   auto need_count = [&]() {
     if (have_count) return;
     float tot = 0.f;
-    if (sharded && blockIdx.x == 0 && warp == 0) {
-      float local;
-      tot = peer_collect_count(p.xc, count_epoch, local);
-      if (lane == 0) {
-        __stcg(p.ws + kFinishLocal, local);
-        __stcg(reinterpret_cast<float*>(ctl + 3), tot);
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctl + 2), "r"(1u) : "memory");
-        trace[2] = global_timer_ns();
-      }
-    } else {
-      if (lane == 0) {
-        while (ld_acquire_gpu(ctl + 2) == 0u) __nanosleep(100);
-        tot = __ldcg(reinterpret_cast<const float*>(ctl + 3));
-      }
-      tot = __shfl_sync(kFull, tot, 0);
+    if (lane == 0) {
+      while (ld_acquire_gpu(ctl + 2) == 0u) __nanosleep(100);
+      tot = __ldcg(reinterpret_cast<const float*>(ctl + 3));
     }
-    mask_count = tot;
+    mask_count = __shfl_sync(kFull, tot, 0);
     have_count = true;
   };
   if (p.stagger_ns > 0) __nanosleep(static_cast<unsigned>(warp * p.stagger_ns + (blockIdx.x & 3) * (p.stagger_ns >> 2)));
@@ -872,7 +846,6 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     __syncwarp();
   }
   flush_pending(true);
-  if (!p.denom && sharded && blockIdx.x == 0 && warp == 0) need_count();      // the collector must collect even without a heatmap
 
   // ---------------------------------------------------------------- single-launch form: masked_average + loss composition
   // (src/dsnt/nn.py:81-94, src/dsnt/model.py:145) as in finish_loss_kernel: warp order inside the CTA, the CTA with the last

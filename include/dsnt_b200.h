@@ -246,9 +246,7 @@ DSNT_API int dsnt_finish_loss(const float* terms, const float* mask, long n, flo
  * the ranks fused into the kernel -- no NCCL launch, no separate combine.  The last CTA stores (out[0], out[1], out[2])
  * into every rank's exchange buffer over NVLink peer mappings (each value as one 64-bit word {float, epoch}: no fence, no
  * flag), waits for all ranks' words in its own buffer and adds them in rank order, so every rank finishes with the same
- * out[0..7] as one process on the whole batch would.  The mask COUNT (dsnt_mask_count_peer, and the count inside
- * dsnt_head_step_fused_peer) has an exchange area of its own in the same buffer, 16 partial counts per rank: the CTAs that add
- * up the mask inside the single-launch step post theirs to the peers directly.
+ * out[0..7] as one process on the whole batch would.
  *   replaces: nothing in the reference (single GPU, src/dsnt/bin/train.py:220); it is what makes masked_average
  *             (src/dsnt/nn.py:81-94) mean "over the global batch" when the batch dimension is sharded.
  *   peers     HOST array of `world` DEVICE pointers; peers[r] is rank r's exchange buffer as mapped into this process
