@@ -1,23 +1,30 @@
-// step_pair.cu -- the one-pass training step for 256x256 fp32 heatmaps (BASELINE config 5) on a PAIR of SMs.
+// step_pair.cu -- the one-pass training step for 256x256 heatmaps (BASELINE config 5) on a CLUSTER of SMs.
 //
 // A 256x256 fp32 heatmap is 256 KiB: more than the 227 KiB of shared memory one CTA can have, which is why config 5 ran the
-// two-kernel path at 12 bytes per pixel.  A thread-block CLUSTER of two CTAs has 2 x 227 KiB: each CTA of the pair takes
-// one half of the heatmap (128 rows, 128 KiB, TMA bulk loads into its own shared memory), reads it ONCE into the registers
-// of its 1024 threads (32 per thread) taking the maximum on the way, turns it into e = 2^(z log2e - max) there, and writes
-// the gradient from there; the pair exchanges its per-half partial results through DISTRIBUTED SHARED MEMORY (each CTA
-// stores into the other's shared memory, both merge in rank order, so both hold bit-identical totals).  HBM sees every
-// logit once: 8 bytes per pixel; shared memory is written once (by the TMA) and read once per heatmap.
+// two-kernel path at 12 bytes per pixel.  A thread-block CLUSTER of CS CTAs (CS = 2 or 4) has CS x 227 KiB: each CTA takes
+// 256 / CS rows of the heatmap (TMA bulk loads into its own shared memory), reads them ONCE into the registers of its
+// 2048 / CS threads (32 pixels per thread) taking the maximum on the way, turns them into e = 2^(z log2e - max) there, and
+// writes the gradient from there; the CTAs exchange their partial results through DISTRIBUTED SHARED MEMORY (each CTA stores
+// into the shared memory of the others, all merge in rank order, so all hold bit-identical totals).  HBM sees every logit
+// once: 8 bytes per pixel (4 for bf16); shared memory is written once (by the TMA) and read once per heatmap.
 //
-// The shared memory of a CTA is a ring of seven 32 KiB chunk buffers; a half heatmap takes four, so while heatmap k is
-// being processed three chunks of heatmap k+1 are already loading, and as soon as k has been read into registers its four
-// buffers take the last chunk of k+1 and the first three of k+2: the loads of the next heatmaps overlap all the arithmetic.
+//   CS = 2: 1024 threads, one CTA per SM: a heatmap per pair of SMs (round 1).
+//   CS = 4:  512 threads, TWO CTAs per SM: four SMs hold two heatmaps in flight, so while one heatmap sits in its
+//            reduction / exchange / window phase (latency, nothing issued) the other CTA of the SM sweeps.  The register
+//            file holds the same number of heatmaps as before (one per two SMs); the phases interleave.
+//
+// The shared memory of a CTA is a ring of NS chunk buffers; a part of a heatmap takes NCH of them (NS > NCH), so while
+// heatmap k is being processed NS - NCH chunks of heatmap k+1 (and k+2) are already loading, and as soon as k has been read
+// into registers its buffers take the next NCH chunks of the stream: the loads of the next heatmaps overlap all the arithmetic.
 //
 // Same mathematics as head_step2.cuh (src/dsnt/nn.py:25-116,274-298, src/dsnt/model.py:24-63,145):
-// column accumulators + one row sum per sweep step give S, S_x, S_y and the variance about the mean without a second look;
-// packed fp32 pairs (FFMA2 / FADD2 / FMUL2).  Regularisers: none and variance (what config 5 uses); the others keep the
-// two-kernel path.  The denominator of masked_average is an input, as for dsnt_head_step.
+// column accumulators + one row sum per sweep step give S, S_x, S_y and the variance about a pivot without a second look;
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2).  Regularisers: none, variance, JS and MSE (KL keeps the two-kernel path).
+// bf16 heatmaps: e stays fp32 in the registers between the sweeps (no fp16 stash as in the 64x64 kernel).  The
+// denominator of masked_average is an input, as for dsnt_head_step.
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "capi_util.cuh"
@@ -29,20 +36,32 @@ namespace cg = cooperative_groups;
 namespace dsnt {
 
 constexpr int kPairH = 256, kPairW = 256;
-constexpr int kPairThreads = 1024;
-constexpr int kPairHalfRows = kPairH / 2;                       // rows per CTA
-constexpr int kPairHalfBytes = kPairHalfRows * kPairW * 4;      // 128 KiB
-constexpr int kPairWV = kPairW / 4;                             // 64 vectors per row
-constexpr int kPairRowsPerStep = kPairThreads / kPairWV;        // 16 rows per sweep step
-constexpr int kPairIters = kPairHalfRows / kPairRowsPerStep;    // 8 sweep steps
-constexpr int kPairChunks = 4;                                  // a half heatmap = 4 chunks of 32 KiB
-constexpr int kPairChunkBytes = kPairHalfBytes / kPairChunks;   // 32 KiB = two sweep steps
-constexpr int kPairSlots = 7;                                   // ring of chunk buffers: 224 KiB of the 227 KiB a CTA may have
-constexpr int kPairSmemBytes = kPairSlots * kPairChunkBytes;
+constexpr int kPairWV = kPairW / 4;                             // 64 vectors of four pixels per row
+constexpr int kPairIters = 8;                                   // sweep steps per heatmap part: 32 pixels per thread
+
+template <int CS, typename T>
+struct PairCfg {
+  static constexpr int ES = sizeof(T);
+  static constexpr int NT = 2048 / CS;                          // threads per CTA
+  static constexpr int NW = NT / 32;
+  static constexpr int ROWS = kPairH / CS;                      // rows per CTA
+  static constexpr int RPS = NT / kPairWV;                      // rows per sweep step
+  static constexpr int STEP_BYTES = RPS * kPairW * ES;          // bytes one sweep step reads
+  static constexpr int PART_BYTES = ROWS * kPairW * ES;
+  static constexpr int NCH = CS == 2 ? 4 : 8;                   // chunks per part
+  static constexpr int IPC = kPairIters / NCH;                  // sweep steps per chunk
+  static constexpr int CHUNK = PART_BYTES / NCH;
+  // ring slots: fp32 CS=2: 7 x 32 KiB = 224 KiB (one CTA per SM); fp32 CS=4: 13 x 8 KiB = 104 KiB (two per SM);
+  // bf16 CS=2: 13 x 16 KiB = 208 KiB; bf16 CS=4: 24 x 4 KiB = 96 KiB (two per SM)
+  static constexpr int NS = CS == 2 ? (ES == 4 ? 7 : 13) : (ES == 4 ? 13 : 24);
+  static constexpr int SMEM = NS * CHUNK;
+  static constexpr int CTAS_PER_SM = CS == 2 ? 1 : 2;
+  static_assert(ROWS % RPS == 0 && ROWS / RPS == kPairIters && kPairIters % NCH == 0 && NS > NCH, "geometry");
+};
 
 struct PairParams {
-  const float* z;
-  float* dz;
+  const void* z;
+  void* dz;
   const float* target;
   const float* mask;
   const float* denom;
@@ -54,17 +73,21 @@ struct PairParams {
   int flags;
   float sigma, reg_coeff;
   float k2, r2_win;       // Gaussian window (JS / MSE): -0.5 / sigma^2 * log2(e) and the window radius^2 (head_stream.cuh: make_geom)
+  int tune;               // DSNT_TUNE_STEP_PAIR_FLAGS (measurements only): 1 = thread 0 issues all loads, 2 = block barrier after
+                          // the maximum, 4 = block barrier after every block sum
 };
 
-// sum over the 1024 threads of one CTA of up to four values, identical on every thread, fixed order
+// sum over the threads of one CTA of up to four values, identical on every thread, fixed order.  `red` has 32 rows; the
+// rows of warps that do not exist stay zero (cleared once at kernel start), so 16 warps reduce like 32.  ONE block
+// barrier: the caller alternates between two `red` arrays, see the kernel.
 __device__ __forceinline__ void pair_block_sum4(float& a, float& b, float& c, float& d, float (*red)[8], int warp, int lane) {
   const float k = warp_sum4_transposed(a, b, c, d, lane);
   if ((lane & 7) == 0) red[warp][lane >> 3] = k;
   __syncthreads();
-  // 32 warps = 32 lanes: every warp adds the per-warp partials with the same butterfly
-  const float k2 = warp_sum4_transposed(red[lane][0], red[lane][1], red[lane][2], red[lane][3], lane);
+  // (up to) 32 warps = 32 lanes: every warp adds the per-warp partials with the same butterfly
+  const float4 r = *reinterpret_cast<const float4*>(&red[lane][0]);
+  const float k2 = warp_sum4_transposed(r.x, r.y, r.z, r.w, lane);
   a = __shfl_sync(kFull, k2, 0); b = __shfl_sync(kFull, k2, 8); c = __shfl_sync(kFull, k2, 16); d = __shfl_sync(kFull, k2, 24);
-  __syncthreads();      // red may be reused
 }
 
 // ... and of six (the variance path: S, the first and the second moments about the pivot)
@@ -75,92 +98,134 @@ __device__ __forceinline__ void pair_block_sum6(float& a, float& b, float& c, fl
   if ((lane & 7) == 0) red[warp][lane >> 3] = k;
   if ((lane & 15) == 0) red[warp][4 + (lane >> 4)] = k2;
   __syncthreads();
-  const float q = warp_sum4_transposed(red[lane][0], red[lane][1], red[lane][2], red[lane][3], lane);
-  const float q2 = warp_sum2_transposed(red[lane][4], red[lane][5], lane);
+  const float4 r = *reinterpret_cast<const float4*>(&red[lane][0]);
+  const float2 r2 = *reinterpret_cast<const float2*>(&red[lane][4]);
+  const float q = warp_sum4_transposed(r.x, r.y, r.z, r.w, lane);
+  const float q2 = warp_sum2_transposed(r2.x, r2.y, lane);
   a = __shfl_sync(kFull, q, 0); b = __shfl_sync(kFull, q, 8); c = __shfl_sync(kFull, q, 16); d = __shfl_sync(kFull, q, 24);
   e = __shfl_sync(kFull, q2, 0); f = __shfl_sync(kFull, q2, 16);
-  __syncthreads();      // red may be reused
 }
 
-template <int REG>
-__global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const PairParams p) {
+// DSNT_TUNE_STEP_PAIR_FLAGS & 8 (measurements only): SM clocks thread 0 of CTA 0 spends in each phase of a heatmap, summed over
+// its heatmaps; [15] counts the heatmaps
+__device__ unsigned long long g_pair_trace[16];
+
+template <int REG, int CS, typename T>
+__global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_SM) head_step_pair_kernel(const PairParams p) {
+  using C = PairCfg<CS, T>;
+  constexpr int NT = C::NT, NW = C::NW, NS = C::NS, NCH = C::NCH, RPS = C::RPS, ES = C::ES;
   constexpr bool kVar = REG == DSNT_REG_VAR;
   constexpr bool kJS = REG == DSNT_REG_JS;
   constexpr bool kMSE = REG == DSNT_REG_MSE;
   constexpr bool kWin = kJS || kMSE;
-  // JS / MSE: the Gaussian window (16 x 16 pixels at sigma = 1 px) lies in the registers of the <= 80 threads that hold its
+  // JS / MSE: the Gaussian window (16 x 16 pixels at sigma = 1 px) lies in the registers of the few threads that hold its
   // vectors.  Its terms need P = e / S, i.e. the merged sums: they are evaluated AFTER the first exchange, block-reduced
   // and exchanged in a second message; the backward evaluates them again (nothing per-pixel is kept: the 64 registers of a
   // thread hold its 32 values of e).  Outside the window the closed forms of head_step2.cuh apply.
   constexpr float tow = 2.0f / kPairW, bw = 1.0f / kPairW - 1.0f, toh = 2.0f / kPairH, bh = 1.0f / kPairH - 1.0f;
   extern __shared__ __align__(128) unsigned char pair_smem[];
-  __shared__ __align__(8) unsigned long long bars[kPairSlots];
-  __shared__ float red[32][8];
-  __shared__ __align__(16) float xin[2][2][4];            // the PEER's partial results, stored here by the peer (st.async over DSMEM);
-                                                          // message number n lands in xin[n & 1]: the peer can be one message ahead
-  __shared__ __align__(8) unsigned long long xbar[1];     // ... the two stores completing 32 bytes on this mbarrier
+  __shared__ __align__(8) unsigned long long bars[NS];
+  __shared__ __align__(16) float red[2][32][8];           // two scratch arrays taken in turn: a reduction needs ONE block barrier
+  __shared__ float redm[32];
+  __shared__ __align__(16) float xin[2][CS][8];           // the partial results of every CTA of the cluster, slot [r] stored by CTA r
+                                                          // (st.async over DSMEM; the own slot locally); message number n lands in
+                                                          // xin[n & 1]: a peer can be one message ahead
+  __shared__ __align__(8) unsigned long long xbar[2];     // ... completing 32 (CS - 1) bytes on xbar[n & 1]
+  __shared__ long long trace_last;
+  const bool tracing = (p.tune & 8) && blockIdx.x == 0 && threadIdx.x == 0;
+  auto stamp = [&](int phase) {
+    if (tracing) {
+      const long long t = clock64();
+      g_pair_trace[phase] += static_cast<unsigned long long>(t - trace_last);
+      trace_last = t;
+    }
+  };
 
   cg::cluster_group cluster = cg::this_cluster();
-  const unsigned rank = cluster.block_rank();            // 0: rows 0..127, 1: rows 128..255
-  const unsigned peer = rank ^ 1u;
-  const long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const unsigned rank = cluster.block_rank();            // rows rank * ROWS ...
+  const long cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // The exchange of a heatmap: thread 0 arms its own xbar for 32 bytes and stores its partial results into the peer's xin
-  // with st.async, which completes the bytes on the PEER's xbar; everybody then waits on the local barrier and reads the
-  // local xin.  No cluster-wide barrier (whose release fence makes all 1024 threads wait for their global stores: the
-  // first version of this kernel, 1053 us at config 5, against 878 us with three such exchanges and less with one).
+  // The exchange of a heatmap: thread 0 puts its CTA's partial results into the own slot and arms the local barrier for
+  // the bytes of the CS - 1 peers; threads 1 .. CS-1 store them into the slot [rank] of one peer each with st.async, which
+  // completes the bytes on THAT CTA's barrier; everybody then waits on the local barrier and reads the local xin.  No
+  // cluster-wide barrier (whose release fence makes all threads wait for their global stores: the first version of this
+  // kernel, 1053 us at config 5, against 878 us with three such exchanges and less with one).  Two barriers in turn: with
+  // more than one peer, message n+1 of a fast peer must not complete bytes of the phase that still waits for message n of
+  // a slow one.
   const uint32_t xin_s = smem_u32(&xin[0][0][0]), xbar_s = smem_u32(&xbar[0]);
-  uint32_t peer_xin_s, peer_xbar_s;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xin_s) : "r"(xin_s), "r"(peer));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xbar_s) : "r"(xbar_s), "r"(peer));
-  uint32_t xn = 0;          // messages exchanged so far: the same on both CTAs (they take the same branches on bit-identical totals)
-  auto send = [&](float a, float b, float c, float d, float e, float f, float g7 = 0.f) {      // thread 0; message number xn
-    const uint32_t dst = peer_xin_s + (xn & 1u) * 32u;
-    mbar_expect_tx(xbar_s, 32);
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
-                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(peer_xbar_s)
-                 : "memory");
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst + 16),
-                 "f"(e), "f"(f), "f"(g7), "f"(0.f), "r"(peer_xbar_s)
-                 : "memory");
+  uint32_t peer_xin_s = 0, peer_xbar_s = 0;
+  if (tid >= 1 && tid < CS) {
+    const unsigned peer = (rank + static_cast<unsigned>(tid)) % CS;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xin_s) : "r"(xin_s), "r"(peer));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xbar_s) : "r"(xbar_s), "r"(peer));
+  }
+  uint32_t xn = 0;          // messages exchanged so far: the same on all CTAs (they take the same branches on bit-identical totals)
+  // post message number xn (values identical on every thread of the CTA)
+  auto post = [&](float a, float b, float c, float d, float e, float f, float g7) {
+    const uint32_t par = xn & 1u;
+    if (tid == 0) {
+      float4* own = reinterpret_cast<float4*>(&xin[par][rank][0]);
+      own[0] = make_float4(a, b, c, d);
+      own[1] = make_float4(e, f, g7, 0.f);
+      mbar_expect_tx(xbar_s + 8 * par, 32 * (CS - 1));      // (release: the own slot is visible to whoever passes the barrier)
+    } else if (tid < CS) {
+      const uint32_t dst = peer_xin_s + (par * CS + rank) * 32u, bar = peer_xbar_s + 8 * par;
+      asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                   "f"(a), "f"(b), "f"(c), "f"(d), "r"(bar)
+                   : "memory");
+      asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst + 16),
+                   "f"(e), "f"(f), "f"(g7), "f"(0.f), "r"(bar)
+                   : "memory");
+    }
+  };
+  // wait for message number xn of every peer; returns the CS slots
+  auto collect = [&]() -> const float (*)[8] {
+    const uint32_t par = xn & 1u;
+    mbar_wait(xbar_s + 8 * par, (xn >> 1) & 1u);
+    ++xn;
+    return xin[par];
   };
   const uint32_t bars_s = smem_u32(&bars[0]), buf_s = smem_u32(pair_smem);
-  const long hm_floats = static_cast<long>(kPairH) * kPairW;
+  const long hm_bytes = static_cast<long>(kPairH) * kPairW * ES;
   // heatmaps of this cluster: hm = cluster_id + k * n_clusters, k = 0 .. nk-1; chunk c of heatmap k is chunk number
-  // g = 4k + c of this CTA's stream and lives in ring slot g mod 7 on that slot's (g / 7)-th use
+  // g = NCH k + c of this CTA's stream and lives in ring slot g mod NS on that slot's (g / NS)-th use
   const long nk = p.n > cluster_id ? (p.n - cluster_id + n_clusters - 1) / n_clusters : 0;
-  auto issue = [&](long k, int c) {      // thread 0
+  auto issue = [&](unsigned g) {
+    const long k = g / NCH;
+    const unsigned c = g % NCH;
     if (k >= nk) return;
     const long hm = cluster_id + k * n_clusters;
-    const unsigned g = static_cast<unsigned>(4 * k + c), slot = g % kPairSlots;
-    const char* src = reinterpret_cast<const char*>(p.z + hm * hm_floats) + static_cast<size_t>(rank) * kPairHalfBytes +
-                      static_cast<size_t>(c) * kPairChunkBytes;
-    mbar_expect_tx(bars_s + 8 * slot, kPairChunkBytes);
-    bulk_load(buf_s + slot * kPairChunkBytes, src, kPairChunkBytes, bars_s + 8 * slot);
+    const unsigned slot = g % NS;
+    const char* src = static_cast<const char*>(p.z) + hm * hm_bytes + static_cast<size_t>(rank) * C::PART_BYTES +
+                      static_cast<size_t>(c) * C::CHUNK;
+    mbar_expect_tx(bars_s + 8 * slot, C::CHUNK);
+    bulk_load(buf_s + slot * C::CHUNK, src, C::CHUNK, bars_s + 8 * slot);
   };
   if (tid == 0) {
-    for (int sl = 0; sl < kPairSlots; ++sl) mbar_init(bars_s + 8 * sl, 1);
+    for (int sl = 0; sl < NS; ++sl) mbar_init(bars_s + 8 * sl, 1);
     mbar_init(xbar_s, 1);
-    for (int c = 0; c < 4; ++c) issue(0, c);
-    for (int c = 0; c < 3; ++c) issue(1, c);
+    mbar_init(xbar_s + 8, 1);
+    for (unsigned g = 0; g < NS; ++g) issue(g);
   }
-  cluster.sync();       // both CTAs' barriers exist before the first remote store
+  for (int i = tid; i < 2 * 32 * 8; i += NT) (&red[0][0][0])[i] = 0.f;
+  cluster.sync();       // every CTA's barriers exist before the first remote store (and red is cleared)
   const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
   const float inv_denom = 1.0f / __ldg(p.denom);
   const float s2 = p.sigma * p.sigma;
 
-  // thread geometry: vector column cv (4 pixels), rows row_base + 16 * it inside this CTA's half
+  // thread geometry: vector column cv (4 pixels), rows r0 + RPS * it inside this CTA's part
   const int cv = tid & (kPairWV - 1), r0 = tid >> 6;
   float xs[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) xs[c] = fmaf(static_cast<float>(cv * 4 + c), tow, bw);
-  const float y0 = fmaf(static_cast<float>(rank * kPairHalfRows + r0), toh, bh);
-  constexpr float dyi = kPairRowsPerStep * toh;
+  const float y0 = fmaf(static_cast<float>(rank * C::ROWS + r0), toh, bh);
+  constexpr float dyi = RPS * toh;
   const f2 l2e2 = pk1(kLog2e);
 
+  if (tracing) trace_last = clock64();
   for (long k = 0; k < nk; ++k) {
     const long hm = cluster_id + k * n_clusters;
-    const unsigned g0 = static_cast<unsigned>(4 * k);       // chunk number of this heatmap's first chunk
+    const unsigned g0 = static_cast<unsigned>(NCH * k);       // chunk number of this heatmap's first chunk
     float tx = 0.f, ty = 0.f;
     if (p.target) {
       const float2 tt = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
@@ -168,33 +233,53 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     }
     const float wgt = (p.mask ? __ldg(p.mask + hm) : 1.0f) * inv_denom;
 
-    // ---------------------------------------------------------------- the half heatmap comes into REGISTERS (32 per thread)
+    // ---------------------------------------------------------------- the part comes into REGISTERS (32 pixels per thread)
     // and its maximum is taken on the way; shared memory is read exactly once, so its buffers are free for the next loads
     // as soon as this sweep is over
     f2 ev[kPairIters][2];
-    float m0 = -INFINITY, m1 = -INFINITY;
+    float mloc;
+    if constexpr (ES == 4) {
+      float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int it = 0; it < kPairIters; ++it) {
-      const unsigned g = g0 + it / 2, slot = g % kPairSlots;
-      if ((it & 1) == 0) mbar_wait(bars_s + 8 * slot, (g / kPairSlots) & 1u);
-      const uint4 r = *reinterpret_cast<const uint4*>(pair_smem + slot * kPairChunkBytes + (it & 1) * (kPairChunkBytes / 2) + tid * 16);
-      unpack_pairs<float>(r, ev[it]);
-      m0 = fmaxf(m0, fmaxf(__uint_as_float(r.x), __uint_as_float(r.y)));
-      m1 = fmaxf(m1, fmaxf(__uint_as_float(r.z), __uint_as_float(r.w)));
+      for (int it = 0; it < kPairIters; ++it) {
+        const unsigned g = g0 + it / C::IPC, slot = g % NS;
+        if (it % C::IPC == 0) mbar_wait(bars_s + 8 * slot, (g / NS) & 1u);
+        const uint4 r = *reinterpret_cast<const uint4*>(pair_smem + slot * C::CHUNK + (it % C::IPC) * C::STEP_BYTES + tid * 16);
+        unpack_pairs<float>(r, ev[it]);
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(r.x), __uint_as_float(r.y)));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(r.z), __uint_as_float(r.w)));
+      }
+      mloc = fmaxf(m0, m1);
+    } else {
+      uint32_t mb = 0xff80ff80u;      // (-inf, -inf)
+#pragma unroll
+      for (int it = 0; it < kPairIters; ++it) {
+        const unsigned g = g0 + it / C::IPC, slot = g % NS;
+        if (it % C::IPC == 0) mbar_wait(bars_s + 8 * slot, (g / NS) & 1u);
+        const uint2 r = *reinterpret_cast<const uint2*>(pair_smem + slot * C::CHUNK + (it % C::IPC) * C::STEP_BYTES + tid * 8);
+        ev[it][0] = bf16x2_to_f2(r.x);
+        ev[it][1] = bf16x2_to_f2(r.y);
+        mb = max_bf16x2(mb, max_bf16x2(r.x, r.y));
+      }
+      mloc = fmaxf(bf16lo(mb), bf16hi(mb));
     }
-    float mloc = warp_max_redux(fmaxf(m0, m1));
-    if (lane == 0) red[warp][0] = mloc;
+    stamp(0);                                  // wait for the loads + shared memory -> registers
+    mloc = warp_max_redux(mloc);
+    if (lane == 0) redm[warp] = mloc;
     __syncthreads();
-    // every thread has its data: this heatmap's four buffers take the last chunk of the next heatmap and the first three of
-    // the one after it (nothing was written to them by the generic proxy, so no proxy fence)
-    if (tid == 0) {
-      issue(k + 1, 3);
-      for (int c = 0; c < 3; ++c) issue(k + 2, c);
+    stamp(1);                                  // block barrier (the slowest warp's loads)
+    // every thread has its data: this heatmap's buffers take the next NCH chunks of the stream (nothing was written to
+    // them by the generic proxy, so no proxy fence)
+    if (p.tune & 1) {
+      if (tid == 0)
+        for (int c = 0; c < NCH; ++c) issue(g0 + NS + c);
+    } else if (tid < NCH) {
+      issue(g0 + NS + tid);
     }
-    mloc = warp_max_redux(red[lane][0]);
-    __syncthreads();                                  // red is free again
-    // Each half is summed relative to ITS OWN maximum; the halves are merged afterwards like two blocks of an online
-    // softmax (S = S_0 2^(m_0 - m) + S_1 2^(m_1 - m)), so ONE exchange per heatmap carries everything.
+    mloc = warp_max_redux(redm[lane & (NW - 1)]);
+    if (p.tune & 2) __syncthreads();
+    // Each part is summed relative to ITS OWN maximum; the parts are merged afterwards like the blocks of an online
+    // softmax (S = sum_r S_r 2^(m_r - m)), so ONE exchange per heatmap carries everything.
     const float m2h = mloc * kLog2e;
     const f2 nm2 = pk1(-m2h);
 
@@ -219,6 +304,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       if constexpr (kVar) Syy = fmaf(rs * dy, dy, Syy);
       if constexpr (kMSE) tt2 = fma2(ev[it][0], ev[it][0], fma2(ev[it][1], ev[it][1], tt2));
     }
+    stamp(2);                                  // issue of the next loads, maximum, exponential sweep
     float c0, c1, c2, c3;
     upk(colE[0], c0, c1);
     upk(colE[1], c2, c3);
@@ -230,45 +316,93 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     float Tth = 0.f;
     if constexpr (!kVar) {
       Tth = hsum(tt2);
-      pair_block_sum4(Sh, Sxh, Syh, Tth, red, warp, lane);
+      pair_block_sum4(Sh, Sxh, Syh, Tth, red[0], warp, lane);
     } else {
       axh = fmaf(c0 * dx0, dx0, fmaf(c1 * dx1, dx1, fmaf(c2 * dx2, dx2, c3 * dx3 * dx3)));
       ayh = Syy;
-      pair_block_sum6(Sh, Sxh, Syh, axh, ayh, Syy, red, warp, lane);      // (the sixth value rides along unused)
+      pair_block_sum6(Sh, Sxh, Syh, axh, ayh, Syy, red[0], warp, lane);      // (the sixth value rides along unused)
     }
-    if (tid == 0) send(m2h, Sh, Sxh, Syh, axh, ayh, Tth);
-    mbar_wait(xbar_s, xn & 1u);
-    // merge in rank order on both CTAs: bit-identical totals
-    const bool first = rank == 0;
-    const float (*xm)[4] = xin[xn & 1u];
-    ++xn;
-    const float p_m = xm[0][0], p_S = xm[0][1], p_Sx = xm[0][2], p_Sy = xm[0][3], p_ax = xm[1][0], p_ay = xm[1][1], p_Tt = xm[1][2];
-    const float h_m[2] = {first ? m2h : p_m, first ? p_m : m2h};
-    const float h_S[2] = {first ? Sh : p_S, first ? p_S : Sh};
-    const float h_Sx[2] = {first ? Sxh : p_Sx, first ? p_Sx : Sxh};
-    const float h_Sy[2] = {first ? Syh : p_Sy, first ? p_Sy : Syh};
-    const float h_ax[2] = {first ? axh : p_ax, first ? p_ax : axh};
-    const float h_ay[2] = {first ? ayh : p_ay, first ? p_ay : ayh};
-    const float m2 = fmaxf(h_m[0], h_m[1]);
-    const float sc0 = ex2(h_m[0] - m2), sc1 = ex2(h_m[1] - m2);
-    // each half was summed relative to ITS OWN maximum: rescaled like two blocks of an online softmax; everything is about
-    // the same pivot, so the halves simply add
-    const float S = fmaf(h_S[0], sc0, h_S[1] * sc1);
-    const float Sxc = fmaf(h_Sx[0], sc0, h_Sx[1] * sc1), Sycm = fmaf(h_Sy[0], sc0, h_Sy[1] * sc1);
+    if (p.tune & 4) __syncthreads();
+    stamp(3);                                  // block sum
+    post(m2h, Sh, Sxh, Syh, axh, ayh, Tth);
+
+    // ---------------------------------------------------------------- JS / MSE: where the Gaussian window lies and its
+    // normalisation -- functions of the target alone, evaluated while the first message is on its way
+    float ginv = 0.f, l2ginv = 0.f;
+    int wi_lo = 0, wi_hi = -1;
+    bool colin = false;
+    if constexpr (kWin) {
+      int j_lo, j_hi;
+      axis_window_fast(tx, kPairW, 0.5f * kPairW, tow, bw, p.r2_win, j_lo, j_hi);
+      axis_window_fast(ty, kPairH, 0.5f * kPairH, toh, bh, p.r2_win, wi_lo, wi_hi);
+      if (j_lo <= j_hi && wi_lo <= wi_hi) {
+        float sx = 0.f, sy = 0.f;                    // every warp for itself: 2 x <= 17 exponentials, no block barrier
+        for (int j = j_lo + lane; j <= j_hi; j += 32) {
+          const float d = fmaf(static_cast<float>(j), tow, bw) - tx;
+          sx += ex2(p.k2 * d * d);
+        }
+        for (int i = wi_lo + lane; i <= wi_hi; i += 32) {
+          const float d = fmaf(static_cast<float>(i), toh, bh) - ty;
+          sy += ex2(p.k2 * d * d);
+        }
+        const float ks = warp_sum2_transposed(sx, sy, lane);
+        sx = __shfl_sync(kFull, ks, 0);
+        sy = __shfl_sync(kFull, ks, 16);
+        ginv = rcp(sx * sy + kEps);
+        l2ginv = lg2(ginv);
+        colin = cv >= (j_lo >> 2) && cv <= (j_hi >> 2);
+      } else {
+        wi_hi = wi_lo - 1;
+      }
+    }
+
+    stamp(4);                                  // post + window geometry
+    // ---------------------------------------------------------------- merge in rank order on every CTA: bit-identical totals
+    float sc[CS];
+    float m2, S, Sxc, Sycm, sax = 0.f, say = 0.f, Tt = 0.f;
+    {
+      const float (*xm)[8] = collect();
+      float4 lo[CS], hi[CS];
+#pragma unroll
+      for (int r = 0; r < CS; ++r) {
+        lo[r] = *reinterpret_cast<const float4*>(&xm[r][0]);
+        hi[r] = *reinterpret_cast<const float4*>(&xm[r][4]);
+      }
+      m2 = lo[0].x;
+#pragma unroll
+      for (int r = 1; r < CS; ++r) m2 = fmaxf(m2, lo[r].x);
+#pragma unroll
+      for (int r = 0; r < CS; ++r) sc[r] = ex2(lo[r].x - m2);
+      // each part was summed relative to ITS OWN maximum: rescaled like the blocks of an online softmax; everything is
+      // about the same pivot, so the parts simply add
+      S = lo[CS - 1].y * sc[CS - 1]; Sxc = lo[CS - 1].z * sc[CS - 1]; Sycm = lo[CS - 1].w * sc[CS - 1];
+      if (kVar) { sax = hi[CS - 1].x * sc[CS - 1]; say = hi[CS - 1].y * sc[CS - 1]; }
+      if (kMSE) Tt = hi[CS - 1].z * sc[CS - 1] * sc[CS - 1];
+#pragma unroll
+      for (int r = CS - 2; r >= 0; --r) {
+        S = fmaf(lo[r].y, sc[r], S); Sxc = fmaf(lo[r].z, sc[r], Sxc); Sycm = fmaf(lo[r].w, sc[r], Sycm);
+        if (kVar) { sax = fmaf(hi[r].x, sc[r], sax); say = fmaf(hi[r].y, sc[r], say); }
+        if (kMSE) Tt = fmaf(hi[r].z, sc[r] * sc[r], Tt);                       // sum e^2 over all parts
+      }
+    }
+    stamp(5);                                  // wait for the peers' message + merge
     const float invS = rcp(S);
     const float mxc = Sxc * invS, myc = Sycm * invS;
     const float mux = pcx + mxc, muy = pcy + myc;
-    const float invSh = (first ? sc0 : sc1) * invS;       // this half's e (relative to its own maximum) -> probability
+    float scme = sc[0];
+#pragma unroll
+    for (int r = 1; r < CS; ++r) scme = rank == r ? sc[r] : scme;
+    const float invSh = scme * invS;       // this part's e (relative to its own maximum) -> probability
 
     float D = 0.f, creg = 0.f, vx = 0.f, vy = 0.f;
     if constexpr (kVar) {
-      vx = fmaf(h_ax[0], sc0, h_ax[1] * sc1) * invS - mxc * mxc;
-      vy = fmaf(h_ay[0], sc0, h_ay[1] * sc1) * invS - myc * myc;
+      vx = sax * invS - mxc * mxc;
+      vy = say * invS - myc * myc;
       // conditioning of the pivot form: (mu - c)^2 <= 16 var keeps the cancellation below 17 fp32 roundings (1e-6 relative)
       const bool ill = !(mxc * mxc <= 16.f * vx) || !(myc * myc <= 16.f * vy);
       if (ill) {
         // exact: second moments about the mean itself, from the registers (column sums are still there, the row sums are
-        // formed again), one more block reduction and one more exchange; both CTAs get here together (identical totals)
+        // formed again), one more block reduction and one more exchange; all CTAs get here together (identical totals)
         const float ex0 = xs[0] - mux, ex1 = xs[1] - mux, ex2v = xs[2] - mux, ex3 = xs[3] - mux;
         float axe = fmaf(c0 * ex0, ex0, fmaf(c1 * ex1, ex1, fmaf(c2 * ex2v, ex2v, c3 * ex3 * ex3)));
         float aye = 0.f;
@@ -279,14 +413,14 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
           aye = fmaf(hsum(add2(ev[it][0], ev[it][1])) * d, d, aye);
         }
         float z0 = 0.f, z1 = 0.f;
-        pair_block_sum4(axe, aye, z0, z1, red, warp, lane);
-        if (tid == 0) send(axe, aye, 0.f, 0.f, 0.f, 0.f);
-        mbar_wait(xbar_s, xn & 1u);
-        const float (*xe)[4] = xin[xn & 1u];
-        ++xn;
-        const float q_ax = xe[0][0], q_ay = xe[0][1];
-        vx = fmaf(first ? axe : q_ax, sc0, (first ? q_ax : axe) * sc1) * invS;
-        vy = fmaf(first ? aye : q_ay, sc0, (first ? q_ay : aye) * sc1) * invS;
+        pair_block_sum4(axe, aye, z0, z1, red[1], warp, lane);
+        post(axe, aye, 0.f, 0.f, 0.f, 0.f, 0.f);
+        const float (*xe)[8] = collect();
+        float qx = xe[CS - 1][0] * sc[CS - 1], qy = xe[CS - 1][1] * sc[CS - 1];
+#pragma unroll
+        for (int r = CS - 2; r >= 0; --r) { qx = fmaf(xe[r][0], sc[r], qx); qy = fmaf(xe[r][1], sc[r], qy); }
+        vx = qx * invS;
+        vy = qy * invS;
       }
       const float ex = vx - s2, ey = vy - s2;
       D = ex * ex + ey * ey;
@@ -294,10 +428,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
     }
 
     // ---------------------------------------------------------------- JS / MSE: the Gaussian window, from the registers
-    float ginv = 0.f, l2ginv = 0.f;
-    int wi_lo = 0, wi_hi = -1;
-    bool colin = false;
-    const int rowb = static_cast<int>(rank) * kPairHalfRows + r0;       // this thread's rows: rowb + 16 it
+    const int rowb = static_cast<int>(rank) * C::ROWS + r0;       // this thread's rows: rowb + RPS it
     const f2 k2p = pk1(p.k2), eps2 = pk1(kEps), half2 = pk1(0.5f), invSh2 = pk1(invSh);
     const f2 wdx[2] = {pk(xs[0] - tx, xs[1] - tx), pk(xs[2] - tx, xs[3] - tx)};
     // the window terms of one pair of pixels: P, and d = log2(P + eps) - 1 - log2(M + eps) (JS) or G (MSE); JS also lgG - L
@@ -315,34 +446,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       }
     };
     if constexpr (kWin) {
-      int j_lo, j_hi;
-      axis_window_fast(tx, kPairW, 0.5f * kPairW, tow, bw, p.r2_win, j_lo, j_hi);
-      axis_window_fast(ty, kPairH, 0.5f * kPairH, toh, bh, p.r2_win, wi_lo, wi_hi);
-      const bool has = j_lo <= j_hi && wi_lo <= wi_hi;
       f2 qa = pk1(0.f), qb = pk1(0.f), qc = pk1(0.f);
-      if (has) {
-        float sx = 0.f, sy = 0.f;                    // every warp for itself: 2 x <= 17 exponentials, no block barrier
-        for (int j = j_lo + lane; j <= j_hi; j += 32) {
-          const float d = fmaf(static_cast<float>(j), tow, bw) - tx;
-          sx += ex2(p.k2 * d * d);
-        }
-        for (int i = wi_lo + lane; i <= wi_hi; i += 32) {
-          const float d = fmaf(static_cast<float>(i), toh, bh) - ty;
-          sy += ex2(p.k2 * d * d);
-        }
-        const float k = warp_sum2_transposed(sx, sy, lane);
-        sx = __shfl_sync(kFull, k, 0);
-        sy = __shfl_sync(kFull, k, 16);
-        ginv = rcp(sx * sy + kEps);
-        l2ginv = lg2(ginv);
-        colin = cv >= (j_lo >> 2) && cv <= (j_hi >> 2);
-      } else {
-        wi_hi = wi_lo - 1;
-      }
       if (colin) {
 #pragma unroll
         for (int it = 0; it < kPairIters; ++it) {
-          const int row = rowb + kPairRowsPerStep * it;
+          const int row = rowb + RPS * it;
           if (row >= wi_lo && row <= wi_hi) {
             const float dyw = (y0 + static_cast<float>(it) * dyi) - ty;
 #pragma unroll
@@ -363,16 +471,17 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
         }
       }
       float a0 = hsum(qa), a1 = hsum(qb), a2 = hsum(qc), a3 = 0.f;
-      pair_block_sum4(a0, a1, a2, a3, red, warp, lane);
-      if (tid == 0) send(a0, a1, a2, 0.f, 0.f, 0.f);
-      mbar_wait(xbar_s, xn & 1u);
-      const float (*xw)[4] = xin[xn & 1u];
-      ++xn;
-      const float w0 = first ? a0 + xw[0][0] : xw[0][0] + a0;       // rank order on both CTAs
-      const float w1 = first ? a1 + xw[0][1] : xw[0][1] + a1;
-      const float w2 = first ? a2 + xw[0][2] : xw[0][2] + a2;
+      stamp(6);                                // window terms (thread 0 holds none unless the window is at the left border)
+      pair_block_sum4(a0, a1, a2, a3, red[1], warp, lane);
+      if (p.tune & 4) __syncthreads();
+      stamp(7);                                // block sum of the window terms: waits for the threads that hold the window
+      post(a0, a1, a2, 0.f, 0.f, 0.f, 0.f);
+      const float (*xw)[8] = collect();
+      stamp(8);                                // second exchange
+      float w0 = xw[0][0], w1 = xw[0][1], w2 = xw[0][2];       // rank order on every CTA
+#pragma unroll
+      for (int r = 1; r < CS; ++r) { w0 += xw[r][0]; w1 += xw[r][1]; w2 += xw[r][2]; }
       if constexpr (kMSE) {
-        const float Tt = fmaf(first ? Tth : p_Tt, sc0 * sc0, (first ? p_Tt : Tth) * sc1 * sc1);      // sum e^2 over both halves
         const float outside = fmaxf(fmaf(Tt * invS, invS, -w1), 0.f);
         D = outside + w0;
         creg = 2.f * (outside + w2);
@@ -423,7 +532,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
       const float kyS = kVar ? rho * 2.f * (vy - s2) * invSh : 0.f;
       const f2 rpS = pk1(kMSE ? 2.f * rho * invSh * invSh : 0.f);
       const f2 kwS = pk1(kJS ? 0.5f * kLn2 * rho * invSh : (kMSE ? -2.f * rho * invSh : 0.f));   // JS: rho (ln2/2) d;  MSE: -2 rho G
-      uint4* dzv = reinterpret_cast<uint4*>(p.dz + hm * hm_floats) + static_cast<size_t>(rank) * (kPairHalfBytes / 16);
+      char* dzb = static_cast<char*>(p.dz) + hm * hm_bytes + static_cast<size_t>(rank) * C::PART_BYTES + tid * (4 * ES);
 #pragma unroll
       for (int it = 0; it < kPairIters; ++it) {
         f2 o[2];
@@ -431,26 +540,34 @@ __global__ void __launch_bounds__(kPairThreads, 1) head_step_pair_kernel(const P
         float rc = fmaf(bS, y, cbS);
         if (kVar) { const float d = y - muy; rc = fmaf(kyS * d, d, rc); }
         const f2 rc2 = pk1(rc);
-        f2 g0 = add2(acol[0], rc2), g1 = add2(acol[1], rc2);
-        if constexpr (kMSE) { g0 = fma2(rpS, ev[it][0], g0); g1 = fma2(rpS, ev[it][1], g1); }      // 2 rho P
+        f2 g0v = add2(acol[0], rc2), g1v = add2(acol[1], rc2);
+        if constexpr (kMSE) { g0v = fma2(rpS, ev[it][0], g0v); g1v = fma2(rpS, ev[it][1], g1v); }      // 2 rho P
         if constexpr (kWin) {
-          const int row = rowb + kPairRowsPerStep * it;
+          const int row = rowb + RPS * it;
           if (colin && row >= wi_lo && row <= wi_hi) {                 // window pixels: the G-dependent term, evaluated again
-            f2 P, d, gl;
-            win_pair(it, 0, y - ty, P, d, gl);
-            g0 = fma2(kwS, d, g0);
-            win_pair(it, 1, y - ty, P, d, gl);
-            g1 = fma2(kwS, d, g1);
+            f2 P, d, glw;
+            win_pair(it, 0, y - ty, P, d, glw);
+            g0v = fma2(kwS, d, g0v);
+            win_pair(it, 1, y - ty, P, d, glw);
+            g1v = fma2(kwS, d, g1v);
           }
         }
-        o[0] = mul2(ev[it][0], g0);
-        o[1] = mul2(ev[it][1], g1);
-        dzv[it * kPairThreads + tid] = pack_pairs<float>(o);
+        o[0] = mul2(ev[it][0], g0v);
+        o[1] = mul2(ev[it][1], g1v);
+        if constexpr (ES == 4) {
+          *reinterpret_cast<uint4*>(dzb + it * C::STEP_BYTES) = pack_pairs<float>(o);
+        } else {
+          float l0, h0, l1, h1;
+          upk(o[0], l0, h0);
+          upk(o[1], l1, h1);
+          *reinterpret_cast<uint2*>(dzb + it * C::STEP_BYTES) = make_uint2(pack_bf16(l0, h0), pack_bf16(l1, h1));
+        }
       }
     }
-
+    stamp(9);                                  // outputs + backward sweep (stores issued)
+    if (tracing) g_pair_trace[15] += 1;
   }
-  cluster.sync();      // neither CTA leaves while the other may still store into its shared memory
+  cluster.sync();      // no CTA leaves while another may still store into its shared memory
 }
 
 static int pair_enabled() {
@@ -458,45 +575,85 @@ static int pair_enabled() {
   return v;
 }
 
+// cluster size: DSNT_TUNE_STEP_PAIR_CS = 2 | 4 overrides the measured default (profiles/r02_v6_kbench_cfg5.txt); read on every
+// call (a launch of 0.3 ms and more), so that the tests can take both forms in one process
+static int pair_cluster_size(int dtype, int reg) {
+  const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_CS");
+  const int forced = e ? std::atoi(e) : 0;
+  if (forced == 2 || forced == 4) return forced;
+  (void)dtype; (void)reg;
+  return 4;
+}
+
 bool step_pair_supported(int dtype, int H, int W, int reg) {
   static const int win = [] { const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_WIN"); return e ? std::atoi(e) : 1; }();
-  return pair_enabled() && dtype == DSNT_DTYPE_F32 && H == kPairH && W == kPairW &&
+  return pair_enabled() && (dtype == DSNT_DTYPE_F32 || dtype == DSNT_DTYPE_BF16) && H == kPairH && W == kPairW &&
          (reg == DSNT_REG_NONE || reg == DSNT_REG_VAR || (win && (reg == DSNT_REG_JS || reg == DSNT_REG_MSE)));
 }
 
-template <int REG>
+// returns 1 when clusters of this shape cannot run on the device
+template <int REG, int CS, typename T>
 static int launch_pair(const PairParams& p, cudaStream_t stream) {
-  auto kern = head_step_pair_kernel<REG>;
+  using C = PairCfg<CS, T>;
+  auto kern = head_step_pair_kernel<REG, CS, T>;
   static int max_clusters_of[kMaxDevices] = {};     // per device: 0 = not asked yet, -1 = clusters of this size cannot run
   int& max_clusters = max_clusters_of[current_device()];
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   if (max_clusters == 0) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess)
       return check_launch("head_step_pair_kernel (shared-memory opt-in)");
     cudaLaunchConfig_t probe = {};
-    probe.gridDim = dim3(2 * sm_count_of_current_device()); probe.blockDim = dim3(kPairThreads); probe.dynamicSmemBytes = kPairSmemBytes;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    probe.gridDim = dim3(CS * C::CTAS_PER_SM * sm_count_of_current_device()); probe.blockDim = dim3(C::NT);
+    probe.dynamicSmemBytes = C::SMEM;
     probe.attrs = at; probe.numAttrs = 1;
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, kern, &probe) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = -1; }
     max_clusters = nc;
+    if (std::getenv("DSNT_TUNE_STEP_PAIR_VERBOSE"))
+      fprintf(stderr, "head_step_pair_kernel<reg %d, cluster %d, %d B>: %d co-resident clusters\n", REG, CS, C::ES, nc);
   }
   if (max_clusters < 0) return 1;      // clusters of this size cannot run here
+  static const int cap = [] { const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_CLUSTERS"); return e ? std::atoi(e) : 0; }();
   long clusters = p.n < max_clusters ? p.n : max_clusters;
+  if (cap > 0 && clusters > cap) clusters = cap;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters)); cfg.blockDim = dim3(kPairThreads);
-  cfg.dynamicSmemBytes = kPairSmemBytes; cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(static_cast<unsigned>(CS * clusters)); cfg.blockDim = dim3(C::NT);
+  cfg.dynamicSmemBytes = C::SMEM; cfg.stream = stream;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (p.tune & 8) {
+    unsigned long long zero[16] = {};
+    cudaMemcpyToSymbol(g_pair_trace, zero, sizeof(zero));
+  }
   if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) {
-    // no room for a cluster of two 224 KiB CTAs on this device / partition: not an error, the caller takes another kernel
+    // no room for such a cluster on this device / partition: not an error, the caller takes another kernel
     cudaGetLastError();
     return 1;
   }
+  if (p.tune & 8) {
+    unsigned long long t[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(t, g_pair_trace, sizeof(t));
+    const double nh = t[15] ? static_cast<double>(t[15]) : 1.0;
+    double tot = 0;
+    for (int i = 0; i < 10; ++i) tot += t[i] / nh;
+    fprintf(stderr, "pair trace <reg %d, cluster %d, %d B> clocks per heatmap (CTA 0, %llu heatmaps, %.0f in all): load+lds %.0f | barrier %.0f | "
+            "exp sweep %.0f | block sum %.0f | post+geometry %.0f | exchange+merge %.0f | window %.0f | window sum %.0f | exchange 2 %.0f | "
+            "backward %.0f\n", REG, CS, C::ES, t[15], tot, t[0] / nh, t[1] / nh, t[2] / nh, t[3] / nh, t[4] / nh, t[5] / nh, t[6] / nh,
+            t[7] / nh, t[8] / nh, t[9] / nh);
+  }
   return check_launch("head_step_pair_kernel");
+}
+
+template <int CS, typename T>
+static int launch_pair_reg(const PairParams& p, int reg, cudaStream_t stream) {
+  switch (reg) {
+    case DSNT_REG_VAR: return launch_pair<DSNT_REG_VAR, CS, T>(p, stream);
+    case DSNT_REG_JS: return launch_pair<DSNT_REG_JS, CS, T>(p, stream);
+    case DSNT_REG_MSE: return launch_pair<DSNT_REG_MSE, CS, T>(p, stream);
+    default: return launch_pair<DSNT_REG_NONE, CS, T>(p, stream);
+  }
 }
 
 // returns 1 when the case is not served
@@ -505,17 +662,19 @@ int launch_step_pair(const void* z, int dtype, long n, int H, int W, const float
                      float* coords, float* stats, float* terms, void* dz, cudaStream_t stream) {
   if (!step_pair_supported(dtype, H, W, reg) || !denom) return 1;
   PairParams p;
-  p.z = static_cast<const float*>(z); p.dz = static_cast<float*>(dz); p.target = target; p.mask = mask; p.denom = denom;
+  p.z = z; p.dz = dz; p.target = target; p.mask = mask; p.denom = denom;
   p.g_loss = g_loss; p.coords = coords; p.stats = stats; p.terms = terms; p.n = n; p.flags = flags; p.sigma = sigma;
   p.reg_coeff = reg_coeff;
   const Geom g = make_geom(H, W, 4, 32, sigma > 0.f ? sigma : 1.f, reg);
   p.k2 = g.k2; p.r2_win = g.r2_win;
-  switch (reg) {
-    case DSNT_REG_VAR: return launch_pair<DSNT_REG_VAR>(p, stream);
-    case DSNT_REG_JS: return launch_pair<DSNT_REG_JS>(p, stream);
-    case DSNT_REG_MSE: return launch_pair<DSNT_REG_MSE>(p, stream);
-    default: return launch_pair<DSNT_REG_NONE>(p, stream);
-  }
+  { const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_FLAGS"); p.tune = e ? std::atoi(e) : 0; }
+  const bool f32 = dtype == DSNT_DTYPE_F32;
+  int rc = 1;
+  if (pair_cluster_size(dtype, reg) == 4)
+    rc = f32 ? launch_pair_reg<4, float>(p, reg, stream) : launch_pair_reg<4, __nv_bfloat16>(p, reg, stream);
+  if (rc == 1)      // (also the fall-back of a device on which clusters of four do not fit)
+    rc = f32 ? launch_pair_reg<2, float>(p, reg, stream) : launch_pair_reg<2, __nv_bfloat16>(p, reg, stream);
+  return rc;
 }
 
 }  // namespace dsnt

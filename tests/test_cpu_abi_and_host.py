@@ -144,7 +144,8 @@ def test_step_support_queries_are_host_logic(libpath):
     assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['none']) == 1
     assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['js']) == 1                     # window terms from the registers
     assert lib.dsnt_head_step_pair_supported(f32, 256, 256, reg['kl']) == 0
-    assert lib.dsnt_head_step_pair_supported(bf16, 256, 256, reg['var']) == 0
+    assert lib.dsnt_head_step_pair_supported(bf16, 256, 256, reg['var']) == 1                   # round 2: bf16 too
+    assert lib.dsnt_head_step_pair_supported(bf16, 256, 256, reg['kl']) == 0
     assert lib.dsnt_head_step_pair_supported(f32, 128, 128, reg['var']) == 0
     assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['var']) == 1
     assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['js']) == 1

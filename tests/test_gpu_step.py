@@ -38,6 +38,19 @@ def always_take_the_step_kernels(dp):
     head.USE_PAIR_STEP = old_pair
 
 
+@pytest.fixture(params=[2, 4])
+def cluster_size(request):
+    """csrc/step_pair.cu in both forms: a heatmap on a pair of CTAs (one per SM) or on four (two per SM)."""
+    import os
+    old = os.environ.get('DSNT_TUNE_STEP_PAIR_CS')
+    os.environ['DSNT_TUNE_STEP_PAIR_CS'] = str(request.param)
+    yield request.param
+    if old is None:
+        del os.environ['DSNT_TUNE_STEP_PAIR_CS']
+    else:
+        os.environ['DSNT_TUNE_STEP_PAIR_CS'] = old
+
+
 def run_step(dp, z, target, mask, reg, hm_sigma=1.0, coeff=1.0, g=None, one_pass=True):
     from dsnt_pose2d_b200 import _lib
     zz = z.detach().clone().to(DEV).requires_grad_(True)
@@ -395,12 +408,15 @@ def test_stacked_single_launch_step_matches_stacked_two_kernel_path_and_oracle(d
 @pytest.mark.parametrize('shape,dtype,reg', [((3, 16, 256, 256), 'f32', 'var'), ((3, 16, 256, 256), 'f32', 'none'),
                                              ((3, 16, 256, 256), 'f32', 'js'), ((3, 16, 256, 256), 'f32', 'mse'),
                                              ((40, 16, 256, 256), 'f32', 'js'), ((40, 16, 256, 256), 'f32', 'var'),
-                                             ((2, 16, 256, 256), 'bf16', 'js'), ((5, 16, 128, 128), 'f32', 'var')])
-def test_step_for_heatmaps_too_large_for_one_ctas_shared_memory(dp, tp, shape, dtype, reg):
+                                             ((2, 16, 256, 256), 'bf16', 'js'), ((3, 16, 256, 256), 'bf16', 'var'),
+                                             ((3, 16, 256, 256), 'bf16', 'none'), ((3, 16, 256, 256), 'bf16', 'mse'),
+                                             ((40, 16, 256, 256), 'bf16', 'js'), ((2, 16, 256, 256), 'f32', 'kl'),
+                                             ((5, 16, 128, 128), 'f32', 'var')])
+def test_step_for_heatmaps_too_large_for_one_ctas_shared_memory(dp, tp, shape, dtype, reg, cluster_size):
     """Heatmaps of which fewer than four fit in one CTA's shared memory (BASELINE config 5: 256x256 with the variance
-    regulariser).  256x256 fp32, not KL: csrc/step_pair.cu, a cluster of two CTAs holding half a heatmap each, partial
-    results exchanged through distributed shared memory -- one pass over the logits.  The rest (bf16 at this size,
-    128x128 fp32) silently takes the two-kernel path.  Both against the fp64 oracle to the usual tolerance."""
+    regulariser).  256x256 fp32 and bf16, not KL: csrc/step_pair.cu, a cluster of two or four CTAs holding a part of a
+    heatmap each, partial results exchanged through distributed shared memory -- one pass over the logits.  The rest (KL
+    at this size, 128x128 fp32) silently takes the two-kernel path.  Both against the fp64 oracle to the usual tolerance."""
     from dsnt_pose2d_b200 import _lib
     b, c, h, w = shape
     gen = torch.Generator().manual_seed(91)
@@ -414,7 +430,7 @@ def test_step_for_heatmaps_too_large_for_one_ctas_shared_memory(dp, tp, shape, d
     launches = _lib.launch_count - before
     two = run_step(dp, z, target, mask, reg, one_pass=False)
     pair = bool(_lib.LIB.dsnt_head_step_pair_supported(0 if dtype == 'f32' else 1, h, w, _lib.REG_IDS[reg]))
-    assert pair == (dtype == 'f32' and (h, w) == (256, 256))
+    assert pair == ((h, w) == (256, 256) and reg != 'kl')
     assert launches == (4 if pair else 3)      # mask count, step, finishing reduction, scale  |  fwd, finish, bwd
     if pair:
         assert abs(got['loss'] - two['loss']) < 3e-6 * abs(two['loss'])
@@ -430,10 +446,12 @@ def test_step_for_heatmaps_too_large_for_one_ctas_shared_memory(dp, tp, shape, d
 
 
 @pytest.mark.parametrize('n,reg,with_mask', [(1, 'var', True), (3, 'none', False), (75, 'var', False), (149, 'none', True),
-                                             (1, 'js', True), (75, 'js', False), (149, 'mse', True)])
-def test_pair_step_edge_counts(dp, tp, n, reg, with_mask):
-    """csrc/step_pair.cu with fewer heatmaps than clusters, one more than the clusters (74 on a B200), and an odd count;
-    without a mask; peaked logits in one half only (the halves are merged like blocks of an online softmax)."""
+                                             (1, 'js', True), (75, 'js', False), (149, 'mse', True), (67, 'js', True),
+                                             (133, 'var', True)])
+def test_pair_step_edge_counts(dp, tp, n, reg, with_mask, cluster_size):
+    """csrc/step_pair.cu with fewer heatmaps than clusters, one more than the clusters (74 pairs on a B200; 66 clusters of
+    four), and an odd count; without a mask; peaked logits in one part only (the parts are merged like blocks of an
+    online softmax)."""
     gen = torch.Generator().manual_seed(95)
     z = torch.randn(n, 1, 256, 256, generator=gen)
     z[:, :, 200:210, 30:40] += 8.0                     # most of the mass in the lower half: the upper half's scale is ~2^-11
