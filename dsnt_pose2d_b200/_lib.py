@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdsnt_b200.so')
+# DSNT_B200_LIB: another build of the same library (developer measurements: tools/probe builds one with the phase trace)
+LIB_PATH = os.environ.get('DSNT_B200_LIB') or os.path.join(_HERE, 'libdsnt_b200.so')
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 REG_IDS = {'none': 0, 'var': 1, 'kl': 2, 'js': 3, 'mse': 4}
