@@ -8,14 +8,24 @@
 // into the shared memory of the others, all merge in rank order, so all hold bit-identical totals).  HBM sees every logit
 // once: 8 bytes per pixel (4 for bf16); shared memory is written once (by the TMA) and read once per heatmap.
 //
-//   CS = 2: 1024 threads, one CTA per SM: a heatmap per pair of SMs (round 1).
-//   CS = 4:  512 threads, TWO CTAs per SM: four SMs hold two heatmaps in flight, so while one heatmap sits in its
-//            reduction / exchange / window phase (latency, nothing issued) the other CTA of the SM sweeps.  The register
-//            file holds the same number of heatmaps as before (one per two SMs); the phases interleave.
+//   CS = 2: 1024 threads, one CTA per SM: a heatmap per pair of SMs.  The default.
+//   CS = 4:  512 threads, TWO CTAs per SM: four SMs hold two heatmaps in flight.  Measured slower on B200 for every
+//            regulariser (profiles/r02_v6_pair_variants.txt): a cluster moves at the pace of the slowest of its four SMs in
+//            every phase, and each of them also hosts a CTA of another cluster somewhere else in ITS cycle.  Kept as the
+//            form a device takes on which two 1024-thread CTAs cannot be co-scheduled (DSNT_TUNE_STEP_PAIR_CS=4 forces it).
 //
-// The shared memory of a CTA is a ring of NS chunk buffers; a part of a heatmap takes NCH of them (NS > NCH), so while
-// heatmap k is being processed NS - NCH chunks of heatmap k+1 (and k+2) are already loading, and as soon as k has been read
-// into registers its buffers take the next NCH chunks of the stream: the loads of the next heatmaps overlap all the arithmetic.
+// The CTA moves in lockstep through the phases of a heatmap (block barriers; letting the warps run free with a warp-granular
+// exchange was measured slower: STG bursts of one warp delay the shared-memory sweeps of another, same file).  A phase that
+// keeps a pipe busy while every warp waits is therefore exposed, and the longest one was the write-back: the path from an SM
+// to L2 takes 32 bytes per clock (tools/probe/store_probe.cu: 128 KiB = 4000 clocks for STG and for TMA alike), and a warp
+// that stores from registers waits for it.  So the gradient of five of the eight sweep steps goes back through the chunk
+// buffers it came in (STS at 90 B/clk, then one asynchronous bulk store per chunk) and only three steps are stored with STG:
+// config 5, variance: 722 -> 666 us (0.92 -> 1.00 of the HBM peak), JS 900 -> 788 us, MSE 914 -> 772 us.
+//
+// The shared memory of a CTA is a ring of NS chunk buffers, one chunk per sweep step; a part of a heatmap takes NCH = 8 of
+// them (NS > NCH), so while heatmap k is being processed NS - NCH chunks of heatmap k+1 are already there.  The buffers of
+// k's first STAGE0 steps take their next loads as soon as k has been read into registers; the others carry k's gradient
+// first and take theirs when the bulk stores have read them (thread 0, a heatmap later, while it waits for the exchange).
 //
 // Same mathematics as head_step2.cuh (src/dsnt/nn.py:25-116,274-298, src/dsnt/model.py:24-63,145):
 // column accumulators + one row sum per sweep step give S, S_x, S_y and the variance about a pivot without a second look;
@@ -54,6 +64,16 @@ struct PairCfg {
   // ring slots: fp32 CS=2: 13 x 16 KiB = 208 KiB (one CTA per SM); fp32 CS=4: 13 x 8 KiB = 104 KiB (two per SM);
   // bf16 CS=2: 24 x 8 KiB = 192 KiB; bf16 CS=4: 24 x 4 KiB = 96 KiB (two per SM)
   static constexpr int NS = ES == 4 ? 13 : 24;
+  // The gradient of the sweep steps >= STAGE0 goes back through the chunk buffers it came in (STS + one bulk store per
+  // chunk, asynchronous), that of the first STAGE0 steps straight from the registers (STG): the SM's path to L2 takes
+  // 32 B/clk (tools/probe/store_probe.cu: 128 KiB = 4000 clocks, whoever sends them), and an STG waits for it.  A staged
+  // buffer is handed to the next load only when its bulk store has read it, an unstaged one right after the sweep:
+  // fp32 keeps three early buffers so that the last chunks of the next heatmap are on their way in time.
+#ifdef DSNT_PAIR_STAGE0      // (measurements: -DDSNT_PAIR_STAGE0=8 is "no staging")
+  static constexpr int STAGE0 = ES == 4 ? DSNT_PAIR_STAGE0 : 0;
+#else
+  static constexpr int STAGE0 = ES == 4 ? 3 : 0;
+#endif
   static constexpr int SMEM = NS * CHUNK;
   static constexpr int CTAS_PER_SM = CS == 2 ? 1 : 2;
   static_assert(ROWS % RPS == 0 && ROWS / RPS == kPairIters && kPairIters % NCH == 0 && NS > NCH, "geometry");
@@ -73,44 +93,64 @@ struct PairParams {
   int flags;
   float sigma, reg_coeff;
   float k2, r2_win;       // Gaussian window (JS / MSE): -0.5 / sigma^2 * log2(e) and the window radius^2 (head_stream.cuh: make_geom)
-  int tune;               // DSNT_TUNE_STEP_PAIR_FLAGS (measurements only): 8 = phase trace
+  int tune;               // DSNT_TUNE_STEP_PAIR_FLAGS (measurements only; a build with -DDSNT_PAIR_TRACE): 8 = phase trace
 };
+
+// sum over the threads of one CTA of up to four values, identical on every thread, fixed order.  `red` has 32 rows; the
+// rows of warps that do not exist stay zero (cleared once at kernel start), so 16 warps reduce like 32.  ONE block
+// barrier: the caller alternates between two `red` arrays, see the kernel.
+__device__ __forceinline__ void pair_block_sum4(float& a, float& b, float& c, float& d, float (*red)[8], int warp, int lane) {
+  const float k = warp_sum4_transposed(a, b, c, d, lane);
+  if ((lane & 7) == 0) red[warp][lane >> 3] = k;
+  __syncthreads();
+  // (up to) 32 warps = 32 lanes: every warp adds the per-warp partials with the same butterfly
+  const float4 r = *reinterpret_cast<const float4*>(&red[lane][0]);
+  const float k2 = warp_sum4_transposed(r.x, r.y, r.z, r.w, lane);
+  a = __shfl_sync(kFull, k2, 0); b = __shfl_sync(kFull, k2, 8); c = __shfl_sync(kFull, k2, 16); d = __shfl_sync(kFull, k2, 24);
+}
+
+// ... and of six (the variance path: S, the first and the second moments about the pivot)
+__device__ __forceinline__ void pair_block_sum6(float& a, float& b, float& c, float& d, float& e, float& f, float (*red)[8],
+                                                int warp, int lane) {
+  const float k = warp_sum4_transposed(a, b, c, d, lane);
+  const float k2 = warp_sum2_transposed(e, f, lane);
+  if ((lane & 7) == 0) red[warp][lane >> 3] = k;
+  if ((lane & 15) == 0) red[warp][4 + (lane >> 4)] = k2;
+  __syncthreads();
+  const float4 r = *reinterpret_cast<const float4*>(&red[lane][0]);
+  const float2 r2 = *reinterpret_cast<const float2*>(&red[lane][4]);
+  const float q = warp_sum4_transposed(r.x, r.y, r.z, r.w, lane);
+  const float q2 = warp_sum2_transposed(r2.x, r2.y, lane);
+  a = __shfl_sync(kFull, q, 0); b = __shfl_sync(kFull, q, 8); c = __shfl_sync(kFull, q, 16); d = __shfl_sync(kFull, q, 24);
+  e = __shfl_sync(kFull, q2, 0); f = __shfl_sync(kFull, q2, 16);
+}
 
 // DSNT_TUNE_STEP_PAIR_FLAGS & 8 (measurements only): SM clocks thread 0 of CTA 0 spends in each phase of a heatmap, summed over
 // its heatmaps; [15] counts the heatmaps
 __device__ unsigned long long g_pair_trace[16];
 
-constexpr int kPairSlotsX = 64;       // warps per heatmap (2048 threads): one exchange slot each
-constexpr int kPairSlotF = 12;        // floats per slot: eight used, 48 bytes apart (128-bit reads of 8 consecutive slots hit 32 banks)
-
-// What the 64 warps of a heatmap exchange: every warp stores its partial results (relative to ITS OWN maximum, about the
-// common pivot) into slot [rank * NW + warp] of every CTA of the cluster; after the wait lane l of every warp holds the
-// slots l and l + 32, rescales them like blocks of an online softmax and the lanes add up with the same butterflies in every
-// warp of every CTA: bit-identical totals everywhere, no block barrier, no cluster barrier.
-struct PairSums {
-  float m, S, Sx, Sy, a, b, scme;     // a, b: second moments (variance) | a: sum e^2 (MSE)
-};
-
 template <int REG, int CS, typename T>
 __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_SM) head_step_pair_kernel(const PairParams p) {
   using C = PairCfg<CS, T>;
-  constexpr int NW = C::NW, NS = C::NS, NCH = C::NCH, RPS = C::RPS, ES = C::ES;
+  constexpr int NT = C::NT, NW = C::NW, NS = C::NS, NCH = C::NCH, RPS = C::RPS, ES = C::ES;
+  constexpr int kEarly = C::STAGE0;      // buffers handed to the next loads right after the sweep
   constexpr bool kVar = REG == DSNT_REG_VAR;
   constexpr bool kJS = REG == DSNT_REG_JS;
   constexpr bool kMSE = REG == DSNT_REG_MSE;
   constexpr bool kWin = kJS || kMSE;
-  static_assert(CS * NW == kPairSlotsX, "one slot per warp of the heatmap");
   // JS / MSE: the Gaussian window (16 x 16 pixels at sigma = 1 px) lies in the registers of the few threads that hold its
-  // vectors.  Its terms need P = e / S, i.e. the merged sums: they are evaluated AFTER the first exchange and exchanged in a
-  // second message; the backward evaluates them again (nothing per-pixel is kept: the 64 registers of a thread hold its 32
-  // values of e).  Outside the window the closed forms of head_step2.cuh apply.
+  // vectors.  Its terms need P = e / S, i.e. the merged sums: they are evaluated AFTER the first exchange, block-reduced
+  // and exchanged in a second message; the backward evaluates them again (nothing per-pixel is kept: the 64 registers of a
+  // thread hold its 32 values of e).  Outside the window the closed forms of head_step2.cuh apply.
   constexpr float tow = 2.0f / kPairW, bw = 1.0f / kPairW - 1.0f, toh = 2.0f / kPairH, bh = 1.0f / kPairH - 1.0f;
   extern __shared__ __align__(128) unsigned char pair_smem[];
   __shared__ __align__(8) unsigned long long bars[NS];
-  __shared__ __align__(16) float xin[2][kPairSlotsX][kPairSlotF];  // message number n lands in xin[n & 1]: a warp can be one message ahead
-  __shared__ __align__(8) unsigned long long xbar[2];     // ... completing 64 x 32 bytes on xbar[n & 1]
-  __shared__ __align__(16) float geo[2][8];               // JS / MSE: window geometry of heatmap k in geo[k & 1] (warp 0, one heatmap ahead)
-  __shared__ unsigned read_count;                         // warps that have their part of the current heatmap in registers
+  __shared__ __align__(16) float red[2][32][8];           // two scratch arrays taken in turn: a reduction needs ONE block barrier
+  __shared__ float redm[32];
+  __shared__ __align__(16) float xin[2][CS][8];           // the partial results of every CTA of the cluster, slot [r] stored by CTA r
+                                                          // (st.async over DSMEM; the own slot locally); message number n lands in
+                                                          // xin[n & 1]: a peer can be one message ahead
+  __shared__ __align__(8) unsigned long long xbar[2];     // ... completing 32 (CS - 1) bytes on xbar[n & 1]
 #ifdef DSNT_PAIR_TRACE
   __shared__ long long trace_last;
   const bool tracing = (p.tune & 8) && blockIdx.x == 0 && threadIdx.x == 0;
@@ -129,20 +169,31 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
   const unsigned rank = cluster.block_rank();            // rows rank * ROWS ...
   const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;      // (32-bit: n < 2^31, checked by the entry point)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // The exchange: lane r < CS of every warp stores the warp's eight floats into slot [rank * NW + warp] of CTA r with
-  // st.async, which completes the bytes on THAT CTA's barrier (the own CTA included); thread 0 arms the local barrier for
-  // the 64 x 32 bytes of a message; everybody waits on the local barrier and reads the local xin.  Two barriers in turn:
-  // message n+1 of a fast warp must not complete bytes of the phase that still waits for message n of a slow one.
+  // The exchange of a heatmap: thread 0 puts its CTA's partial results into the own slot and arms the local barrier for
+  // the bytes of the CS - 1 peers; threads 1 .. CS-1 store them into the slot [rank] of one peer each with st.async, which
+  // completes the bytes on THAT CTA's barrier; everybody then waits on the local barrier and reads the local xin.  No
+  // cluster-wide barrier (whose release fence makes all threads wait for their global stores: the first version of this
+  // kernel, 1053 us at config 5, against 878 us with three such exchanges and less with one).  Two barriers in turn: with
+  // more than one peer, message n+1 of a fast peer must not complete bytes of the phase that still waits for message n of
+  // a slow one.
   const uint32_t xin_s = smem_u32(&xin[0][0][0]), xbar_s = smem_u32(&xbar[0]);
-  uint32_t xn = 0;          // messages exchanged so far: the same on all warps of the cluster (same branches on bit-identical totals)
-  // post message number xn (values identical on every lane of the warp)
+  uint32_t peer_xin_s = 0, peer_xbar_s = 0;
+  if (tid >= 1 && tid < CS) {
+    const unsigned peer = (rank + static_cast<unsigned>(tid)) % CS;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xin_s) : "r"(xin_s), "r"(peer));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_xbar_s) : "r"(xbar_s), "r"(peer));
+  }
+  uint32_t xn = 0;          // messages exchanged so far: the same on all CTAs (they take the same branches on bit-identical totals)
+  // post message number xn (values identical on every thread of the CTA)
   auto post = [&](float a, float b, float c, float d, float e, float f, float g7) {
     const uint32_t par = xn & 1u;
-    if (tid == 0) mbar_expect_tx(xbar_s + 8 * par, 32 * kPairSlotsX);
-    if (lane < CS) {
-      uint32_t dst, bar;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(xin_s + (par * kPairSlotsX + rank * NW + warp) * (4u * kPairSlotF)), "r"(lane));
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(xbar_s + 8 * par), "r"(lane));
+    if (tid == 0) {
+      float4* own = reinterpret_cast<float4*>(&xin[par][rank][0]);
+      own[0] = make_float4(a, b, c, d);
+      own[1] = make_float4(e, f, g7, 0.f);
+      mbar_expect_tx(xbar_s + 8 * par, 32 * (CS - 1));      // (release: the own slot is visible to whoever passes the barrier)
+    } else if (tid < CS) {
+      const uint32_t dst = peer_xin_s + (par * CS + rank) * 32u, bar = peer_xbar_s + 8 * par;
       asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
                    "f"(a), "f"(b), "f"(c), "f"(d), "r"(bar)
                    : "memory");
@@ -151,8 +202,8 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
                    : "memory");
     }
   };
-  // wait for message number xn of all 64 warps; lane l reads the slots l and l + 32 of what is returned
-  auto collect = [&]() -> const float (*)[kPairSlotF] {
+  // wait for message number xn of every peer; returns the CS slots
+  auto collect = [&]() -> const float (*)[8] {
     const uint32_t par = xn & 1u;
     mbar_wait(xbar_s + 8 * par, (xn >> 1) & 1u);
     ++xn;
@@ -174,54 +225,23 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
     mbar_expect_tx(bars_s + 8 * slot, C::CHUNK);
     bulk_load(buf_s + slot * C::CHUNK, src, C::CHUNK, bars_s + 8 * slot);
   };
-  // JS / MSE: where the Gaussian window of a heatmap lies and its normalisation -- functions of the target alone; ONE warp
-  // works them out, a heatmap ahead (while it would wait for the exchange), the others read six numbers
-  auto geometry = [&](int k) {      // warp 0, all lanes
-    if (k >= nk) return;
-    const float2 tt = __ldg(reinterpret_cast<const float2*>(p.target) + (cluster_id + k * n_clusters));
-    int j_lo, j_hi, i_lo, i_hi;
-    axis_window_fast(tt.x, kPairW, 0.5f * kPairW, tow, bw, p.r2_win, j_lo, j_hi);
-    axis_window_fast(tt.y, kPairH, 0.5f * kPairH, toh, bh, p.r2_win, i_lo, i_hi);
-    float ginv = 0.f, l2ginv = 0.f;
-    if (j_lo <= j_hi && i_lo <= i_hi) {
-      float sx = 0.f, sy = 0.f;
-      for (int j = j_lo + lane; j <= j_hi; j += 32) {
-        const float d = fmaf(static_cast<float>(j), tow, bw) - tt.x;
-        sx += ex2(p.k2 * d * d);
-      }
-      for (int i = i_lo + lane; i <= i_hi; i += 32) {
-        const float d = fmaf(static_cast<float>(i), toh, bh) - tt.y;
-        sy += ex2(p.k2 * d * d);
-      }
-      const float ks = warp_sum2_transposed(sx, sy, lane);
-      sx = __shfl_sync(kFull, ks, 0);
-      sy = __shfl_sync(kFull, ks, 16);
-      ginv = rcp(sx * sy + kEps);
-      l2ginv = lg2(ginv);
-    } else {
-      j_lo = 1; j_hi = 0; i_lo = 1; i_hi = 0;
-    }
-    if (lane == 0) {
-      float4* gq = reinterpret_cast<float4*>(&geo[k & 1][0]);
-      gq[0] = make_float4(ginv, l2ginv, __int_as_float(j_lo), __int_as_float(j_hi));
-      gq[1] = make_float4(__int_as_float(i_lo), __int_as_float(i_hi), 0.f, 0.f);
-    }
-    __syncwarp();
-  };
   if (tid == 0) {
     for (int sl = 0; sl < NS; ++sl) mbar_init(bars_s + 8 * sl, 1);
     mbar_init(xbar_s, 1);
     mbar_init(xbar_s + 8, 1);
-    read_count = 0;
     for (unsigned g = 0; g < NS; ++g) issue(g);
   }
-  if (kWin && warp == 0) geometry(0);
-  cluster.sync();       // every CTA's barriers exist before the first remote store (and geo[0] is there)
+  for (int i = tid; i < 2 * 32 * 8; i += NT) (&red[0][0][0])[i] = 0.f;
+  cluster.sync();       // every CTA's barriers exist before the first remote store (and red is cleared)
+  const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
+  const float inv_denom = 1.0f / __ldg(p.denom);
   const float s2 = p.sigma * p.sigma;
 
   // thread geometry: vector column cv (4 pixels), rows r0 + RPS * it inside this CTA's part
   const int cv = tid & (kPairWV - 1), r0 = tid >> 6;
-  const float xs0 = fmaf(static_cast<float>(cv * 4), tow, bw);      // this thread's pixels: x = xs0 + c * tow
+  float xs[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xs[c] = fmaf(static_cast<float>(cv * 4 + c), tow, bw);
   const float y0 = fmaf(static_cast<float>(rank * C::ROWS + r0), toh, bh);
   constexpr float dyi = RPS * toh;
   const f2 l2e2 = pk1(kLog2e);
@@ -232,17 +252,16 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
   for (int k = 0; k < nk; ++k) {
     const int hm = cluster_id + k * n_clusters;
     const unsigned g0 = static_cast<unsigned>(NCH * k);       // chunk number of this heatmap's first chunk
-    const float xk = opaque(xs0);
-    const float xs[4] = {xk, xk + tow, xk + 2.f * tow, xk + 3.f * tow};
     float tx = 0.f, ty = 0.f;
     if (p.target) {
       const float2 tt = __ldg(reinterpret_cast<const float2*>(p.target) + hm);
       tx = tt.x; ty = tt.y;
     }
+    const float wgt = (p.mask ? __ldg(p.mask + hm) : 1.0f) * inv_denom;
 
     // ---------------------------------------------------------------- the part comes into REGISTERS (32 pixels per thread)
     // and its maximum is taken on the way; shared memory is read exactly once, so its buffers are free for the next loads
-    // as soon as every warp is through this sweep
+    // as soon as this sweep is over
     f2 ev[kPairIters][2];
     float mloc;
     if constexpr (ES == 4) {
@@ -270,22 +289,17 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
       }
       mloc = fmaxf(bf16lo(mb), bf16hi(mb));
     }
-    // Every WARP sums relative to ITS OWN maximum (no block-wide maximum, no block barrier); the 64 warps of the heatmap are
-    // merged afterwards like the blocks of an online softmax (S = sum_w S_w 2^(m_w - m)): ONE exchange carries everything.
-    mloc = warp_max_redux(mloc);       // (depends on every value the warp has read)
-    {
-      // The warp's data is in registers.  The LAST warp of the CTA to get here hands this heatmap's buffers to the next NCH
-      // chunks of the stream (nothing was written to them by the generic proxy, so no proxy fence); nobody waits.
-      unsigned last = 0;
-      if (lane == 0) {
-        unsigned old;
-        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&read_count)), "f"(mloc) : "memory");
-        last = (old + 1) % NW == 0 ? 1u : 0u;
-      }
-      last = __shfl_sync(kFull, last, 0);
-      if (last && lane < NCH) issue(g0 + NS + lane);
-    }
-    stamp(0);                                  // wait for the loads, shared memory -> registers, hand-over of the buffers
+    stamp(0);                                  // wait for the loads + shared memory -> registers
+    mloc = warp_max_redux(mloc);
+    if (lane == 0) redm[warp] = mloc;
+    __syncthreads();
+    stamp(1);                                  // block barrier (the slowest warp's loads)
+    // every thread has its data: this heatmap's buffers take the next NCH chunks of the stream (nothing was written to
+    // them by the generic proxy, so no proxy fence)
+    if (tid < kEarly) issue(g0 + NS + tid);
+    mloc = warp_max_redux(redm[lane & (NW - 1)]);
+    // Each part is summed relative to ITS OWN maximum; the parts are merged afterwards like the blocks of an online
+    // softmax (S = sum_r S_r 2^(m_r - m)), so ONE exchange per heatmap carries everything.
     const float m2h = mloc * kLog2e;
     const f2 nm2 = pk1(-m2h);
 
@@ -310,93 +324,136 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
       if constexpr (kVar) Syy = fmaf(rs * dy, dy, Syy);
       if constexpr (kMSE) tt2 = fma2(ev[it][0], ev[it][0], fma2(ev[it][1], ev[it][1], tt2));
     }
-    PairSums t;
-    {
-      float c0, c1, c2, c3;
-      upk(colE[0], c0, c1);
-      upk(colE[1], c2, c3);
-      float Sh = (c0 + c1) + (c2 + c3);
-      const float dx0 = xs[0] - pcx, dx1 = xs[1] - pcx, dx2 = xs[2] - pcx, dx3 = xs[3] - pcx;
-      float Sxh = fmaf(c0, dx0, fmaf(c1, dx1, fmaf(c2, dx2, c3 * dx3)));
-      float fourth = 0.f, fifth = 0.f;
-      if constexpr (kVar) {
-        fourth = fmaf(c0 * dx0, dx0, fmaf(c1 * dx1, dx1, fmaf(c2 * dx2, dx2, c3 * dx3 * dx3)));
-        fifth = warp_sum(Syy);
-      }
-      if constexpr (kMSE) fourth = hsum(tt2);
-      const float kq = warp_sum4_transposed(Sh, Sxh, Syc, fourth, lane);
-      Sh = __shfl_sync(kFull, kq, 0); Sxh = __shfl_sync(kFull, kq, 8);
-      const float Syh = __shfl_sync(kFull, kq, 16);
-      fourth = __shfl_sync(kFull, kq, 24);
-      stamp(1);                                // exponential sweep + the warp's sums
-      post(m2h, Sh, Sxh, Syh, fourth, fifth, 0.f);
+    stamp(2);                                  // issue of the next loads, maximum, exponential sweep
+    float c0, c1, c2, c3;
+    upk(colE[0], c0, c1);
+    upk(colE[1], c2, c3);
+    float Sh = (c0 + c1) + (c2 + c3);
+    const float dx0 = xs[0] - pcx, dx1 = xs[1] - pcx, dx2 = xs[2] - pcx, dx3 = xs[3] - pcx;
+    float Sxh = fmaf(c0, dx0, fmaf(c1, dx1, fmaf(c2, dx2, c3 * dx3)));
+    float Syh = Syc;
+    float axh = 0.f, ayh = 0.f;
+    float Tth = 0.f;
+    if constexpr (!kVar) {
+      Tth = hsum(tt2);
+      pair_block_sum4(Sh, Sxh, Syh, Tth, red[0], warp, lane);
+    } else {
+      axh = fmaf(c0 * dx0, dx0, fmaf(c1 * dx1, dx1, fmaf(c2 * dx2, dx2, c3 * dx3 * dx3)));
+      ayh = Syy;
+      pair_block_sum6(Sh, Sxh, Syh, axh, ayh, Syy, red[0], warp, lane);      // (the sixth value rides along unused)
     }
-    if (kWin && warp == 0) geometry(k + 1);    // ... for the next heatmap, while this one's message is on its way
+    stamp(3);                                  // block sum
+    post(m2h, Sh, Sxh, Syh, axh, ayh, Tth);
 
-    // ---------------------------------------------------------------- merge: the same arithmetic in every warp of the cluster
-    {
-      const float (*xm)[kPairSlotF] = collect();
-      float s0, s1, S, Sx, Sy, fourth = 0.f, fifth = 0.f;
-      {
-        const float4 q0 = *reinterpret_cast<const float4*>(&xm[lane][0]), q1 = *reinterpret_cast<const float4*>(&xm[lane + 32][0]);
-        t.m = warp_max_redux(fmaxf(q0.x, q1.x));
-        s0 = ex2(q0.x - t.m); s1 = ex2(q1.x - t.m);
-        // each warp summed relative to ITS OWN maximum: rescaled like the blocks of an online softmax; everything is about
-        // the same pivot, so the parts simply add
-        S = fmaf(q0.y, s0, q1.y * s1); Sx = fmaf(q0.z, s0, q1.z * s1); Sy = fmaf(q0.w, s0, q1.w * s1);
-      }
-      if constexpr (kVar) {
-        const float2 qa = *reinterpret_cast<const float2*>(&xm[lane][4]), qb = *reinterpret_cast<const float2*>(&xm[lane + 32][4]);
-        fourth = fmaf(qa.x, s0, qb.x * s1);
-        fifth = fmaf(qa.y, s0, qb.y * s1);
-      }
-      if constexpr (kMSE) fourth = fmaf(xm[lane][4], s0 * s0, xm[lane + 32][4] * s1 * s1);      // sum e^2 over all parts
-      const float kq = warp_sum4_transposed(S, Sx, Sy, fourth, lane);
-      t.S = __shfl_sync(kFull, kq, 0); t.Sx = __shfl_sync(kFull, kq, 8); t.Sy = __shfl_sync(kFull, kq, 16);
-      t.a = __shfl_sync(kFull, kq, 24);
-      t.b = 0.f;
-      if constexpr (kVar) t.b = warp_sum(fifth);
-      t.scme = ex2(m2h - t.m);
+    // ---------------------------------------------------------------- while the first message is on its way: the buffers whose
+    // bulk stores (previous heatmap) have been read take their next loads
+    if (kEarly < NCH && tid == 0 && k > 0) {
+      bulk_wait_read();
+      for (int c = kEarly; c < NCH; ++c) issue(g0 - NCH + NS + c);
     }
-    stamp(2);                                  // post, wait for the 64 warps, merge
-    const float m2 = t.m, S = t.S;
+    // JS / MSE: where the Gaussian window lies and its normalisation -- functions of the target alone
+    float ginv = 0.f, l2ginv = 0.f;
+    int wi_lo = 0, wi_hi = -1;
+    bool colin = false;
+    if constexpr (kWin) {
+      int j_lo, j_hi;
+      axis_window_fast(tx, kPairW, 0.5f * kPairW, tow, bw, p.r2_win, j_lo, j_hi);
+      axis_window_fast(ty, kPairH, 0.5f * kPairH, toh, bh, p.r2_win, wi_lo, wi_hi);
+      if (j_lo <= j_hi && wi_lo <= wi_hi) {
+        // Normalisation of the target Gaussian (src/dsnt/nn.py:168-180 divides by its sum over the image).  A window that
+        // the image border does not clip holds the whole sum to theta, and a sum of Gaussian samples at unit spacing is
+        // sigma sqrt(2 pi) (1 + 2 e^(-2 pi^2 sigma^2) cos(..) + ...): to 5.4e-9 relative from sigma = 1 px on (Poisson
+        // summation).  Clipped windows and narrower Gaussians are summed: every warp for itself, no block barrier.
+        const float spx = p.sigma * (0.5f * kPairW);       // sigma in pixels (H == W)
+        float sx = spx * 2.5066282746310002f, sy = sx;
+        if (!(spx >= 1.0f && j_lo > 0 && j_hi < kPairW - 1 && wi_lo > 0 && wi_hi < kPairH - 1)) {
+          sx = 0.f; sy = 0.f;
+          for (int j = j_lo + lane; j <= j_hi; j += 32) {
+            const float d = fmaf(static_cast<float>(j), tow, bw) - tx;
+            sx += ex2(p.k2 * d * d);
+          }
+          for (int i = wi_lo + lane; i <= wi_hi; i += 32) {
+            const float d = fmaf(static_cast<float>(i), toh, bh) - ty;
+            sy += ex2(p.k2 * d * d);
+          }
+          const float ks = warp_sum2_transposed(sx, sy, lane);
+          sx = __shfl_sync(kFull, ks, 0);
+          sy = __shfl_sync(kFull, ks, 16);
+        }
+        ginv = rcp(sx * sy + kEps);
+        l2ginv = lg2(ginv);
+        colin = cv >= (j_lo >> 2) && cv <= (j_hi >> 2);
+      } else {
+        wi_hi = wi_lo - 1;
+      }
+    }
+
+    stamp(4);                                  // post + window geometry
+
+    // ---------------------------------------------------------------- merge in rank order on every CTA: bit-identical totals
+    float sc[CS];
+    float m2, S, Sxc, Sycm, sax = 0.f, say = 0.f, Tt = 0.f;
+    {
+      const float (*xm)[8] = collect();
+      float4 lo[CS], hi[CS];
+#pragma unroll
+      for (int r = 0; r < CS; ++r) {
+        lo[r] = *reinterpret_cast<const float4*>(&xm[r][0]);
+        hi[r] = *reinterpret_cast<const float4*>(&xm[r][4]);
+      }
+      m2 = lo[0].x;
+#pragma unroll
+      for (int r = 1; r < CS; ++r) m2 = fmaxf(m2, lo[r].x);
+#pragma unroll
+      for (int r = 0; r < CS; ++r) sc[r] = ex2(lo[r].x - m2);
+      // each part was summed relative to ITS OWN maximum: rescaled like the blocks of an online softmax; everything is
+      // about the same pivot, so the parts simply add
+      S = lo[CS - 1].y * sc[CS - 1]; Sxc = lo[CS - 1].z * sc[CS - 1]; Sycm = lo[CS - 1].w * sc[CS - 1];
+      if (kVar) { sax = hi[CS - 1].x * sc[CS - 1]; say = hi[CS - 1].y * sc[CS - 1]; }
+      if (kMSE) Tt = hi[CS - 1].z * sc[CS - 1] * sc[CS - 1];
+#pragma unroll
+      for (int r = CS - 2; r >= 0; --r) {
+        S = fmaf(lo[r].y, sc[r], S); Sxc = fmaf(lo[r].z, sc[r], Sxc); Sycm = fmaf(lo[r].w, sc[r], Sycm);
+        if (kVar) { sax = fmaf(hi[r].x, sc[r], sax); say = fmaf(hi[r].y, sc[r], say); }
+        if (kMSE) Tt = fmaf(hi[r].z, sc[r] * sc[r], Tt);                       // sum e^2 over all parts
+      }
+    }
+    stamp(5);                                  // wait for the peers' message + merge
     const float invS = rcp(S);
-    const float mxc = t.Sx * invS, myc = t.Sy * invS;
+    const float mxc = Sxc * invS, myc = Sycm * invS;
     const float mux = pcx + mxc, muy = pcy + myc;
-    const float invSh = t.scme * invS;       // this warp's e (relative to its own maximum) -> probability
+    float scme = sc[0];
+#pragma unroll
+    for (int r = 1; r < CS; ++r) scme = rank == r ? sc[r] : scme;
+    const float invSh = scme * invS;       // this part's e (relative to its own maximum) -> probability
 
     float D = 0.f, creg = 0.f, vx = 0.f, vy = 0.f;
     if constexpr (kVar) {
-      vx = t.a * invS - mxc * mxc;
-      vy = t.b * invS - myc * myc;
+      vx = sax * invS - mxc * mxc;
+      vy = say * invS - myc * myc;
       // conditioning of the pivot form: (mu - c)^2 <= 16 var keeps the cancellation below 17 fp32 roundings (1e-6 relative)
       const bool ill = !(mxc * mxc <= 16.f * vx) || !(myc * myc <= 16.f * vy);
       if (ill) {
         // exact: second moments about the mean itself, from the registers (column sums are still there, the row sums are
-        // formed again) and one more exchange; all warps get here together (identical totals)
-        f2 ce[2] = {pk1(0.f), pk1(0.f)};
+        // formed again), one more block reduction and one more exchange; all CTAs get here together (identical totals)
+        const float ex0 = xs[0] - mux, ex1 = xs[1] - mux, ex2v = xs[2] - mux, ex3 = xs[3] - mux;
+        float axe = fmaf(c0 * ex0, ex0, fmaf(c1 * ex1, ex1, fmaf(c2 * ex2v, ex2v, c3 * ex3 * ex3)));
         float aye = 0.f;
         const float eyb = y0 - muy;
 #pragma unroll
         for (int it = 0; it < kPairIters; ++it) {
           const float d = eyb + static_cast<float>(it) * dyi;
-          ce[0] = add2(ce[0], ev[it][0]);
-          ce[1] = add2(ce[1], ev[it][1]);
           aye = fmaf(hsum(add2(ev[it][0], ev[it][1])) * d, d, aye);
         }
-        float c0, c1, c2, c3;
-        upk(ce[0], c0, c1);
-        upk(ce[1], c2, c3);
-        const float ex0 = xs[0] - mux, ex1 = xs[1] - mux, ex2v = xs[2] - mux, ex3 = xs[3] - mux;
-        float axe = fmaf(c0 * ex0, ex0, fmaf(c1 * ex1, ex1, fmaf(c2 * ex2v, ex2v, c3 * ex3 * ex3)));
-        const float kq = warp_sum2_transposed(axe, aye, lane);
-        post(m2h, __shfl_sync(kFull, kq, 0), __shfl_sync(kFull, kq, 16), 0.f, 0.f, 0.f, 0.f);
-        const float (*xe)[kPairSlotF] = collect();
-        const float4 lo0 = *reinterpret_cast<const float4*>(&xe[lane][0]), lo1 = *reinterpret_cast<const float4*>(&xe[lane + 32][0]);
-        const float s0 = ex2(lo0.x - m2), s1 = ex2(lo1.x - m2);
-        const float kr = warp_sum2_transposed(fmaf(lo0.y, s0, lo1.y * s1), fmaf(lo0.z, s0, lo1.z * s1), lane);
-        vx = __shfl_sync(kFull, kr, 0) * invS;
-        vy = __shfl_sync(kFull, kr, 16) * invS;
+        float z0 = 0.f, z1 = 0.f;
+        pair_block_sum4(axe, aye, z0, z1, red[1], warp, lane);
+        post(axe, aye, 0.f, 0.f, 0.f, 0.f, 0.f);
+        const float (*xe)[8] = collect();
+        float qx = xe[CS - 1][0] * sc[CS - 1], qy = xe[CS - 1][1] * sc[CS - 1];
+#pragma unroll
+        for (int r = CS - 2; r >= 0; --r) { qx = fmaf(xe[r][0], sc[r], qx); qy = fmaf(xe[r][1], sc[r], qy); }
+        vx = qx * invS;
+        vy = qy * invS;
       }
       const float ex = vx - s2, ey = vy - s2;
       D = ex * ex + ey * ey;
@@ -404,16 +461,6 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
     }
 
     // ---------------------------------------------------------------- JS / MSE: the Gaussian window, from the registers
-    float ginv = 0.f, l2ginv = 0.f;
-    int wi_lo = 1, wi_hi = 0;
-    bool colin = false;
-    if constexpr (kWin) {
-      const float4* gq = reinterpret_cast<const float4*>(&geo[k & 1][0]);      // (written before warp 0 posted this heatmap's message)
-      const float4 ga = gq[0], gb = gq[1];
-      ginv = ga.x; l2ginv = ga.y;
-      wi_lo = __float_as_int(gb.x); wi_hi = __float_as_int(gb.y);
-      colin = cv >= (__float_as_int(ga.z) >> 2) && cv <= (__float_as_int(ga.w) >> 2) && __float_as_int(ga.z) <= __float_as_int(ga.w);
-    }
     const int rowb = static_cast<int>(rank) * C::ROWS + r0;       // this thread's rows: rowb + RPS it
     const f2 k2p = pk1(p.k2), eps2 = pk1(kEps), half2 = pk1(0.5f), invSh2 = pk1(invSh);
     const f2 wdx[2] = {pk(xs[0] - tx, xs[1] - tx), pk(xs[2] - tx, xs[3] - tx)};
@@ -456,33 +503,28 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
           }
         }
       }
-      float a0 = hsum(qa), a1 = hsum(qb), a2 = hsum(qc);
-      if (__any_sync(kFull, colin)) {          // (most warps hold no window pixel: they post zeros at once)
-        const float kq = warp_sum4_transposed(a0, a1, a2, 0.f, lane);
-        a0 = __shfl_sync(kFull, kq, 0); a1 = __shfl_sync(kFull, kq, 8); a2 = __shfl_sync(kFull, kq, 16);
-      }
-      stamp(3);                                // window terms
+      float a0 = hsum(qa), a1 = hsum(qb), a2 = hsum(qc), a3 = 0.f;
+      stamp(6);                                // window terms (thread 0 holds none unless the window is at the left border)
+      pair_block_sum4(a0, a1, a2, a3, red[1], warp, lane);
+        stamp(7);                                // block sum of the window terms: waits for the threads that hold the window
       post(a0, a1, a2, 0.f, 0.f, 0.f, 0.f);
-      const float (*xw)[kPairSlotF] = collect();
-      const float4 lo0 = *reinterpret_cast<const float4*>(&xw[lane][0]), lo1 = *reinterpret_cast<const float4*>(&xw[lane + 32][0]);
-      const float kq = warp_sum4_transposed(lo0.x + lo1.x, lo0.y + lo1.y, lo0.z + lo1.z, 0.f, lane);
-      const float w0 = __shfl_sync(kFull, kq, 0), w1 = __shfl_sync(kFull, kq, 8), w2 = __shfl_sync(kFull, kq, 16);
+      const float (*xw)[8] = collect();
+      stamp(8);                                // second exchange
+      float w0 = xw[0][0], w1 = xw[0][1], w2 = xw[0][2];       // rank order on every CTA
+#pragma unroll
+      for (int r = 1; r < CS; ++r) { w0 += xw[r][0]; w1 += xw[r][1]; w2 += xw[r][2]; }
       if constexpr (kMSE) {
-        const float outside = fmaxf(fmaf(t.a * invS, invS, -w1), 0.f);
+        const float outside = fmaxf(fmaf(Tt * invS, invS, -w1), 0.f);
         D = outside + w0;
         creg = 2.f * (outside + w2);
       } else {
         creg = 0.5f * kLn2 * (1.0f + w0);
         D = fmaf(0.5f * kLn2, w1, creg);
       }
-      stamp(4);                                // second exchange
     }
 
     // ---------------------------------------------------------------- outputs + the scalars of the backward
     float dist = 0.f, a = 0.f, b = 0.f;
-    // (per-launch scalars are read where they are used: no register holds them through the sweeps)
-    const float gl = p.g_loss ? __ldg(p.g_loss) : 1.0f;
-    const float wgt = (p.mask ? __ldg(p.mask + hm) : 1.0f) * (1.0f / __ldg(p.denom));
     if (p.target) {
       const float dx = mux - tx, dy = muy - ty;
       const float d2 = dx * dx + dy * dy;
@@ -522,7 +564,8 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
       const float kyS = kVar ? rho * 2.f * (vy - s2) * invSh : 0.f;
       const f2 rpS = pk1(kMSE ? 2.f * rho * invSh * invSh : 0.f);
       const f2 kwS = pk1(kJS ? 0.5f * kLn2 * rho * invSh : (kMSE ? -2.f * rho * invSh : 0.f));   // JS: rho (ln2/2) d;  MSE: -2 rho G
-      char* dzb = static_cast<char*>(p.dz) + static_cast<long>(hm) * hm_bytes + static_cast<size_t>(rank) * C::PART_BYTES + tid * (4 * ES);
+      char* dzp = static_cast<char*>(p.dz) + static_cast<long>(hm) * hm_bytes + static_cast<size_t>(rank) * C::PART_BYTES;
+      char* dzb = dzp + tid * (4 * ES);
 #pragma unroll
       for (int it = 0; it < kPairIters; ++it) {
         f2 o[2];
@@ -544,21 +587,36 @@ __global__ void __launch_bounds__(PairCfg<CS, T>::NT, PairCfg<CS, T>::CTAS_PER_S
         }
         o[0] = mul2(ev[it][0], g0v);
         o[1] = mul2(ev[it][1], g1v);
+        // sweep steps < kEarly: straight to global memory; the others back into the chunk buffer they came from
+        char* dst = it < kEarly ? dzb + it * C::STEP_BYTES
+                                : reinterpret_cast<char*>(pair_smem) + ((g0 + it) % NS) * C::CHUNK + tid * (4 * ES);
         if constexpr (ES == 4) {
-          *reinterpret_cast<uint4*>(dzb + it * C::STEP_BYTES) = pack_pairs<float>(o);
+          *reinterpret_cast<uint4*>(dst) = pack_pairs<float>(o);
         } else {
           float l0, h0, l1, h1;
           upk(o[0], l0, h0);
           upk(o[1], l1, h1);
-          *reinterpret_cast<uint2*>(dzb + it * C::STEP_BYTES) = make_uint2(pack_bf16(l0, h0), pack_bf16(l1, h1));
+          *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(l0, h0), pack_bf16(l1, h1));
+        }
+      }
+      if constexpr (kEarly < NCH) {
+        fence_async_smem();           // the bulk stores (async proxy) read what this thread wrote
+        __syncthreads();
+        if (tid == 0) {
+          for (int c = kEarly; c < NCH; ++c)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dzp + c * C::CHUNK),
+                         "r"(buf_s + ((g0 + c) % NS) * C::CHUNK), "r"(C::CHUNK)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
-    stamp(5);                                  // outputs + backward sweep (stores issued)
+    stamp(9);                                  // outputs + backward sweep (stores issued)
 #ifdef DSNT_PAIR_TRACE
     if (tracing) g_pair_trace[15] += 1;
 #endif
   }
+  if (kEarly < NCH && tid == 0) bulk_wait_all();      // the last heatmap's bulk stores still read this CTA's shared memory
   cluster.sync();      // no CTA leaves while another may still store into its shared memory
 }
 
@@ -567,14 +625,15 @@ static int pair_enabled() {
   return v;
 }
 
-// cluster size: DSNT_TUNE_STEP_PAIR_CS = 2 | 4 overrides the measured default (profiles/r02_v6_kbench_cfg5.txt); read on every
-// call (a launch of 0.3 ms and more), so that the tests can take both forms in one process
+// cluster size: DSNT_TUNE_STEP_PAIR_CS = 2 | 4 overrides the measured default (profiles/r02_v6_pair_variants.txt: two CTAs
+// of 1024 threads, one per SM, beat four CTAs of 512 threads, two per SM, for every regulariser and both dtypes); read on
+// every call (a launch of 0.3 ms and more), so that the tests can take both forms in one process
 static int pair_cluster_size(int dtype, int reg) {
   const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_CS");
   const int forced = e ? std::atoi(e) : 0;
   if (forced == 2 || forced == 4) return forced;
   (void)dtype; (void)reg;
-  return 4;
+  return 2;
 }
 
 bool step_pair_supported(int dtype, int H, int W, int reg) {
@@ -630,9 +689,10 @@ static int launch_pair(const PairParams& p, cudaStream_t stream) {
     const double nh = t[15] ? static_cast<double>(t[15]) : 1.0;
     double tot = 0;
     for (int i = 0; i < 10; ++i) tot += t[i] / nh;
-    fprintf(stderr, "pair trace <reg %d, cluster %d, %d B> clocks per heatmap (CTA 0, %llu heatmaps, %.0f in all): load+lds %.0f | "
-            "exp sweep + warp sums %.0f | exchange + merge %.0f | window %.0f | exchange 2 %.0f | backward %.0f\n", REG, CS, C::ES, t[15], tot,
-            t[0] / nh, t[1] / nh, t[2] / nh, t[3] / nh, t[4] / nh, t[5] / nh);
+    fprintf(stderr, "pair trace <reg %d, cluster %d, %d B> clocks per heatmap (CTA 0, %llu heatmaps, %.0f in all): load+lds %.0f | barrier %.0f | "
+            "exp sweep %.0f | block sum %.0f | post+geometry %.0f | exchange+merge %.0f | window %.0f | window sum %.0f | exchange 2 %.0f | "
+            "backward %.0f\n", REG, CS, C::ES, t[15], tot, t[0] / nh, t[1] / nh, t[2] / nh, t[3] / nh, t[4] / nh, t[5] / nh, t[6] / nh,
+            t[7] / nh, t[8] / nh, t[9] / nh);
   }
   return check_launch("head_step_pair_kernel");
 }
@@ -660,11 +720,14 @@ int launch_step_pair(const void* z, int dtype, long n, int H, int W, const float
   p.k2 = g.k2; p.r2_win = g.r2_win;
   { const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_FLAGS"); p.tune = e ? std::atoi(e) : 0; }
   const bool f32 = dtype == DSNT_DTYPE_F32;
+  const int cs = pair_cluster_size(dtype, reg);
   int rc = 1;
-  if (pair_cluster_size(dtype, reg) == 4)
-    rc = f32 ? launch_pair_reg<4, float>(p, reg, stream) : launch_pair_reg<4, __nv_bfloat16>(p, reg, stream);
-  if (rc == 1)      // (also the fall-back of a device on which clusters of four do not fit)
-    rc = f32 ? launch_pair_reg<2, float>(p, reg, stream) : launch_pair_reg<2, __nv_bfloat16>(p, reg, stream);
+  for (int attempt = 0; attempt < 2 && rc == 1; ++attempt) {      // (a device on which the preferred clusters do not fit takes the other size)
+    if ((cs == 4) == (attempt == 0))
+      rc = f32 ? launch_pair_reg<4, float>(p, reg, stream) : launch_pair_reg<4, __nv_bfloat16>(p, reg, stream);
+    else
+      rc = f32 ? launch_pair_reg<2, float>(p, reg, stream) : launch_pair_reg<2, __nv_bfloat16>(p, reg, stream);
+  }
   return rc;
 }
 

@@ -331,7 +331,9 @@ def _head_with_target_grad(z, target, mask, reg, sigma, reg_coeff, preact, thres
 
 
 USE_PAIR_STEP = True          # 256x256 fp32 (not KL): the cluster-of-two-CTAs one-pass step (csrc/step_pair.cu),
-                              # 724 us against 970 us of forward + backward at BASELINE config 5 (variance regulariser)
+                              # 666 us against 970 us of forward + backward at BASELINE config 5 (variance regulariser)
+USE_PAIR_STEP_BF16 = False    # 256x256 bf16: the same kernel serves it at 4 B/px but is bound by the SM (MUFU + exchange
+                              # latency per heatmap), 594 us (variance) against 510 us of the two-kernel path at 6 B/px
 # Sharded batch: take the single-launch step with both exchanges inside the kernel (dsnt_head_step_fused_peer).  The count
 # is published by the last CTA to arrive and picked up by every warp only before its first backward, so the exchange --
 # and the wait for a rank that started later -- hides behind the first loads and the first forward.  DSNT_FUSED_PEER_STEP=0
@@ -358,7 +360,7 @@ def takes_one_pass(z, reg, sigma, sharded):
     single process only -- the size of the batch."""
     h, w = int(z.shape[-2]), int(z.shape[-1])
     key = (z.dtype, h, w, reg, sigma, sharded, z.numel() * z.element_size() >= STEP_MIN_BYTES, STEP_MIN_BYTES,
-           USE_PAIR_STEP)
+           USE_PAIR_STEP, USE_PAIR_STEP_BF16)
     hit = _one_pass_cache.get(key)
     if hit is None:
         hit = step_supported(z, reg) and _step_pays(z, h, w, _lib.REG_IDS[reg], sigma, group=None, sharded=sharded)
@@ -372,11 +374,12 @@ _one_pass_cache = {}
 def step_supported(z, reg=None):
     """True when `dsnt_head_step` (one pass over the logits) can take heatmaps of this dtype and SHAPE (the batch size plays
     no part, so that the ranks of a sharded batch agree): at least four of them fit in shared memory, or -- for larger
-    ones, given the regulariser -- the cluster-of-two-CTAs kernel serves the case (256x256 fp32; not KL)."""
+    ones, given the regulariser -- the cluster-of-two-CTAs kernel serves the case (256x256 fp32; not KL; bf16 only with
+    `USE_PAIR_STEP_BF16`, where the two-kernel path is the faster one)."""
     if z.dtype not in (torch.float32, torch.bfloat16) or z.dim() < 2 or z.shape[-1] == 0 or z.shape[-2] == 0:
         return False
-    if reg is not None and USE_PAIR_STEP and _lib.LIB.dsnt_head_step_pair_supported(
-            _lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1]), _lib.REG_IDS[reg]):
+    if reg is not None and USE_PAIR_STEP and (z.dtype == torch.float32 or USE_PAIR_STEP_BF16) and \
+            _lib.LIB.dsnt_head_step_pair_supported(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1]), _lib.REG_IDS[reg]):
         return True
     return bool(_lib.LIB.dsnt_head_step_supported(_lib.dtype_id(z), int(z.shape[-2]), int(z.shape[-1])))
 

@@ -150,7 +150,9 @@ def test_step_support_queries_are_host_logic(libpath):
     assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['var']) == 1
     assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['js']) == 1
     assert lib.dsnt_head_step_supported_reg(f32, 256, 256, reg['kl']) == 0
-    assert lib.dsnt_head_step_supported_reg(bf16, 256, 256, reg['js']) == 0                      # two-kernel path
+    assert lib.dsnt_head_step_supported_reg(bf16, 256, 256, reg['js']) == 1                      # served (the dispatcher still prefers
+                                                                                                 # the two-kernel path: head.USE_PAIR_STEP_BF16)
+    assert lib.dsnt_head_step_supported_reg(bf16, 256, 256, reg['kl']) == 0                      # two-kernel path
     # exchange buffer of the peer reductions: two parities x 16 ranks x float4
     assert lib.dsnt_peer_exchange_bytes() == 2 * 16 * 4 * 8     # two parities x 16 ranks x 4 words of 8 bytes
     assert lib.dsnt_finish_workspace_bytes() >= (256 * 4 + 4 + 256) * 4

@@ -33,9 +33,11 @@ def always_take_the_step_kernels(dp):
     from dsnt_pose2d_b200 import head
     old, head.STEP_MIN_BYTES = head.STEP_MIN_BYTES, 0
     old_pair, head.USE_PAIR_STEP = head.USE_PAIR_STEP, True
+    old_bf16, head.USE_PAIR_STEP_BF16 = head.USE_PAIR_STEP_BF16, True       # (off by default: slower than the two-kernel path)
     yield
     head.STEP_MIN_BYTES = old
     head.USE_PAIR_STEP = old_pair
+    head.USE_PAIR_STEP_BF16 = old_bf16
 
 
 @pytest.fixture(params=[2, 4])
@@ -443,6 +445,20 @@ def test_step_for_heatmaps_too_large_for_one_ctas_shared_memory(dp, tp, shape, d
     scale = mask[:n_chk].sum().clamp(min=1).item() / mask.sum().clamp(min=1).item()
     assert float(np.abs(got['coords'][:n_chk] - ref['coords'].numpy()).max()) < TOL
     assert rel_l2(got['dz'][:n_chk], ref['dz'].numpy() * scale) < (4e-3 if dtype == 'bf16' else TOL)
+
+
+def test_bf16_at_256_takes_the_two_kernel_path_by_default(dp):
+    """256x256 bf16: csrc/step_pair.cu serves it (4 B/px) but is bound by the SM and slower than forward + backward at 6 B/px
+    (profiles/r02_v6_kbench_cfg5.txt), so the dispatcher keeps the two-kernel path unless head.USE_PAIR_STEP_BF16 is set."""
+    from dsnt_pose2d_b200 import _lib, head
+    z = torch.randn(2, 4, 256, 256, device=DEV).to(torch.bfloat16)
+    assert head.step_supported(z, 'var')
+    head.USE_PAIR_STEP_BF16 = False
+    try:
+        assert not head.step_supported(z, 'var') and head.step_supported(z.float(), 'var')
+        assert _lib.LIB.dsnt_head_step_pair_supported(1, 256, 256, _lib.REG_IDS['var']) == 1      # the kernel itself is there
+    finally:
+        head.USE_PAIR_STEP_BF16 = True
 
 
 @pytest.mark.parametrize('n,reg,with_mask', [(1, 'var', True), (3, 'none', False), (75, 'var', False), (149, 'none', True),
