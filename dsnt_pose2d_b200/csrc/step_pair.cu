@@ -63,20 +63,27 @@ struct PairCfg {
   static constexpr int CHUNK = PART_BYTES / NCH;
   // ring slots: fp32 CS=2: 13 x 16 KiB = 208 KiB (one CTA per SM); fp32 CS=4: 13 x 8 KiB = 104 KiB (two per SM);
   // bf16 CS=2: 24 x 8 KiB = 192 KiB; bf16 CS=4: 24 x 4 KiB = 96 KiB (two per SM)
+#ifdef DSNT_PAIR_NS_F32        // (measurements)
+  static constexpr int NS = ES == 4 ? (CS == 2 ? DSNT_PAIR_NS_F32 : 13) : 24;
+#else
   static constexpr int NS = ES == 4 ? 13 : 24;
+#endif
   // The gradient of the sweep steps >= STAGE0 goes back through the chunk buffers it came in (STS + one bulk store per
   // chunk, asynchronous), that of the first STAGE0 steps straight from the registers (STG): the SM's path to L2 takes
   // 32 B/clk (tools/probe/store_probe.cu: 128 KiB = 4000 clocks, whoever sends them), and an STG waits for it.  A staged
   // buffer is handed to the next load only when its bulk store has read it, an unstaged one right after the sweep:
   // fp32 keeps three early buffers so that the last chunks of the next heatmap are on their way in time.
 #ifdef DSNT_PAIR_STAGE0      // (measurements: -DDSNT_PAIR_STAGE0=8 is "no staging")
-  static constexpr int STAGE0 = ES == 4 ? DSNT_PAIR_STAGE0 : 0;
+  static constexpr int STAGE0 = ES == 4 ? (CS == 2 ? DSNT_PAIR_STAGE0 : 3) : 0;
 #else
   static constexpr int STAGE0 = ES == 4 ? 3 : 0;
 #endif
   static constexpr int SMEM = NS * CHUNK;
   static constexpr int CTAS_PER_SM = CS == 2 ? 1 : 2;
   static_assert(ROWS % RPS == 0 && ROWS / RPS == kPairIters && kPairIters % NCH == 0 && NS > NCH, "geometry");
+  // chunk c of heatmap k+1 lives in the buffer of chunk c - (NS - NCH) of heatmap k: if that one were staged, it would be
+  // released a heatmap later, after the sweep that waits for the load -- a dead-lock by construction
+  static_assert(STAGE0 == NCH || NS >= 2 * NCH || STAGE0 > 2 * NCH - 1 - NS, "a staged buffer the next sweep waits for");
 };
 
 struct PairParams {

@@ -98,7 +98,11 @@ def test_step_is_taken_only_where_supported(dp):
     assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV), 'kl')    # KL at 256x256: two-kernel path
     assert _lib_pair(256, 256, 'var') and _lib_pair(256, 256, 'none') and _lib_pair(256, 256, 'js') and _lib_pair(256, 256, 'mse')
     assert not _lib_pair(256, 256, 'kl') and not _lib_pair(128, 128, 'var')
-    assert not head.step_supported(torch.empty(1, 1, 256, 256, device=DEV, dtype=torch.bfloat16), 'js')   # two-kernel path
+    bf = torch.empty(1, 1, 256, 256, device=DEV, dtype=torch.bfloat16)
+    assert head.step_supported(bf, 'js')                # (these tests switch head.USE_PAIR_STEP_BF16 on, see the fixture)
+    head.USE_PAIR_STEP_BF16 = False
+    assert not head.step_supported(bf, 'js')            # the default: two-kernel path
+    head.USE_PAIR_STEP_BF16 = True
     assert not head.step_supported(torch.empty(1, 1, 7, 7, device=DEV))         # no 16-byte vectors
 
 

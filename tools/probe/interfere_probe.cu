@@ -2,7 +2,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -o tools/probe/interfere_probe tools/probe/interfere_probe.cu
 // 2 CTAs of 512 threads per SM.  CTA A (blockIdx < 148): mode 0 idle, 1 = STG.128 storm from registers, 2 = STS + TMA bulk
 // stores.  CTA B (blockIdx >= 148) measures the clocks of fixed pieces of work: (a) 64 KiB of LDS.128, (b) 32 MUFU per
-// thread, (c) a bulk load of 8 KiB from global + wait, (d) st.async to itself + mbarrier wait, (e) 64 KiB of STG.128.
+// thread, (c) a bulk load of 8 KiB from global + wait, (d) 64 KiB of STG.128.
 #include <cstdio>
 #include <cstdint>
 #include <vector>
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(512, 2) probe(float4* out, const float4* in, l
   }
   // ---- B: the measured neighbour
   const int b = blockIdx.x - 148;
-  long long t_lds = 0, t_mufu = 0, t_tma = 0, t_async = 0, t_stg = 0;
+  long long t_lds = 0, t_mufu = 0, t_tma = 0, t_stg = 0;
   float acc = 0.f;
   for (int it = 0; it < 8; ++it) s[it * 512 + tid] = make_float4(tid, it, 1.f, 2.f);
   __syncthreads();
@@ -85,9 +85,7 @@ __global__ void __launch_bounds__(512, 2) probe(float4* out, const float4* in, l
     __syncthreads();
     long long t3 = clock64();
     t_tma += t3 - t2;
-    __syncthreads();
-    long long t4 = clock64();
-    t_async += t4 - t3;
+    long long t4 = t3;
 #pragma unroll
     for (int it = 0; it < 8; ++it) dst[(r & 63) * 4096 + it * 512 + tid] = make_float4(acc, 1.f, 2.f, 3.f);
     __syncthreads();
@@ -96,7 +94,7 @@ __global__ void __launch_bounds__(512, 2) probe(float4* out, const float4* in, l
   }
   if (tid == 0) {
     long long* o = res + 5 * b;
-    o[0] = t_lds / reps; o[1] = t_mufu / reps; o[2] = t_tma / reps; o[3] = t_async / reps; o[4] = t_stg / reps;
+    o[0] = t_lds / reps; o[1] = t_mufu / reps; o[2] = t_tma / reps; o[3] = 0; o[4] = t_stg / reps;
     if (acc == 12345.678f) o[0] = 0;
     if (b == 0) *stop = 1;
   }
@@ -127,7 +125,7 @@ int main() {
     long long m[5];
     for (int k = 0; k < 5; ++k) { std::vector<long long> v; for (int b = 0; b < 148; ++b) v.push_back(h[5 * b + k]); std::sort(v.begin(), v.end()); m[k] = v[74]; }
     printf("neighbour %-28s (%3d of 148 B-CTAs share an SM with exactly one A): 64 KiB LDS.128 %5lld clk | 32 MUFU/thread %5lld | 8 KiB bulk load %5lld | "
-           "st.async + wait %5lld | 64 KiB STG.128 %5lld  [%s]\n", names[mode], paired, m[0], m[1], m[2], m[3], m[4], cudaGetErrorString(e));
+           "64 KiB STG.128 %5lld  [%s]\n", names[mode], paired, m[0], m[1], m[2], m[4], cudaGetErrorString(e));
   }
   return 0;
 }

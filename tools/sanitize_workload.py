@@ -5,8 +5,8 @@ heatmaps -- the sanitizer instruments every memory access, so sizes are what fin
     compute-sanitizer --tool racecheck python tools/sanitize_workload.py [case ...]
 
 Cases: step (64x64 single-launch one-pass, fp32 + bf16, every regulariser), stacked (hourglass single launch),
-generic (one-pass kernels for 28x28 / KL: dsnt_mask_count + dsnt_head_step + dsnt_finish_loss), pair (256x256 fp32 on a
-cluster of two CTAs: DSMEM exchange), two (forward + streaming backward), level1 (nn.* operators), peer (2 ranks under
+generic (one-pass kernels for 28x28 / KL: dsnt_mask_count + dsnt_head_step + dsnt_finish_loss), pair (256x256 fp32 / bf16 on
+clusters of two and four CTAs: DSMEM exchange, staged bulk stores), two (forward + streaming backward), level1 (nn.* operators), peer (2 ranks under
 torchrun: the exchanges over peer memory)."""
 
 import os
@@ -63,9 +63,17 @@ def case_generic():
 
 
 def case_pair():
-    for reg in ('var', 'none'):
-        z, t, m = inputs(2, 3, 256, 256)
-        print('pair', reg, run(z, t, m, reg, True))
+    # two clusters only, so that each walks three heatmaps: the staged buffers are handed on (bulk-store read -> next load)
+    os.environ['DSNT_TUNE_STEP_PAIR_CLUSTERS'] = '2'
+    _head.STEP_MIN_BYTES = 0
+    _head.USE_PAIR_STEP_BF16 = True
+    for cs in ('2', '4'):
+        os.environ['DSNT_TUNE_STEP_PAIR_CS'] = cs
+        for dtype in (torch.float32, torch.bfloat16):
+            for reg in ('var', 'none', 'js', 'mse'):
+                z, t, m = inputs(2, 3, 256, 256, dtype)
+                print('pair', cs, dtype, reg, run(z, t, m, reg, True))
+    del os.environ['DSNT_TUNE_STEP_PAIR_CS']
 
 
 def case_two():
