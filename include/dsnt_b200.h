@@ -125,11 +125,13 @@ DSNT_API int dsnt_head_bwd(const void* z, int dtype, int input_is_logits, long n
  * dsnt_mask_count: out[2] = sum mask (n when mask is NULL), out[3] = max(out[2], 1); workspace as dsnt_finish_loss.
  */
 DSNT_API int dsnt_head_step_supported(int dtype, int H, int W);
-/* ... for a given regulariser: the shared-memory ring above, or the cluster-of-two-CTAs kernel below (256x256 fp32). */
+/* ... for a given regulariser: the shared-memory ring above, or the cluster kernel below (256x256). */
 DSNT_API int dsnt_head_step_supported_reg(int dtype, int H, int W, int reg);
-/* 256x256 fp32 (BASELINE config 5) with no, the variance, the JS or the MSE regulariser is served by a cluster of two CTAs,
- * each holding half the heatmap in shared memory, partial results exchanged through distributed shared memory
- * (csrc/step_pair.cu); KL at this size keeps the two-kernel path. */
+/* 256x256 (BASELINE config 5) with no, the variance, the JS or the MSE regulariser is served by a cluster of two CTAs
+ * (four where two 1024-thread CTAs cannot be co-scheduled), each holding a part of the heatmap in registers, partial results
+ * exchanged through distributed shared memory, most of the gradient written back by bulk stores (csrc/step_pair.cu); KL
+ * at this size keeps the two-kernel path.  fp32 runs at the HBM roofline; bf16 is served too but bound by the SM and slower
+ * than dsnt_head_fwd + dsnt_head_bwd, so the Python dispatcher does not take it by default. */
 DSNT_API int dsnt_head_step_pair_supported(int dtype, int H, int W, int reg);
 DSNT_API int dsnt_head_step(const void* z, int dtype, long n, int H, int W, const float* target, const float* mask,
                             const float* denom, const float* g_loss, float reg_coeff, int reg, float sigma, int flags,
