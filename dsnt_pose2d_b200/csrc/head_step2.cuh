@@ -572,16 +572,22 @@ __global__ void __launch_bounds__(NWMAX * 32, 1) head_step2_kernel(const HeadSte
     if constexpr (kWin) {
       f2 qa = pk1(0.f), qb = pk1(0.f), qc = pk1(0.f);
       if (nwv > 0) {
-        float sx = 0.f, sy = 0.f;
-        for (int j = j_lo + lane; j <= j_hi; j += 32) {
-          const float d = fmaf(static_cast<float>(j), tow, bw) - tx;
-          sx += ex2(g.k2 * d * d);
-        }
-        for (int i = i_lo + lane; i <= i_hi; i += 32) {
-          const float d = fmaf(static_cast<float>(i), toh, bh) - ty;
-          sy += ex2(g.k2 * d * d);
-        }
-        {
+        // Normalisation of the target Gaussian (src/dsnt/nn.py:168-180 divides by its sum over the image).  A window the image
+        // border does not clip holds the whole sum to theta, and unit-spaced samples of a Gaussian sum to sigma sqrt(2 pi)
+        // within 5.4e-9 relative from sigma = 1 px on (Poisson summation); clipped windows and narrower Gaussians are summed.
+        // (fp32 builds only: in the bf16 JS build, at 96 registers, the extra branch costs spills -- 189 -> 217 us measured.)
+        const float spx = p.sigma * (0.5f * W), spy = p.sigma * (0.5f * H);
+        float sx = spx * 2.5066282746310002f, sy = spy * 2.5066282746310002f;
+        if (sizeof(T) != 4 || !(spx >= 1.0f && spy >= 1.0f && j_lo > 0 && j_hi < W - 1 && i_lo > 0 && i_hi < H - 1)) {
+          sx = 0.f; sy = 0.f;
+          for (int j = j_lo + lane; j <= j_hi; j += 32) {
+            const float d = fmaf(static_cast<float>(j), tow, bw) - tx;
+            sx += ex2(g.k2 * d * d);
+          }
+          for (int i = i_lo + lane; i <= i_hi; i += 32) {
+            const float d = fmaf(static_cast<float>(i), toh, bh) - ty;
+            sy += ex2(g.k2 * d * d);
+          }
           const float k = warp_sum2_transposed(sx, sy, lane);
           sx = __shfl_sync(kFull, k, 0);
           sy = __shfl_sync(kFull, k, 16);
