@@ -366,6 +366,36 @@ def test_pair_kernel_gaussian_window_at_256(dp, reg, kind, cluster_size, monkeyp
     assert e_loss < TOL and e_reg < TOL and e_dz < TOL
 
 
+@pytest.mark.parametrize('offset_px', [0.0, 0.3, 1.0, 4.0])
+@pytest.mark.parametrize('cluster_size', [2, 4])
+def test_pair_mse_where_the_prediction_sits_on_the_target(dp, offset_px, cluster_size, monkeypatch):
+    """csrc/step_pair.cu, MSE on heatmaps that ARE the target Gaussian shifted by 0 ... 4 px: D from 0 to 2 sum G^2, against
+    the fp64 oracle.  The window's (P - G)^2 is evaluated pixel by pixel from the registers, so D keeps its relative accuracy
+    down to zero.  (A variant that carries sum e G and sum G^2 on the first exchange and needs no second message -- D as a
+    polynomial in 1/S, with this evaluation as the fallback where it cancels -- passed this test in both branches and was
+    30 us SLOWER at config 5: profiles/r02_v6_pair_variants.txt, run H.)  At a zero offset the direction of the Euclidean
+    gradient is undefined -- the reference back-propagates NaN there -- so only the regulariser is compared."""
+    from oracle import torch_port as tp
+    monkeypatch.setenv('DSNT_TUNE_STEP_PAIR_CS', str(cluster_size))
+    gen = torch.Generator().manual_seed(103)
+    n, h, w = 3, 256, 256
+    target = torch.rand(n, 1, 2, generator=gen) * 1.2 - 0.6
+    target[0, 0] = torch.tensor([0.3, 0.001])                 # ... one of them astride the halves
+    centre = target + offset_px * (2.0 / w) * torch.tensor([0.6, 0.8])
+    z = (tp.make_gauss(centre, w, h, 2.0 * 1.0 / w) + 1e-30).log().clamp(min=-60.0)
+    zz = z.to(DEV).requires_grad_(True)
+    out = dp.dsnt_head(zz, target.to(DEV), None, reg='mse', hm_sigma=1.0, reg_coeff=50.0, one_pass=True)
+    out.loss.backward()
+    ref = tp.head_loss_and_grad(z, target, None, 'mse', 1.0, 50.0, dtype=torch.float64)
+    e_reg = abs(out.reg.item() - ref['reg'].item())
+    e_dz = rel_l2(zz.grad.cpu().double().numpy(), ref['dz'].numpy())
+    print('offset %.2f px: reg %.3e abs.err %.1e dz %.1e' % (offset_px, ref['reg'].item(), e_reg, e_dz))
+    assert (out.coords.detach().cpu().double() - ref['coords']).abs().max().item() < TOL
+    assert e_reg < TOL * ref['reg'].item() + 2e-8            # (the fp32 logits of an exact match still leave D ~ 1e-9)
+    if offset_px > 0:
+        assert e_dz < TOL
+
+
 def test_reordered_visible_devices():
     """CUDA_VISIBLE_DEVICES reordered: device 0 of the process is another physical GPU; the per-device launch
     caches and the cooperative launch must not care.  Runs the smoke check in a subprocess."""
