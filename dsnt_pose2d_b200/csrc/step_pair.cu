@@ -725,7 +725,10 @@ int launch_step_pair(const void* z, int dtype, long n, int H, int W, const float
   p.reg_coeff = reg_coeff;
   const Geom g = make_geom(H, W, 4, 32, sigma > 0.f ? sigma : 1.f, reg);
   p.k2 = g.k2; p.r2_win = g.r2_win;
+  p.tune = 0;
+#ifdef DSNT_PAIR_TRACE
   { const char* e = std::getenv("DSNT_TUNE_STEP_PAIR_FLAGS"); p.tune = e ? std::atoi(e) : 0; }
+#endif
   const bool f32 = dtype == DSNT_DTYPE_F32;
   const int cs = pair_cluster_size(dtype, reg);
   int rc = 1;
